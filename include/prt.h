@@ -1,0 +1,179 @@
+/*
+ * prt.h -- C ABI of libprt.so, the B200 (sm_100a) ray-fan / eigenray engine.
+ *
+ * This is the drop-in boundary for pygenray's hot path.  pygenray is pure Python and has no FFI
+ * of its own; the seam these entry points replace is the ARRAY-LEVEL interface of
+ * /root/reference/src/pygenray/launch_rays.py:
+ *
+ *   _unpack_envi(environment, flatearth)                 :717-742  -> prt_env_create
+ *   _shoot_ray_array(y0, ..., cin, cpin, rin, zin, depths, depth_ranges, bottom_angles,
+ *                    rtol, terminate_backwards, debug)   :325-484  \
+ *   _interpolate_ray(sols, range_save)                   :745-784   > prt_shoot_fan (batched over
+ *   Pool.imap(_shoot_single_ray_process, y0s)            :157-164  /   launch angles)
+ *   find_eigenrays / _find_single_eigenray               eigenrays.py:62-120, 206-268
+ *                                                                  -> prt_find_brackets,
+ *                                                                     prt_refine_brackets
+ *
+ * Conventions
+ *   - plain C types only; every array is a raw pointer + explicit sizes; FP64 everywhere.
+ *   - `*_dev` pointers are DEVICE pointers owned by the caller (e.g. torch CUDA tensors);
+ *     calls taking a `stream` are asynchronous on that CUDA stream (cudaStream_t passed as void*;
+ *     NULL = the legacy default stream).  The library allocates nothing persistent except the
+ *     environment handle.
+ *   - return value: PRT_SUCCESS or a PRT_ERR_* code for argument / CUDA errors only
+ *     (prt_last_error() has the text).  Per-ray failures are DATA: the `status` output holds a
+ *     PRT_RAY_* code per launch angle, mirroring the reference's "dropped ray -> None"
+ *     convention (launch_rays.py:305-306, 430, 448, 456, 477).
+ *   - angles passed to the library are INTERNAL launch angles in degrees (positive = down-going,
+ *     i.e. y0[2] = sin(radians(angle)) / c); the sign flips of shoot_rays / shoot_ray
+ *     (launch_rays.py:64-67, 251) belong to the host layer.
+ *   - ODE state sign convention: z positive downwards, exactly as inside _shoot_ray_array.
+ */
+#ifndef PRT_H
+#define PRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRT_ABI_VERSION 1
+
+/* return codes */
+#define PRT_SUCCESS 0
+#define PRT_ERR_ARG 1
+#define PRT_ERR_CUDA 2
+#define PRT_ERR_NO_DEVICE 3
+
+/* per-ray status */
+#define PRT_RAY_OK 0             /* reached receiver_range */
+#define PRT_RAY_STEP_TOO_SMALL 1 /* solve_ivp status -1 (launch_rays.py:427-430) */
+#define PRT_RAY_VERTICAL 2       /* vertical_ray event (launch_rays.py:443-448) */
+#define PRT_RAY_BBOX 3           /* ray_bounding_box_event (launch_rays.py:451-456) */
+#define PRT_RAY_BACKWARDS 4      /* |theta_bounce| > 90 with terminate_backwards (launch_rays.py:474-477) */
+#define PRT_RAY_BOTTOM_OOB 5     /* bounce outside the bathymetry grid: interp1d raises ValueError (:469) */
+#define PRT_RAY_BRENTQ_SIGN 6    /* scipy brentq ValueError inside solve_ivp */
+#define PRT_RAY_BRENTQ_ITER 7    /* scipy brentq RuntimeError inside solve_ivp */
+#define PRT_RAY_MAX_BOUNCES 9    /* safety cap `max_bounces` hit (no reference equivalent) */
+
+/* per-ray work counters, out_counters[k][ray] */
+#define PRT_CNT_NFEV 0     /* right-hand-side evaluations (== sum of sol.nfev) */
+#define PRT_CNT_ATTEMPTS 1 /* RK45 step attempts */
+#define PRT_CNT_ACCEPTED 2 /* accepted steps */
+#define PRT_CNT_SEGMENTS 3 /* solve_ivp segments (1 + bounces) */
+#define PRT_CNT_BISECT 4   /* event-function evaluations inside root searches */
+#define PRT_CNT_DENSE 5    /* dense-output constructions */
+#define PRT_CNT_N 6
+
+/* eigenray bracket status */
+#define PRT_EIG_CONVERGED 0 /* |z_end + receiver_depth| < ztol */
+#define PRT_EIG_RAY_DROPPED 1 /* a trial ray was dropped (eigenrays.py:241-245) */
+#define PRT_EIG_MAX_ITER 2  /* iteration limit (eigenrays.py:265-266) */
+
+typedef struct prt_env prt_env_t;
+
+int prt_abi_version(void);
+const char *prt_last_error(void);
+
+/* number of visible CUDA devices (0 if none / no driver) */
+int prt_device_count(void);
+
+/*
+ * Stage one environment on `device`.  Inputs are HOST arrays exactly as returned by the
+ * reference's _unpack_envi (launch_rays.py:717-742), plus the not-a-knot cubic spline of
+ * bottom_angles over depth_ranges (the interp1d(kind="cubic") that _shoot_ray_array rebuilds per
+ * ray, launch_rays.py:397-399) as piecewise-polynomial coefficients:
+ *   cin, cpin     [n_r][n_z]   sound speed and d c / d z, C order [range][depth]
+ *   rin [n_r], zin [n_z]       grid coordinates (ascending)
+ *   depth_ranges, depths [n_b] bathymetry
+ *   ba_x [n_ba]                spline breakpoints; ba_c [4][n_ba-1] coefficients, highest power
+ *                              first, local variable (x - ba_x[i])
+ */
+int prt_env_create(int device, int32_t n_r, int32_t n_z, const double *rin, const double *zin,
+                   const double *cin, const double *cpin, int32_t n_b, const double *depth_ranges,
+                   const double *depths, int32_t n_ba, const double *ba_x, const double *ba_c,
+                   prt_env_t **out);
+int prt_env_destroy(prt_env_t *env);
+/* bytes of device memory held by the environment */
+int64_t prt_env_device_bytes(const prt_env_t *env);
+
+/*
+ * Shoot a fan of n_rays launch angles from (source_range, source_depth) to receiver_range
+ * (source_range < receiver_range; backwards shots are mirrored by the caller as the reference
+ * does, launch_rays.py:124-131).
+ *
+ *   angles_dev [n_rays]        internal launch angles [deg], or NULL if y0_dev is given
+ *   y0_dev     [n_rays][3]     explicit initial states [T, z, p] (as _shoot_ray_array's y0), or NULL
+ *   range_save_dev [n_save]    the save grid np.linspace(source_range, receiver_range, n_save);
+ *                              NULL / n_save = 0 -> arrival table only
+ *   out_traj_dev [3][n_rays][n_save]  T, z, p on the save grid (_interpolate_ray); NULL if n_save = 0
+ *   out_final_dev [3][n_rays]  exact final state (sols[-1].y[:, -1]); NaN for dropped rays
+ *   out_n_bottom_dev, out_n_surface_dev, out_status_dev [n_rays] int32
+ *   out_counters_dev [PRT_CNT_N][n_rays] uint32, or NULL
+ */
+int prt_shoot_fan(const prt_env_t *env, int64_t n_rays, const double *angles_dev, const double *y0_dev,
+                  double source_depth, double source_range, double receiver_range, double rtol, double atol,
+                  int32_t terminate_backwards, int32_t n_save, const double *range_save_dev,
+                  double *out_traj_dev, double *out_final_dev, int32_t *out_n_bottom_dev,
+                  int32_t *out_n_surface_dev, int32_t *out_status_dev, uint32_t *out_counters_dev,
+                  int32_t max_bounces, void *stream);
+
+/*
+ * Same, HOST pointers in and out: stages the launch angles, runs the fan and copies the results
+ * back (synchronous).  This is the call a non-Python host (C, Fortran, Julia via ccall) binds.
+ */
+int prt_shoot_fan_host(const prt_env_t *env, int64_t n_rays, const double *angles, const double *y0,
+                       double source_depth, double source_range, double receiver_range, double rtol,
+                       double atol, int32_t terminate_backwards, int32_t n_save, const double *range_save,
+                       double *out_traj, double *out_final, int32_t *out_n_bottom, int32_t *out_n_surface,
+                       int32_t *out_status, uint32_t *out_counters, int32_t max_bounces);
+
+/*
+ * Eigenray bracketing (eigenrays.py:62-79): for every receiver depth, find adjacent surviving fan
+ * rays whose final depths straddle it (sign change of zs[:, -1] + receiver_depth, zs negative-z).
+ *   z_end_dev [n_rays]   final depths of the surviving fan rays in STORED convention (= -z)
+ *   thetas_dev [n_rays]  their launch angles in the fan's stored (user) convention
+ *   receiver_depths_dev [n_rcv]
+ * Two passes: prt_count_brackets fills counts_dev[n_rcv]; after an exclusive scan into
+ * offsets_dev[n_rcv] (caller), prt_fill_brackets writes, in (receiver, ray) order,
+ *   br_z1/z2/th1/th2/rd [n_brackets] and br_rcv [n_brackets] (receiver index).
+ */
+int prt_count_brackets(int64_t n_rays, const double *z_end_dev, int32_t n_rcv,
+                       const double *receiver_depths_dev, int32_t *counts_dev, void *stream);
+int prt_fill_brackets(int64_t n_rays, const double *z_end_dev, const double *thetas_dev, int32_t n_rcv,
+                      const double *receiver_depths_dev, const int64_t *offsets_dev, double *br_z1_dev,
+                      double *br_z2_dev, double *br_th1_dev, double *br_th2_dev, double *br_rd_dev,
+                      int32_t *br_rcv_dev, int64_t *br_k_dev, void *stream);
+
+/*
+ * Regula-falsi refinement of n_br brackets (eigenrays.py:206-268), all brackets advanced together
+ * one trial shot per round; each trial is a full ray (no trajectory).  theta are USER angles: the
+ * trial ray is launched with internal angle -theta (launch_rays.py:251).
+ *   work_dev: caller-provided scratch of prt_refine_workspace_bytes(n_br) bytes
+ *   out_theta_dev [n_br]  converged user launch angle (NaN otherwise)
+ *   out_final_dev [3][n_br], out_n_bottom_dev, out_n_surface_dev, out_status_dev (PRT_EIG_*),
+ *   out_shots_dev [n_br], out_ray_status_dev [n_br] (PRT_RAY_* of the dropped trial)
+ * Synchronous with respect to the host (the round loop reads the active count back).
+ */
+int64_t prt_refine_workspace_bytes(int64_t n_br);
+int prt_refine_brackets(const prt_env_t *env, int64_t n_br, const double *z1_dev, const double *z2_dev,
+                        const double *th1_dev, const double *th2_dev, const double *rd_dev,
+                        double source_depth, double source_range, double receiver_range, double rtol,
+                        double atol, int32_t terminate_backwards, double ztol, int32_t max_iter,
+                        double *out_theta_dev, double *out_final_dev, int32_t *out_n_bottom_dev,
+                        int32_t *out_n_surface_dev, int32_t *out_status_dev, int32_t *out_shots_dev,
+                        int32_t *out_ray_status_dev, void *work_dev, int32_t max_bounces, void *stream);
+
+/* number of kernels this library has launched in the calling process (monotonic; for bench.py) */
+int64_t prt_launch_count(void);
+
+/* FP64 FMA-pipe microbenchmark: runs `iters` dependent-chain DFMA rounds on every SM and returns
+ * the achieved FLOP/s (2 flops per FMA), or a negative value on error.  Used as the roofline
+ * denominator of bench.py (MEASURED_PEAKS.json has no FP64 figure). */
+double prt_measure_fp64_peak(int device, int32_t iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRT_H */

@@ -1,0 +1,815 @@
+// prt_core.h -- per-ray integrator of the B200 ray-fan path (device code; header-only).
+//
+// One call of prt_integrate_ray() == the reference's _shoot_ray_array + _interpolate_ray for one
+// launch angle (/root/reference/src/pygenray/launch_rays.py:325-484, 745-784), i.e. a chain of
+// scipy.integrate.solve_ivp(RK45, rtol, atol=1e-6, 4 terminal events, dense_output=True) segments
+// (launch_rays.py:593-681; scipy 1.18.1 integrate/_ivp/{rk,ivp,common,base}.py) joined by specular
+// reflections.  The structure here is NOT the reference's: there is no solver object, no list of
+// interpolants and no post-hoc resampling -- the ray streams through registers, the sound-speed
+// lookup is shared between c and dc/dz, events reuse the sound speed of the FSAL stage, asin is
+// replaced by exact threshold tests, and save points are emitted while stepping.
+//
+// Rounding contract ("PRT arithmetic"): IEEE binary64, every written
+// operation is one correctly rounded +,-,*,/,sqrt or fma; fma only where PRT_FMA is written
+// (nvcc -fmad=false, g++ -ffp-contract=off).  The same contract is restated independently in
+// oracle/prt_oracle.c, which is how bit-for-bit parity against the CPU oracle is testable.
+//
+// The functions are __host__ __device__ only so that tests/host_harness can compile this header
+// with g++ and compare it bit-for-bit with the oracle on a machine without a GPU; the shipped
+// library (libprt.so) only ever calls them from kernels and has no CPU execution path.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PRT_HD __host__ __device__ __forceinline__
+#define PRT_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define PRT_HD inline
+#define PRT_HD_NOINLINE
+#endif
+
+struct alignas(16) prt_d2 {
+    double x, y;
+};
+
+#if defined(__CUDA_ARCH__)
+PRT_HD prt_d2 prt_ld2(const prt_d2* p)
+{
+    double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    prt_d2 r;
+    r.x = v.x;
+    r.y = v.y;
+    return r;
+}
+PRT_HD double prt_ld(const double* p) { return __ldg(p); }
+#define PRT_FMA(a, b, c) __fma_rn((a), (b), (c))
+PRT_HD double prt_bits_to_double(uint64_t b) { return __longlong_as_double((long long)b); }
+PRT_HD uint64_t prt_double_to_bits(double d) { return (uint64_t)__double_as_longlong(d); }
+#else
+#include <string.h>
+PRT_HD prt_d2 prt_ld2(const prt_d2* p) { return *p; }
+PRT_HD double prt_ld(const double* p) { return *p; }
+#define PRT_FMA(a, b, c) fma((a), (b), (c))
+PRT_HD double prt_bits_to_double(uint64_t b)
+{
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+PRT_HD uint64_t prt_double_to_bits(double d)
+{
+    uint64_t b;
+    memcpy(&b, &d, 8);
+    return b;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// Per-ray status: why the reference would have returned None for this launch angle
+// (launch_rays.py:427-430, 443-456, 474-477; exceptions raised inside solve_ivp / interp1d).
+// (values are those of include/prt.h; when prt.h was included first its macros are used)
+#ifndef PRT_RAY_OK
+enum {
+    PRT_RAY_OK = 0,
+    PRT_RAY_STEP_TOO_SMALL = 1,
+    PRT_RAY_VERTICAL = 2,
+    PRT_RAY_BBOX = 3,
+    PRT_RAY_BACKWARDS = 4,
+    PRT_RAY_BOTTOM_OOB = 5,
+    PRT_RAY_BRENTQ_SIGN = 6,
+    PRT_RAY_BRENTQ_ITER = 7,
+    PRT_RAY_MAX_BOUNCES = 9
+};
+enum { PRT_CNT_NFEV = 0, PRT_CNT_ATTEMPTS, PRT_CNT_ACCEPTED, PRT_CNT_SEGMENTS, PRT_CNT_BISECT, PRT_CNT_DENSE, PRT_CNT_N };
+#endif
+
+// Device view of one environment (all pointers device memory, one allocation; see prt_env.cu).
+struct prt_env_view {
+    int32_t n_r, n_z, n_b, n_ba;
+    const prt_d2* grid;     // [n_r][n_z] {c, dc/dz} interleaved: one 16-byte load per node
+    const prt_d2* rpair;    // [n_r-1] {rin[i], rin[i+1]}   : cell edges in one 16-byte load
+    const prt_d2* zpair;    // [n_z-1] {zin[j], zin[j+1]}
+    const prt_d2* bxpair;   // [n_b-1] {depth_ranges[i], depth_ranges[i+1]}
+    const prt_d2* bvpair;   // [n_b-1] {depths[i], depths[i+1]}
+    const double* ba_x;     // [n_ba] bottom-angle spline breakpoints
+    const double* ba_c;     // [4][n_ba-1] PPoly coefficients, highest power first
+    double r0, r_inv, z0, z_inv, b0, b_inv;  // cell-index guesses: (v - x0) * inv (any value is correct)
+    double bb_zmax, bb_zmin, bb_rmin, bb_rmax;  // zin[-1]+1e-6, zin[0]-1e-6, rin[0]-1e-6, rin[-1]+1e-6
+};
+
+// np.nextafter(t, +inf) (scipy rk.py:119) by integer increment of the bit pattern
+PRT_HD double prt_next_up(double t)
+{
+    if (t != t || t == (double)INFINITY) return t;
+    if (t == 0.0) return 4.9406564584124654e-324;
+    uint64_t b = prt_double_to_bits(t);
+    b = (t > 0.0) ? b + 1 : b - 1;
+    return prt_bits_to_double(b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Python builtin min/max and numpy.maximum NaN semantics (scipy rk.py:155-163, common.py:117-134)
+PRT_HD double prt_py_min(double a, double b) { return (b < a) ? b : a; }
+PRT_HD double prt_py_max(double a, double b) { return (b > a) ? b : a; }
+PRT_HD double prt_np_maximum(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+
+// ---------------------------------------------------------------------------------------------
+// Elementary functions of the rounding contract
+
+// x^(-1/5): stands for error_norm ** (-1/5), scipy rk.py:155,163.
+PRT_HD double prt_pow_m02(double x)
+{
+    if (x != x) return x;
+    if (x == (double)INFINITY) return 0.0;
+    double post = 1.0;
+    if (x < 0x1p-1022) {
+        x = x * 0x1p100;
+        post = 0x1p20;
+    }
+    uint64_t b = prt_double_to_bits(x);
+    int e = (int)((b >> 52) & 0x7ff) - 1023;
+    double m = prt_bits_to_double((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
+    int q = (e >= 0) ? (e / 5) : -((4 - e) / 5);
+    int r = e - 5 * q;
+    double y = PRT_FMA(PRT_FMA(0.05264997, m, -0.28570902), m, 1.23209767);
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        double y2 = y * y;
+        double y4 = y2 * y2;
+        double y5 = y4 * y;
+        double res = PRT_FMA(-m, y5, 1.0);
+        y = PRT_FMA(y * 0.2, res, y);
+    }
+    // 2^(-r/5)
+    double tr = (r == 0) ? 1.0
+              : (r == 1) ? 0x1.bdb8cdadbe120p-1
+              : (r == 2) ? 0x1.8406003b2ae5cp-1
+              : (r == 3) ? 0x1.51cb453b9536cp-1
+                         : 0x1.2611186bae674p-1;
+    y = y * tr;
+    double p2 = prt_bits_to_double((uint64_t)(1023 - q) << 52);
+    return (y * p2) * post;
+}
+
+PRT_HD double prt_k_sin(double r)
+{
+    double z = r * r;
+    double s = 1.0 / 355687428096000.0;
+    s = PRT_FMA(s, z, -1.0 / 1307674368000.0);
+    s = PRT_FMA(s, z, 1.0 / 6227020800.0);
+    s = PRT_FMA(s, z, -1.0 / 39916800.0);
+    s = PRT_FMA(s, z, 1.0 / 362880.0);
+    s = PRT_FMA(s, z, -1.0 / 5040.0);
+    s = PRT_FMA(s, z, 1.0 / 120.0);
+    s = PRT_FMA(s, z, -1.0 / 6.0);
+    return PRT_FMA(r * z, s, r);
+}
+
+PRT_HD double prt_k_cos(double r)
+{
+    double z = r * r;
+    double s = 1.0 / 20922789888000.0;
+    s = PRT_FMA(s, z, -1.0 / 87178291200.0);
+    s = PRT_FMA(s, z, 1.0 / 479001600.0);
+    s = PRT_FMA(s, z, -1.0 / 3628800.0);
+    s = PRT_FMA(s, z, 1.0 / 40320.0);
+    s = PRT_FMA(s, z, -1.0 / 720.0);
+    s = PRT_FMA(s, z, 1.0 / 24.0);
+    s = PRT_FMA(s, z, -0.5);
+    return PRT_FMA(z, s, 1.0);
+}
+
+#define PRT_PIO2_HI 0x1.921fb54442d18p+0
+#define PRT_PIO2_LO 0x1.1a62633145c07p-54
+#define PRT_TWO_OVER_PI 0.6366197723675814
+#define PRT_RAD2DEG 57.29577951308232
+#define PRT_DEG2RAD 0.017453292519943295
+
+// sin(x): np.sin of launch_rays.py:143, 285, 480
+PRT_HD_NOINLINE double prt_sin(double x)
+{
+    if (x != x || fabs(x) == (double)INFINITY) return (double)NAN;
+    if (fabs(x) <= 0.7853981633974483) return prt_k_sin(x);
+    double n = floor(PRT_FMA(x, PRT_TWO_OVER_PI, 0.5));
+    double r = PRT_FMA(-n, PRT_PIO2_HI, x);
+    r = PRT_FMA(-n, PRT_PIO2_LO, r);
+    int k = (int)((long long)n & 3);
+    if (k == 0) return prt_k_sin(r);
+    if (k == 1) return prt_k_cos(r);
+    if (k == 2) return -prt_k_sin(r);
+    return -prt_k_cos(r);
+}
+
+PRT_HD double prt_asin_core(double a)
+{
+    double th = PRT_FMA(a * a, a * (1.0 / 6.0), a);
+#pragma unroll 1
+    for (int it = 0; it < 3; ++it) {
+        double d = (prt_k_sin(th) - a) / prt_k_cos(th);
+        th = th - d;
+    }
+    return th;
+}
+
+// asin(x): np.arcsin of integration_processes.py:333; |x| > 1 -> NaN
+PRT_HD_NOINLINE double prt_asin(double x)
+{
+    if (x != x) return x;
+    double a = fabs(x);
+    if (a > 1.0) return NAN;
+    double t;
+    if (a <= 0.5) {
+        t = prt_asin_core(a);
+    } else {
+        double s = sqrt((1.0 - a) * 0.5);
+        t = PRT_FMA(-2.0, prt_asin_core(s), PRT_PIO2_HI);
+    }
+    return (x < 0.0) ? -t : t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cell lookup: k = clamp(np.searchsorted(a, v, side="left") - 1, 0, n-2)
+// (integration_processes.py:152-157, 221-224), returning the cell edges {a[k], a[k+1]} with it.
+// Guess from the mean spacing, hunt a few cells, bisect as a fallback: result is exact for any
+// sorted grid; the guess only affects speed.
+PRT_HD int prt_locate(const prt_d2* pair, int n, double x0, double inv, double v, prt_d2& edges)
+{
+    const int m = n - 2;
+    int g;
+    if (v != v) {
+        g = m;  // NaN sorts last in np.searchsorted
+        edges = prt_ld2(pair + g);
+        return g;
+    }
+    double gf = (v - x0) * inv;
+    g = (gf > 0.0) ? ((gf < (double)m) ? (int)gf : m) : 0;
+    edges = prt_ld2(pair + g);
+    int it = 0;
+    for (;;) {
+        if (g > 0 && !(edges.x < v)) --g;
+        else if (g < m && edges.y < v) ++g;
+        else return g;
+        edges = prt_ld2(pair + g);
+        if (++it == 6) break;
+    }
+    // fallback: lower_bound over the n nodes (node i = pair[i].x, node n-1 = pair[m].y)
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = lo + ((hi - lo) >> 1);
+        double a = (mid <= m) ? prt_ld(&pair[mid].x) : prt_ld(&pair[m].y);
+        if (a < v) lo = mid + 1;
+        else hi = mid;
+    }
+    g = lo - 1;
+    g = g > m ? m : g;
+    g = g < 0 ? 0 : g;
+    edges = prt_ld2(pair + g);
+    return g;
+}
+
+// c(x, z) and dc/dz(x, z): bilinear_interp (integration_processes.py:101-174) evaluated ONCE for
+// both fields (the reference evaluates it twice with identical weights, :86-87).
+PRT_HD void prt_field(const prt_env_view& E, double x, double z, double& c, double& cz)
+{
+    prt_d2 re, ze;
+    int i = prt_locate(E.rpair, E.n_r, E.r0, E.r_inv, x, re);
+    int j = prt_locate(E.zpair, E.n_z, E.z0, E.z_inv, z, ze);
+    const prt_d2* g = E.grid + ((size_t)i * (size_t)E.n_z + (size_t)j);
+    prt_d2 v00 = prt_ld2(g);
+    prt_d2 v01 = prt_ld2(g + 1);
+    prt_d2 v10 = prt_ld2(g + E.n_z);
+    prt_d2 v11 = prt_ld2(g + E.n_z + 1);
+    double wx = (x - re.x) / (re.y - re.x);
+    double wy = (z - ze.x) / (ze.y - ze.x);
+    double ax = 1.0 - wx, ay = 1.0 - wy;
+    double w00 = ax * ay, w10 = wx * ay, w01 = ax * wy, w11 = wx * wy;
+    double a = w00 * v00.x;
+    a = PRT_FMA(w10, v10.x, a);
+    a = PRT_FMA(w01, v01.x, a);
+    a = PRT_FMA(w11, v11.x, a);
+    double b = w00 * v00.y;
+    b = PRT_FMA(w10, v10.y, b);
+    b = PRT_FMA(w01, v01.y, b);
+    b = PRT_FMA(w11, v11.y, b);
+    c = a;
+    cz = b;
+}
+
+// bottom depth at x: linear_interp (integration_processes.py:177-235)
+PRT_HD double prt_bathy(const prt_env_view& E, double x)
+{
+    prt_d2 xe;
+    int i = prt_locate(E.bxpair, E.n_b, E.b0, E.b_inv, x, xe);
+    prt_d2 v = prt_ld2(E.bvpair + i);
+    double w = (x - xe.x) / (xe.y - xe.x);
+    return PRT_FMA(w, v.y, (1.0 - w) * v.x);
+}
+
+// derivsrd (integration_processes.py:26-98); also returns c for event reuse
+PRT_HD void prt_rhs(const prt_env_view& E, double x, double z, double p, double& dT, double& dz, double& dp,
+                    double& c_out)
+{
+    double c, cz;
+    prt_field(E, x, z, c, cz);
+    double c2 = c * c;
+    double arg = PRT_FMA(-c2, p * p, 1.0);
+    if (arg <= 0.0) arg = 1e-30;
+    double fact = 1.0 / sqrt(arg);
+    dT = fact / c;
+    dz = (c * p) * fact;
+    dp = ((-fact) * cz) / c2;
+    c_out = c;
+}
+
+// The four event functions (integration_processes.py:238-303) as a 4-bit mask of "+1" values.
+// theta = degrees(asin(p*c)) is only ever compared with 0 and +-(90 - 1e-3), so
+//   theta < 0  <=>  -1 <= p*c < 0,   theta > 0  <=>  0 < p*c <= 1          (asin is odd, NaN outside)
+//   |theta| > 90-1e-3  <=>  literal evaluation, needed only when |p*c| is within 1e-8 of 1.
+#define PRT_EV_SURFACE 1
+#define PRT_EV_BOTTOM 2
+#define PRT_EV_VERTICAL 4
+#define PRT_EV_BBOX 8
+
+PRT_HD bool prt_ev_vertical(double pc)
+{
+    double a = fabs(pc);
+    if (!(a > 0.99999999)) return false;  // sin(89.999 deg) = 1 - 1.5e-10
+    if (a > 1.0) return false;            // asin -> NaN, comparison false
+    return fabs(prt_asin(pc) * PRT_RAD2DEG) > (90.0 - 1e-3);
+}
+
+PRT_HD int prt_events(const prt_env_view& E, double x, double z, double p, double c)
+{
+    double pc = p * c;
+    int m = 0;
+    if ((z < 0.0) && (pc < 0.0) && (pc >= -1.0)) m |= PRT_EV_SURFACE;
+    if ((pc > 0.0) && (pc <= 1.0)) {
+        if (z > prt_bathy(E, x)) m |= PRT_EV_BOTTOM;
+    }
+    if (prt_ev_vertical(pc)) m |= PRT_EV_VERTICAL;
+    if ((z > E.bb_zmax) | (z < E.bb_zmin) | (x < E.bb_rmin) | (x > E.bb_rmax)) m |= PRT_EV_BBOX;
+    return m;
+}
+
+// single event evaluated on demand (inside the root search)
+PRT_HD bool prt_event_one(const prt_env_view& E, int which, double x, double z, double p)
+{
+    if (which == 3) return (z > E.bb_zmax) | (z < E.bb_zmin) | (x < E.bb_rmin) | (x > E.bb_rmax);
+    if (which == 0 && !(z < 0.0)) return false;
+    double c, cz;
+    prt_field(E, x, z, c, cz);
+    double pc = p * c;
+    if (which == 0) return (pc < 0.0) && (pc >= -1.0);
+    if (which == 1) return (pc > 0.0) && (pc <= 1.0) && (z > prt_bathy(E, x));
+    return prt_ev_vertical(pc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dormand-Prince tableau (scipy rk.py:538-565), zeros omitted
+#define A21 (1.0 / 5)
+#define A31 (3.0 / 40)
+#define A32 (9.0 / 40)
+#define A41 (44.0 / 45)
+#define A42 (-56.0 / 15)
+#define A43 (32.0 / 9)
+#define A51 (19372.0 / 6561)
+#define A52 (-25360.0 / 2187)
+#define A53 (64448.0 / 6561)
+#define A54 (-212.0 / 729)
+#define A61 (9017.0 / 3168)
+#define A62 (-355.0 / 33)
+#define A63 (46732.0 / 5247)
+#define A64 (49.0 / 176)
+#define A65 (-5103.0 / 18656)
+#define B1 (35.0 / 384)
+#define B3 (500.0 / 1113)
+#define B4 (125.0 / 192)
+#define B5 (-2187.0 / 6784)
+#define B6 (11.0 / 84)
+#define E1 (-71.0 / 57600)
+#define E3 (71.0 / 16695)
+#define E4 (-71.0 / 1920)
+#define E5 (17253.0 / 339200)
+#define E6 (-22.0 / 525)
+#define E7 (1.0 / 40)
+#define C2 (1.0 / 5)
+#define C3 (3.0 / 10)
+#define C4 (4.0 / 5)
+#define C5 (8.0 / 9)
+
+#define PRT_SQRT3 1.7320508075688772
+
+PRT_HD double prt_rms3(double a, double b, double c)
+{
+    double s = a * a;
+    s = PRT_FMA(b, b, s);
+    s = PRT_FMA(c, c, s);
+    return sqrt(s) / PRT_SQRT3;
+}
+
+// Q = K^T P for one component (scipy rk.py:178-180); Q0 = K1 because P[:,0] = e_1
+struct prt_q3 {
+    double q1, q2, q3;
+};
+PRT_HD prt_q3 prt_dense_q(double k1, double k3, double k4, double k5, double k6, double k7)
+{
+    prt_q3 q;
+    double a = (-8048581381.0 / 2820520608.0) * k1;
+    a = PRT_FMA(131558114200.0 / 32700410799.0, k3, a);
+    a = PRT_FMA(-1754552775.0 / 470086768.0, k4, a);
+    a = PRT_FMA(127303824393.0 / 49829197408.0, k5, a);
+    a = PRT_FMA(-282668133.0 / 205662961.0, k6, a);
+    a = PRT_FMA(40617522.0 / 29380423.0, k7, a);
+    q.q1 = a;
+    a = (8663915743.0 / 2820520608.0) * k1;
+    a = PRT_FMA(-68118460800.0 / 10900136933.0, k3, a);
+    a = PRT_FMA(14199869525.0 / 1410260304.0, k4, a);
+    a = PRT_FMA(-318862633887.0 / 49829197408.0, k5, a);
+    a = PRT_FMA(2019193451.0 / 616988883.0, k6, a);
+    a = PRT_FMA(-110615467.0 / 29380423.0, k7, a);
+    q.q2 = a;
+    a = (-12715105075.0 / 11282082432.0) * k1;
+    a = PRT_FMA(87487479700.0 / 32700410799.0, k3, a);
+    a = PRT_FMA(-10690763975.0 / 1880347072.0, k4, a);
+    a = PRT_FMA(701980252875.0 / 199316789632.0, k5, a);
+    a = PRT_FMA(-1453857185.0 / 822651844.0, k6, a);
+    a = PRT_FMA(69997945.0 / 29380423.0, k7, a);
+    q.q3 = a;
+    return q;
+}
+
+// RkDenseOutput._call_impl (scipy rk.py:715-737) for one component
+PRT_HD double prt_dense_eval(double q0, const prt_q3& q, double h, double y_old, double p1, double p2, double p3,
+                             double p4)
+{
+    double a = q0 * p1;
+    a = PRT_FMA(q.q1, p2, a);
+    a = PRT_FMA(q.q2, p3, a);
+    a = PRT_FMA(q.q3, p4, a);
+    return PRT_FMA(h, a, y_old);
+}
+
+// cubic spline of the bottom angle (launch_rays.py:397-399, 469) as host-prepared PPoly
+PRT_HD double prt_bottom_angle(const prt_env_view& E, double x, bool& oob)
+{
+    const int n = E.n_ba;
+    oob = false;
+    double x_first = prt_ld(E.ba_x), x_last = prt_ld(E.ba_x + n - 1);
+    if (!(x >= x_first) || !(x <= x_last)) {
+        oob = true;
+        return 0.0;
+    }
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = lo + ((hi - lo) >> 1);
+        if (prt_ld(E.ba_x + mid) < x) lo = mid + 1;
+        else hi = mid;
+    }
+    int i = lo - 1;
+    i = i < 0 ? 0 : i;
+    i = i > n - 2 ? n - 2 : i;
+    double s = x - prt_ld(E.ba_x + i);
+    const int m = n - 1;
+    double v = prt_ld(E.ba_c + i);
+    v = PRT_FMA(v, s, prt_ld(E.ba_c + m + i));
+    v = PRT_FMA(v, s, prt_ld(E.ba_c + 2 * m + i));
+    v = PRT_FMA(v, s, prt_ld(E.ba_c + 3 * m + i));
+    return v;
+}
+
+// y0 = [0, z_src, sin(radians(angle)) / c(src)]  (launch_rays.py:140-144, 284-285)
+PRT_HD void prt_initial_state(const prt_env_view& E, double source_depth, double source_range, double angle_deg,
+                              double& T, double& z, double& p)
+{
+    double c, cz;
+    prt_field(E, source_range, source_depth, c, cz);
+    T = 0.0;
+    z = source_depth;
+    p = prt_sin(angle_deg * PRT_DEG2RAD) / c;
+}
+
+// np.argmin(np.abs(range_save - v)) for ascending range_save, scanning forward from `start`
+// (the minimum is never below start)
+PRT_HD int prt_argmin_from(const double* rs, int n, int start, double v)
+{
+    int best = start;
+    double bd = fabs(prt_ld(rs + start) - v);
+    for (int i = start + 1; i < n; ++i) {
+        double d = fabs(prt_ld(rs + i) - v);
+        if (d < bd) {
+            bd = d;
+            best = i;
+        } else
+            break;
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Trajectory sink: stores save point i of this ray.  kernels pass a strided global-memory sink.
+struct prt_traj_sink {
+    double* T;       // &out_T[ray][0]
+    double* z;
+    double* p;
+    int64_t stride;  // element stride between consecutive save points of one ray
+    PRT_HD void put(int i, double vT, double vz, double vp) const
+    {
+        T[(int64_t)i * stride] = vT;
+        z[(int64_t)i * stride] = vz;
+        p[(int64_t)i * stride] = vp;
+    }
+};
+
+struct prt_ray_result {
+    double T, z, p;
+    int32_t n_bottom, n_surface, status;
+};
+
+//
+// The ray.  SAVE = emit the num_range_save resampling of _interpolate_ray while stepping.
+//
+template <bool SAVE>
+PRT_HD void prt_integrate_ray(const prt_env_view& E, double T, double z, double p, double x0, double x_end,
+                              double rtol, double atol, bool terminate_backwards, int n_save,
+                              const double* range_save, const prt_traj_sink& sink, int max_bounces,
+                              prt_ray_result& res, uint32_t* cnt)
+{
+    if (rtol < 100.0 * 2.220446049250313e-16) rtol = 100.0 * 2.220446049250313e-16;  // validate_tol
+    double x = x0;
+    int n_surface = 0, n_bottom = 0, status = PRT_RAY_OK;
+    int cursor = 0;  // first save index not yet owned by a finished segment
+    uint32_t c_nfev = 0, c_att = 0, c_acc = 0, c_seg = 0, c_bis = 0, c_dense = 0;
+
+    while (x < x_end) {  // launch_rays.py:404 -- one iteration per solve_ivp segment
+        ++c_seg;
+        // ---- RK45.__init__ (rk.py:85-103): f0 and select_initial_step (common.py:68-134)
+        double t = x;
+        double f0, f1, f2, c_here;
+        prt_rhs(E, t, z, p, f0, f1, f2, c_here);
+        ++c_nfev;
+        int g = prt_events(E, t, z, p, c_here);  // g = [event(t0, y0)]  ivp.py:641
+        double h_abs;
+        {
+            double interval = fabs(x_end - t);
+            double s0 = PRT_FMA(fabs(T), rtol, atol), s1 = PRT_FMA(fabs(z), rtol, atol), s2 = PRT_FMA(fabs(p), rtol, atol);
+            double d0 = prt_rms3(T / s0, z / s1, p / s2);
+            double d1 = prt_rms3(f0 / s0, f1 / s1, f2 / s2);
+            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (0.01 * d0) / d1;
+            h0 = prt_py_min(h0, interval);
+            double g0, g1, g2, cc;
+            prt_rhs(E, t + h0, PRT_FMA(h0, f1, z), PRT_FMA(h0, f2, p), g0, g1, g2, cc);
+            ++c_nfev;
+            double d2 = prt_rms3((g0 - f0) / s0, (g1 - f1) / s1, (g2 - f2) / s2) / h0;
+            double h1;
+            if (d1 <= 1e-15 && d2 <= 1e-15) h1 = prt_py_max(1e-6, h0 * 1e-3);
+            else h1 = 1.0 / prt_pow_m02(0.01 / prt_py_max(d1, d2));
+            h_abs = prt_py_min(prt_py_min(100.0 * h0, h1), interval);
+        }
+        int n_ts = 1;             // len(ts) of this segment
+        int event = -1;           // terminal event of this segment
+        bool finished = false;
+
+        for (;;) {  // ivp.py:659 -- one iteration per accepted step
+            // ---- _step_impl (rk.py:111-176)
+            double min_step = 10.0 * fabs(prt_next_up(t) - t);
+            if (h_abs < min_step) h_abs = min_step;
+            bool rejected = false, failed = false;
+            double h = 0.0, t_new = t, yT = T, yz = z, yp = p;
+            double k2T, k2z, k2p, k3T, k3z, k3p, k4T, k4z, k4p, k5T, k5z, k5p, k6T, k6z, k6p, k7T, k7z, k7p, c_new;
+            for (;;) {
+                if (h_abs < min_step) {
+                    failed = true;
+                    break;
+                }
+                ++c_att;
+                t_new = t + h_abs;
+                if (t_new - x_end > 0.0) t_new = x_end;
+                h = t_new - t;
+                h_abs = fabs(h);
+                double cc, a, b;
+                // stage 2
+                prt_rhs(E, PRT_FMA(C2, h, t), PRT_FMA(h, A21 * f1, z), PRT_FMA(h, A21 * f2, p), k2T, k2z, k2p, cc);
+                // stage 3
+                a = A31 * f1; a = PRT_FMA(A32, k2z, a);
+                b = A31 * f2; b = PRT_FMA(A32, k2p, b);
+                prt_rhs(E, PRT_FMA(C3, h, t), PRT_FMA(h, a, z), PRT_FMA(h, b, p), k3T, k3z, k3p, cc);
+                // stage 4
+                a = A41 * f1; a = PRT_FMA(A42, k2z, a); a = PRT_FMA(A43, k3z, a);
+                b = A41 * f2; b = PRT_FMA(A42, k2p, b); b = PRT_FMA(A43, k3p, b);
+                prt_rhs(E, PRT_FMA(C4, h, t), PRT_FMA(h, a, z), PRT_FMA(h, b, p), k4T, k4z, k4p, cc);
+                // stage 5
+                a = A51 * f1; a = PRT_FMA(A52, k2z, a); a = PRT_FMA(A53, k3z, a); a = PRT_FMA(A54, k4z, a);
+                b = A51 * f2; b = PRT_FMA(A52, k2p, b); b = PRT_FMA(A53, k3p, b); b = PRT_FMA(A54, k4p, b);
+                prt_rhs(E, PRT_FMA(C5, h, t), PRT_FMA(h, a, z), PRT_FMA(h, b, p), k5T, k5z, k5p, cc);
+                // stage 6 (c = 1)
+                a = A61 * f1; a = PRT_FMA(A62, k2z, a); a = PRT_FMA(A63, k3z, a); a = PRT_FMA(A64, k4z, a); a = PRT_FMA(A65, k5z, a);
+                b = A61 * f2; b = PRT_FMA(A62, k2p, b); b = PRT_FMA(A63, k3p, b); b = PRT_FMA(A64, k4p, b); b = PRT_FMA(A65, k5p, b);
+                prt_rhs(E, PRT_FMA(1.0, h, t), PRT_FMA(h, a, z), PRT_FMA(h, b, p), k6T, k6z, k6p, cc);
+                // y_new
+                double sT = B1 * f0; sT = PRT_FMA(B3, k3T, sT); sT = PRT_FMA(B4, k4T, sT); sT = PRT_FMA(B5, k5T, sT); sT = PRT_FMA(B6, k6T, sT);
+                double sz = B1 * f1; sz = PRT_FMA(B3, k3z, sz); sz = PRT_FMA(B4, k4z, sz); sz = PRT_FMA(B5, k5z, sz); sz = PRT_FMA(B6, k6z, sz);
+                double sp = B1 * f2; sp = PRT_FMA(B3, k3p, sp); sp = PRT_FMA(B4, k4p, sp); sp = PRT_FMA(B5, k5p, sp); sp = PRT_FMA(B6, k6p, sp);
+                yT = PRT_FMA(h, sT, T);
+                yz = PRT_FMA(h, sz, z);
+                yp = PRT_FMA(h, sp, p);
+                // f_new (FSAL stage 7)
+                prt_rhs(E, t + h, yz, yp, k7T, k7z, k7p, c_new);
+                c_nfev += 6;
+                // error norm (rk.py:105-109, 145-147)
+                double eT = E1 * f0; eT = PRT_FMA(E3, k3T, eT); eT = PRT_FMA(E4, k4T, eT); eT = PRT_FMA(E5, k5T, eT); eT = PRT_FMA(E6, k6T, eT); eT = PRT_FMA(E7, k7T, eT);
+                double ez = E1 * f1; ez = PRT_FMA(E3, k3z, ez); ez = PRT_FMA(E4, k4z, ez); ez = PRT_FMA(E5, k5z, ez); ez = PRT_FMA(E6, k6z, ez); ez = PRT_FMA(E7, k7z, ez);
+                double ep = E1 * f2; ep = PRT_FMA(E3, k3p, ep); ep = PRT_FMA(E4, k4p, ep); ep = PRT_FMA(E5, k5p, ep); ep = PRT_FMA(E6, k6p, ep); ep = PRT_FMA(E7, k7p, ep);
+                double scT = PRT_FMA(prt_np_maximum(fabs(T), fabs(yT)), rtol, atol);
+                double scz = PRT_FMA(prt_np_maximum(fabs(z), fabs(yz)), rtol, atol);
+                double scp = PRT_FMA(prt_np_maximum(fabs(p), fabs(yp)), rtol, atol);
+                double err = prt_rms3((eT * h) / scT, (ez * h) / scz, (ep * h) / scp);
+                if (err < 1.0) {
+                    double factor = (err == 0.0) ? 10.0 : prt_py_min(10.0, 0.9 * prt_pow_m02(err));
+                    if (rejected) factor = prt_py_min(1.0, factor);
+                    h_abs *= factor;
+                    break;
+                }
+                h_abs *= prt_py_max(0.2, 0.9 * prt_pow_m02(err));
+                rejected = true;
+            }
+            if (failed) {
+                status = PRT_RAY_STEP_TOO_SMALL;
+                break;
+            }
+            ++c_acc;
+            const double t_old = t;
+            finished = (t_new - x_end >= 0.0);  // base.py:205-206
+
+            // ---- events at the step end (ivp.py:678-699); c(t_new, y_new) comes from the FSAL stage,
+            // which was evaluated at t + h: identical unless the clipped step made t + h != t_new
+            if (t + h != t_new) {
+                double cz_unused;
+                prt_field(E, t_new, yz, c_new, cz_unused);
+            }
+            int g_new = prt_events(E, t_new, yz, yp, c_new);
+            // find_active_events (ivp.py:134-157): up for direction +1, up|down for direction 0
+            int up = (~g) & g_new, down = g & (~g_new);
+            int active = (up & (PRT_EV_SURFACE | PRT_EV_BOTTOM)) | ((up | down) & (PRT_EV_VERTICAL | PRT_EV_BBOX));
+            g = g_new;
+
+            // dense output is needed if an event fired or a save point lies in (t_old, t_new]
+            bool need_dense = (active != 0);
+            if (SAVE && !need_dense) need_dense = (cursor < n_save - 1) && (prt_ld(range_save + cursor) <= t_new);
+            prt_q3 qT = {0.0, 0.0, 0.0}, qz = qT, qp = qT;
+            if (need_dense) {
+                ++c_dense;
+                qT = prt_dense_q(f0, k3T, k4T, k5T, k6T, k7T);
+                qz = prt_dense_q(f1, k3z, k4z, k5z, k6z, k7z);
+                qp = prt_dense_q(f2, k3p, k4p, k5p, k6p, k7p);
+            }
+
+            bool terminal = false, popped = false;
+            double root = t_new;
+            if (active) {
+                // handle_events (ivp.py:80-131): every event is terminal -> earliest root, ties to
+                // the lower event index.  solve_event_equation = brentq on a +-1 function = bisection.
+                double best_root = 0.0;
+                int best = -1;
+                for (int e = 0; e < 4 && status == PRT_RAY_OK; ++e) {
+                    if (!(active & (1 << e))) continue;
+                    // brentq(f, t_old, t_new, xtol=4eps, rtol=4eps, maxiter=100)
+                    double xpre = t_old, xcur = t_new, xblk = 0.0;
+                    bool fpre, fcur, fblk = false;
+                    {
+                        // f(t_old): x = 0 -> y_old exactly;  f(t_new): x = (t_new - t_old)/h
+                        fpre = prt_event_one(E, e, t_old, PRT_FMA(h, 0.0, z), PRT_FMA(h, 0.0, p));
+                        double xx = (t_new - t_old) / h;
+                        double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
+                        fcur = prt_event_one(E, e, t_new, prt_dense_eval(f1, qz, h, z, p1, p2, p3, p4),
+                                             prt_dense_eval(f2, qp, h, p, p1, p2, p3, p4));
+                        c_bis += 2;
+                    }
+                    if (fpre == fcur) {
+                        status = PRT_RAY_BRENTQ_SIGN;
+                        break;
+                    }
+                    double rootv = 0.0;
+                    bool converged = false;
+                    for (int i = 0; i < 100; ++i) {
+                        if (fpre != fcur) {
+                            xblk = xpre;
+                            fblk = fpre;
+                        }
+                        // |f| == 1 always: the "fabs(fblk) < fabs(fcur)" swap never happens
+                        double delta = (4 * 2.220446049250313e-16 + 4 * 2.220446049250313e-16 * fabs(xcur)) / 2;
+                        double sbis = (xblk - xcur) / 2;
+                        if (fabs(sbis) < delta) {
+                            rootv = xcur;
+                            converged = true;
+                            break;
+                        }
+                        // fabs(fcur) < fabs(fpre) is never true -> always bisect
+                        xpre = xcur;
+                        fpre = fcur;
+                        if (fabs(sbis) > delta) xcur += sbis;
+                        else xcur += (sbis > 0 ? delta : -delta);
+                        double xx = (xcur - t_old) / h;
+                        double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
+                        fcur = prt_event_one(E, e, xcur, prt_dense_eval(f1, qz, h, z, p1, p2, p3, p4),
+                                             prt_dense_eval(f2, qp, h, p, p1, p2, p3, p4));
+                        ++c_bis;
+                        (void)fblk;
+                    }
+                    if (!converged) {
+                        status = PRT_RAY_BRENTQ_ITER;
+                        break;
+                    }
+                    if (best < 0 || rootv < best_root) {
+                        best = e;
+                        best_root = rootv;
+                    }
+                }
+                if (status != PRT_RAY_OK) break;
+                event = best;
+                root = best_root;
+                terminal = true;
+                popped = (n_ts > 1) && (root == t_old);  // donot_append, ivp.py:701-710
+            }
+
+            // ---- _interpolate_ray (launch_rays.py:745-784), streamed
+            if (SAVE) {
+                int ub = n_save - 1;
+                if (terminal) {
+                    int start = cursor > 0 ? cursor - 1 : 0;
+                    ub = prt_argmin_from(range_save, n_save, start, root);  // idx2
+                }
+                if (!popped) {
+                    while (cursor < ub) {
+                        double rsv = prt_ld(range_save + cursor);
+                        if (!terminal && !(rsv <= t_new)) break;
+                        double xx = (rsv - t_old) / h;
+                        double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
+                        sink.put(cursor, prt_dense_eval(f0, qT, h, T, p1, p2, p3, p4),
+                                 prt_dense_eval(f1, qz, h, z, p1, p2, p3, p4),
+                                 prt_dense_eval(f2, qp, h, p, p1, p2, p3, p4));
+                        ++cursor;
+                    }
+                }
+                if (terminal) cursor = ub;  // the next segment owns indices >= idx2
+            }
+
+            // ---- advance the state
+            if (terminal) {
+                if (!popped) {
+                    double xx = (root - t_old) / h;
+                    double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
+                    double nT = prt_dense_eval(f0, qT, h, T, p1, p2, p3, p4);
+                    double nz = prt_dense_eval(f1, qz, h, z, p1, p2, p3, p4);
+                    double np_ = prt_dense_eval(f2, qp, h, p, p1, p2, p3, p4);
+                    T = nT; z = nz; p = np_;
+                }  // else: sol.y[:, -1] stays the state at t_old
+                t = root;
+                break;
+            }
+            T = yT; z = yz; p = yp;
+            f0 = k7T; f1 = k7z; f2 = k7p;
+            t = t_new;
+            ++n_ts;
+            if (finished) break;
+        }
+        if (status != PRT_RAY_OK) break;
+        if (event < 0) break;  // reached x_end (sol.status == 0), launch_rays.py:425-426
+
+        // ---- bounce (launch_rays.py:432-480)
+        if (event == 2) { status = PRT_RAY_VERTICAL; break; }
+        if (event == 3) { status = PRT_RAY_BBOX; break; }
+        x = t;
+        double c, cz;
+        prt_field(E, x, z, c, cz);
+        double theta = prt_asin(p * c) * PRT_RAD2DEG;  // ray_angle
+        double theta_bounce;
+        if (event == 0) {
+            theta_bounce = -theta;
+            ++n_surface;
+        } else {
+            bool oob;
+            double beta = prt_bottom_angle(E, x, oob);
+            if (oob) { status = PRT_RAY_BOTTOM_OOB; break; }
+            theta_bounce = 2.0 * beta - theta;
+            ++n_bottom;
+        }
+        if (terminate_backwards && (fabs(theta_bounce) > 90.0)) { status = PRT_RAY_BACKWARDS; break; }
+        p = prt_sin(theta_bounce * PRT_DEG2RAD) / c;
+        if (n_surface + n_bottom >= max_bounces) { status = PRT_RAY_MAX_BOUNCES; break; }
+    }
+
+    if (status == PRT_RAY_OK) {
+        if (SAVE && n_save > 0) sink.put(n_save - 1, T, z, p);  // exact final state, launch_rays.py:772-775
+        res.T = T; res.z = z; res.p = p;
+    } else {
+        res.T = NAN; res.z = NAN; res.p = NAN;
+    }
+    res.n_bottom = n_bottom;
+    res.n_surface = n_surface;
+    res.status = status;
+    if (cnt) {
+        cnt[PRT_CNT_NFEV] = c_nfev; cnt[PRT_CNT_ATTEMPTS] = c_att; cnt[PRT_CNT_ACCEPTED] = c_acc;
+        cnt[PRT_CNT_SEGMENTS] = c_seg; cnt[PRT_CNT_BISECT] = c_bis; cnt[PRT_CNT_DENSE] = c_dense;
+    }
+}

@@ -1,0 +1,103 @@
+// prt_env_layout.h -- host-side packing of one environment into the single buffer the kernels read.
+//
+// Input = the seven arrays of the reference's _unpack_envi (/root/reference/src/pygenray/
+// launch_rays.py:717-742) + the bottom-angle cubic spline as PPoly coefficients.  Output = one
+// contiguous, 256-byte-aligned blob laid out for 16-byte loads:
+//   grid   [n_r][n_z] {c, dc/dz}   -- both fields of a node in one LDG.128
+//   rpair  [n_r-1] {r[i], r[i+1]}  -- both edges of a cell in one LDG.128 (same for z, bathymetry)
+// and a prt_env_view whose pointers are offsets into the blob until prt_env_rebase() is applied.
+#pragma once
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "prt_core.h"
+
+struct prt_env_blob {
+    std::vector<unsigned char> bytes;
+    prt_env_view view;  // pointers hold byte OFFSETS into bytes
+};
+
+static inline size_t prt_align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+static inline void prt_pack_pairs(prt_d2* dst, const double* a, int n)
+{
+    for (int i = 0; i < n - 1; ++i) {
+        dst[i].x = a[i];
+        dst[i].y = a[i + 1];
+    }
+}
+
+static inline double prt_inv_mean_step(const double* a, int n)
+{
+    double span = a[n - 1] - a[0];
+    if (!(span > 0.0)) return 0.0;
+    return (double)(n - 1) / span;
+}
+
+// returns 0 on success, nonzero on invalid sizes
+static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double* zin, const double* cin,
+                               const double* cpin, int n_b, const double* depth_ranges, const double* depths,
+                               int n_ba, const double* ba_x, const double* ba_c, prt_env_blob& out)
+{
+    if (n_r < 2 || n_z < 2 || n_b < 2 || n_ba < 2) return 1;
+    size_t o_grid = 0;
+    size_t o_rpair = o_grid + prt_align256(sizeof(prt_d2) * (size_t)n_r * n_z);
+    size_t o_zpair = o_rpair + prt_align256(sizeof(prt_d2) * (size_t)(n_r - 1));
+    size_t o_bx = o_zpair + prt_align256(sizeof(prt_d2) * (size_t)(n_z - 1));
+    size_t o_bv = o_bx + prt_align256(sizeof(prt_d2) * (size_t)(n_b - 1));
+    size_t o_bax = o_bv + prt_align256(sizeof(prt_d2) * (size_t)(n_b - 1));
+    size_t o_bac = o_bax + prt_align256(sizeof(double) * (size_t)n_ba);
+    size_t total = o_bac + prt_align256(sizeof(double) * 4 * (size_t)(n_ba - 1));
+    out.bytes.assign(total, 0);
+    unsigned char* base = out.bytes.data();
+    prt_d2* grid = reinterpret_cast<prt_d2*>(base + o_grid);
+    const size_t n_nodes = (size_t)n_r * n_z;
+    for (size_t k = 0; k < n_nodes; ++k) {
+        grid[k].x = cin[k];
+        grid[k].y = cpin[k];
+    }
+    prt_pack_pairs(reinterpret_cast<prt_d2*>(base + o_rpair), rin, n_r);
+    prt_pack_pairs(reinterpret_cast<prt_d2*>(base + o_zpair), zin, n_z);
+    prt_pack_pairs(reinterpret_cast<prt_d2*>(base + o_bx), depth_ranges, n_b);
+    prt_pack_pairs(reinterpret_cast<prt_d2*>(base + o_bv), depths, n_b);
+    memcpy(base + o_bax, ba_x, sizeof(double) * n_ba);
+    memcpy(base + o_bac, ba_c, sizeof(double) * 4 * (size_t)(n_ba - 1));
+
+    prt_env_view& v = out.view;
+    v.n_r = n_r; v.n_z = n_z; v.n_b = n_b; v.n_ba = n_ba;
+    v.grid = reinterpret_cast<const prt_d2*>(o_grid);
+    v.rpair = reinterpret_cast<const prt_d2*>(o_rpair);
+    v.zpair = reinterpret_cast<const prt_d2*>(o_zpair);
+    v.bxpair = reinterpret_cast<const prt_d2*>(o_bx);
+    v.bvpair = reinterpret_cast<const prt_d2*>(o_bv);
+    v.ba_x = reinterpret_cast<const double*>(o_bax);
+    v.ba_c = reinterpret_cast<const double*>(o_bac);
+    v.r0 = rin[0]; v.r_inv = prt_inv_mean_step(rin, n_r);
+    v.z0 = zin[0]; v.z_inv = prt_inv_mean_step(zin, n_z);
+    v.b0 = depth_ranges[0]; v.b_inv = prt_inv_mean_step(depth_ranges, n_b);
+    // ray_bounding_box_event tolerances (integration_processes.py:280-303)
+    const double tol = 1e-6;
+    v.bb_zmax = zin[n_z - 1] + tol;
+    v.bb_zmin = zin[0] - tol;
+    v.bb_rmin = rin[0] - tol;
+    v.bb_rmax = rin[n_r - 1] + tol;
+    return 0;
+}
+
+// turn the offsets of `view` into pointers relative to `base` (host or device address)
+static inline prt_env_view prt_env_rebase(const prt_env_view& view, const void* base)
+{
+    prt_env_view v = view;
+    const unsigned char* b = static_cast<const unsigned char*>(base);
+    v.grid = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.grid));
+    v.rpair = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.rpair));
+    v.zpair = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.zpair));
+    v.bxpair = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.bxpair));
+    v.bvpair = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.bvpair));
+    v.ba_x = reinterpret_cast<const double*>(b + reinterpret_cast<size_t>(view.ba_x));
+    v.ba_c = reinterpret_cast<const double*>(b + reinterpret_cast<size_t>(view.ba_c));
+    return v;
+}

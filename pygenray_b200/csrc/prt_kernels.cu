@@ -1,0 +1,583 @@
+// prt_kernels.cu -- sm_100a kernels + the C ABI of libprt.so (include/prt.h).
+//
+// K1  prt_fan_kernel<SAVE>      one FP64 thread per launch angle: the whole ray (all solve_ivp
+//                               segments, events, reflections, save-grid resampling) in registers.
+// K2  prt_refine_round_kernel   one regula-falsi trial shot per active eigenray bracket.
+// K3  prt_count/fill_brackets   sign-change bracketing of the arrival table.
+//     prt_fp64_peak_kernel      DFMA-pipe microbenchmark (roofline denominator).
+//
+// No tensor cores on purpose: the path is a scalar adaptive ODE, not a contraction.  The
+// environment grid is read through the read-only (LDG.NC) path as 16-byte {c, dc/dz} nodes and
+// stays L1/L2 resident (DESIGN.md sections 2 and 5).
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+
+#include "../../include/prt.h"
+#include "prt_core.h"
+#include "prt_env_layout.h"
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+#define PRT_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(PRT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+    } while (0)
+
+struct prt_env {
+    int device;
+    void* dev_blob;
+    size_t bytes;
+    prt_env_view view;  // device pointers
+};
+
+// ---------------------------------------------------------------------------------------------
+// K1: the fan
+struct prt_fan_params {
+    int64_t n_rays;
+    const double* angles;
+    const double* y0;
+    double source_depth, source_range, receiver_range, rtol, atol;
+    int32_t terminate_backwards, n_save;
+    const double* range_save;
+    double* out_traj;
+    double* out_final;
+    int32_t* out_nb;
+    int32_t* out_ns;
+    int32_t* out_status;
+    uint32_t* out_counters;
+    int32_t max_bounces;
+};
+
+template <bool SAVE>
+__global__ void __launch_bounds__(128) prt_fan_kernel(const __grid_constant__ prt_env_view E,
+                                                      const __grid_constant__ prt_fan_params P)
+{
+    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= P.n_rays) return;
+    double T, z, p;
+    if (P.y0) {
+        T = P.y0[3 * ray];
+        z = P.y0[3 * ray + 1];
+        p = P.y0[3 * ray + 2];
+    } else {
+        prt_initial_state(E, P.source_depth, P.source_range, P.angles[ray], T, z, p);
+    }
+    prt_traj_sink sink;
+    sink.stride = 1;
+    sink.T = sink.z = sink.p = nullptr;
+    if (SAVE) {
+        const size_t plane = (size_t)P.n_rays * (size_t)P.n_save;
+        sink.T = P.out_traj + (size_t)ray * (size_t)P.n_save;
+        sink.z = sink.T + plane;
+        sink.p = sink.z + plane;
+    }
+    prt_ray_result res;
+    uint32_t cnt[PRT_CNT_N];
+    prt_integrate_ray<SAVE>(E, T, z, p, P.source_range, P.receiver_range, P.rtol, P.atol,
+                            P.terminate_backwards != 0, P.n_save, P.range_save, sink, P.max_bounces, res, cnt);
+    if (SAVE && res.status != PRT_RAY_OK) {
+        // the reference returns None for a dropped ray; leave no half-written trajectory behind
+        for (int i = 0; i < P.n_save; ++i) sink.put(i, NAN, NAN, NAN);
+    }
+    P.out_final[ray] = res.T;
+    P.out_final[P.n_rays + ray] = res.z;
+    P.out_final[2 * P.n_rays + ray] = res.p;
+    P.out_nb[ray] = res.n_bottom;
+    P.out_ns[ray] = res.n_surface;
+    P.out_status[ray] = res.status;
+    if (P.out_counters) {
+#pragma unroll
+        for (int k = 0; k < PRT_CNT_N; ++k) P.out_counters[(size_t)k * P.n_rays + ray] = cnt[k];
+    }
+}
+
+static int pick_block(int64_t n_units, int device)
+{
+    // spread small fans over all SMs: one warp per block until every SM has 4 warps
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (n_units <= (int64_t)sms * 4 * 32) return 32;
+    if (n_units <= (int64_t)sms * 8 * 64) return 64;
+    return 128;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: bracketing (eigenrays.py:62-79)
+__device__ __forceinline__ double prt_sign(double v) { return (double)((v > 0.0) - (v < 0.0)); }  // np.sign (NaN -> 0 here)
+
+__global__ void prt_count_brackets_kernel(int64_t n_rays, const double* __restrict__ z_end, int32_t n_rcv,
+                                          const double* __restrict__ rds, int32_t* __restrict__ counts)
+{
+    const int rcv = blockIdx.y;
+    const double rd = rds[rcv];
+    int local = 0;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_rays - 1;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        double a = z_end[k] + rd, b = z_end[k + 1] + rd;
+        // np.sign propagates NaN: NaN - x != 0 is True, so a NaN neighbour counts as a change
+        bool change = (a != a) || (b != b) || (prt_sign(b) - prt_sign(a) != 0.0);
+        local += change ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&counts[rcv], local);
+}
+
+// one block per receiver walks the fan in order so that brackets come out sorted by ray index
+__global__ void prt_fill_brackets_kernel(int64_t n_rays, const double* __restrict__ z_end,
+                                         const double* __restrict__ thetas, int32_t n_rcv,
+                                         const double* __restrict__ rds, const int64_t* __restrict__ offsets,
+                                         double* __restrict__ z1, double* __restrict__ z2, double* __restrict__ th1,
+                                         double* __restrict__ th2, double* __restrict__ brd, int32_t* __restrict__ brcv,
+                                         int64_t* __restrict__ bk)
+{
+    const int rcv = blockIdx.x;
+    const double rd = rds[rcv];
+    __shared__ int warp_tot[32];
+    __shared__ long long base;
+    if (threadIdx.x == 0) base = offsets[rcv];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int64_t start = 0; start < n_rays - 1; start += blockDim.x) {
+        int64_t k = start + threadIdx.x;
+        bool change = false;
+        if (k < n_rays - 1) {
+            double a = z_end[k] + rd, b = z_end[k + 1] + rd;
+            change = (a != a) || (b != b) || (prt_sign(b) - prt_sign(a) != 0.0);
+        }
+        unsigned ballot = __ballot_sync(0xffffffffu, change);
+        int within = __popc(ballot & ((1u << lane) - 1));
+        if (lane == 0) warp_tot[warp] = __popc(ballot);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < n_warps; ++w) {
+            if (w < warp) before += warp_tot[w];
+            total += warp_tot[w];
+        }
+        if (change) {
+            long long o = base + before + within;
+            z1[o] = z_end[k];
+            z2[o] = z_end[k + 1];
+            th1[o] = thetas[k];
+            th2[o] = thetas[k + 1];
+            brd[o] = rd;
+            brcv[o] = rcv;
+            bk[o] = k;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) base += total;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: regula falsi, one trial shot per active bracket per round (eigenrays.py:206-268)
+struct prt_refine_state {
+    double *z1, *z2, *th1, *th2, *th;  // [n_br]
+    int32_t *iter, *shots;             // [n_br]
+    int32_t *list_a, *list_b;          // active bracket ids (ping-pong)
+    int32_t* counters;                 // [2] active counts (ping-pong)
+};
+
+struct prt_refine_params {
+    int64_t n_br;
+    const double* rd;
+    double source_depth, source_range, receiver_range, rtol, atol, ztol;
+    int32_t terminate_backwards, max_iter, max_bounces;
+    double* out_theta;
+    double* out_final;
+    int32_t *out_nb, *out_ns, *out_status, *out_shots, *out_ray_status;
+};
+
+__global__ void prt_refine_init_kernel(prt_refine_state S, int64_t n_br, const double* __restrict__ z1,
+                                       const double* __restrict__ z2, const double* __restrict__ th1,
+                                       const double* __restrict__ th2, const double* __restrict__ rd,
+                                       prt_refine_params P)
+{
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) {
+        S.counters[0] = (int32_t)n_br;
+        S.counters[1] = 0;
+    }
+    if (b >= n_br) return;
+    S.z1[b] = z1[b];
+    S.z2[b] = z2[b];
+    S.th1[b] = th1[b];
+    S.th2[b] = th2[b];
+    // regula_falsi_thetas, eigenrays.py:118-120
+    S.th[b] = th1[b] - (z1[b] + rd[b]) * (th2[b] - th1[b]) / (z2[b] - z1[b]);
+    S.iter[b] = 0;
+    S.shots[b] = 0;
+    S.list_a[b] = (int32_t)b;
+    P.out_theta[b] = NAN;
+    P.out_final[b] = NAN;
+    P.out_final[n_br + b] = NAN;
+    P.out_final[2 * n_br + b] = NAN;
+    P.out_nb[b] = 0;
+    P.out_ns[b] = 0;
+    P.out_status[b] = PRT_EIG_MAX_ITER;
+    P.out_shots[b] = 0;
+    P.out_ray_status[b] = 0;
+}
+
+__global__ void __launch_bounds__(128) prt_refine_round_kernel(const __grid_constant__ prt_env_view E,
+                                                               const __grid_constant__ prt_refine_params P,
+                                                               prt_refine_state S, const int32_t* __restrict__ list_in,
+                                                               int32_t* __restrict__ list_out, const int32_t* n_in,
+                                                               int32_t* n_out)
+{
+    const int n_active = *n_in;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_active) return;
+    const int b = list_in[idx];
+    const double rd = P.rd[b];
+    double th = S.th[b];
+    double T, z, p;
+    prt_initial_state(E, P.source_depth, P.source_range, -th, T, z, p);  // shoot_ray negates, launch_rays.py:251
+    prt_traj_sink sink;
+    sink.T = sink.z = sink.p = nullptr;
+    sink.stride = 1;
+    prt_ray_result res;
+    prt_integrate_ray<false>(E, T, z, p, P.source_range, P.receiver_range, P.rtol, P.atol,
+                             P.terminate_backwards != 0, 0, nullptr, sink, P.max_bounces, res, nullptr);
+    const int shots = ++S.shots[b];
+    P.out_shots[b] = shots;
+    if (res.status != PRT_RAY_OK) {  // ray is None, eigenrays.py:241-245
+        P.out_status[b] = PRT_EIG_RAY_DROPPED;
+        P.out_ray_status[b] = res.status;
+        return;
+    }
+    const double zend = -res.z;  // ray.z[-1] (negative-z convention)
+    if (fabs(zend + rd) < P.ztol) {  // eigenrays.py:247-250
+        P.out_status[b] = PRT_EIG_CONVERGED;
+        P.out_theta[b] = th;
+        P.out_final[b] = res.T;
+        P.out_final[P.n_br + b] = res.z;
+        P.out_final[2 * P.n_br + b] = res.p;
+        P.out_nb[b] = res.n_bottom;
+        P.out_ns[b] = res.n_surface;
+        return;
+    }
+    double z1 = S.z1[b], z2 = S.z2[b], th1 = S.th1[b], th2 = S.th2[b];
+    if (prt_sign(zend + rd) == prt_sign(z1 + rd)) {  // eigenrays.py:253-259
+        z1 = zend;
+        th1 = th;
+        S.z1[b] = z1;
+        S.th1[b] = th1;
+    } else {
+        z2 = zend;
+        th2 = th;
+        S.z2[b] = z2;
+        S.th2[b] = th2;
+    }
+    S.th[b] = th1 - (z1 + rd) * (th2 - th1) / (z2 - z1);  // eigenrays.py:261-263
+    const int it = S.iter[b];
+    if (it > P.max_iter) {  // eigenrays.py:265-266
+        P.out_status[b] = PRT_EIG_MAX_ITER;
+        return;
+    }
+    S.iter[b] = it + 1;
+    list_out[atomicAdd(n_out, 1)] = b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 FMA-pipe peak: 8 independent DFMA chains per thread
+__global__ void prt_fp64_peak_kernel(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+           x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+            x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+        }
+    }
+    double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[0] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+extern "C" {
+
+int prt_abi_version(void) { return PRT_ABI_VERSION; }
+const char* prt_last_error(void) { return g_last_error.c_str(); }
+int64_t prt_launch_count(void) { return g_launches.load(); }
+
+int prt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int prt_env_create(int device, int32_t n_r, int32_t n_z, const double* rin, const double* zin, const double* cin,
+                   const double* cpin, int32_t n_b, const double* depth_ranges, const double* depths, int32_t n_ba,
+                   const double* ba_x, const double* ba_c, prt_env_t** out)
+{
+    if (!out || !rin || !zin || !cin || !cpin || !depth_ranges || !depths || !ba_x || !ba_c)
+        return fail(PRT_ERR_ARG, "prt_env_create: null pointer");
+    if (prt_device_count() <= device || device < 0)
+        return fail(PRT_ERR_NO_DEVICE, "prt_env_create: no such CUDA device (this library has no CPU path)");
+    prt_env_blob blob;
+    if (prt_env_pack(n_r, n_z, rin, zin, cin, cpin, n_b, depth_ranges, depths, n_ba, ba_x, ba_c, blob))
+        return fail(PRT_ERR_ARG, "prt_env_create: every grid needs at least 2 points");
+    PRT_CUDA(cudaSetDevice(device));
+    void* dev = nullptr;
+    PRT_CUDA(cudaMalloc(&dev, blob.bytes.size()));
+    cudaError_t e = cudaMemcpy(dev, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(dev);
+        return fail(PRT_ERR_CUDA, std::string("cudaMemcpy(env): ") + cudaGetErrorString(e));
+    }
+    prt_env* env = new prt_env;
+    env->device = device;
+    env->dev_blob = dev;
+    env->bytes = blob.bytes.size();
+    env->view = prt_env_rebase(blob.view, dev);
+    *out = env;
+    return PRT_SUCCESS;
+}
+
+int prt_env_destroy(prt_env_t* env)
+{
+    if (!env) return PRT_SUCCESS;
+    cudaSetDevice(env->device);
+    cudaFree(env->dev_blob);
+    delete env;
+    return PRT_SUCCESS;
+}
+
+int64_t prt_env_device_bytes(const prt_env_t* env) { return env ? (int64_t)env->bytes : 0; }
+
+int prt_shoot_fan(const prt_env_t* env, int64_t n_rays, const double* angles_dev, const double* y0_dev,
+                  double source_depth, double source_range, double receiver_range, double rtol, double atol,
+                  int32_t terminate_backwards, int32_t n_save, const double* range_save_dev, double* out_traj_dev,
+                  double* out_final_dev, int32_t* out_n_bottom_dev, int32_t* out_n_surface_dev,
+                  int32_t* out_status_dev, uint32_t* out_counters_dev, int32_t max_bounces, void* stream)
+{
+    if (!env) return fail(PRT_ERR_ARG, "prt_shoot_fan: null environment");
+    if (n_rays < 0) return fail(PRT_ERR_ARG, "prt_shoot_fan: n_rays < 0");
+    if (n_rays == 0) return PRT_SUCCESS;
+    if (!angles_dev && !y0_dev) return fail(PRT_ERR_ARG, "prt_shoot_fan: need angles_dev or y0_dev");
+    if (!out_final_dev || !out_n_bottom_dev || !out_n_surface_dev || !out_status_dev)
+        return fail(PRT_ERR_ARG, "prt_shoot_fan: null output pointer");
+    const bool save = (n_save > 0);
+    if (save && (n_save < 2 || !range_save_dev || !out_traj_dev))
+        return fail(PRT_ERR_ARG, "prt_shoot_fan: n_save >= 2, range_save_dev and out_traj_dev required to save");
+    if (!(source_range < receiver_range))
+        return fail(PRT_ERR_ARG, "prt_shoot_fan: source_range must be < receiver_range (mirror backwards shots)");
+    PRT_CUDA(cudaSetDevice(env->device));
+    prt_fan_params P;
+    P.n_rays = n_rays; P.angles = angles_dev; P.y0 = y0_dev;
+    P.source_depth = source_depth; P.source_range = source_range; P.receiver_range = receiver_range;
+    P.rtol = rtol; P.atol = atol; P.terminate_backwards = terminate_backwards; P.n_save = save ? n_save : 0;
+    P.range_save = range_save_dev; P.out_traj = out_traj_dev; P.out_final = out_final_dev;
+    P.out_nb = out_n_bottom_dev; P.out_ns = out_n_surface_dev; P.out_status = out_status_dev;
+    P.out_counters = out_counters_dev; P.max_bounces = max_bounces > 0 ? max_bounces : (1 << 20);
+    const int block = pick_block(n_rays, env->device);
+    const unsigned grid = (unsigned)((n_rays + block - 1) / block);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (save) prt_fan_kernel<true><<<grid, block, 0, s>>>(env->view, P);
+    else prt_fan_kernel<false><<<grid, block, 0, s>>>(env->view, P);
+    g_launches.fetch_add(1);
+    PRT_CUDA(cudaGetLastError());
+    return PRT_SUCCESS;
+}
+
+int prt_shoot_fan_host(const prt_env_t* env, int64_t n_rays, const double* angles, const double* y0,
+                       double source_depth, double source_range, double receiver_range, double rtol, double atol,
+                       int32_t terminate_backwards, int32_t n_save, const double* range_save, double* out_traj,
+                       double* out_final, int32_t* out_n_bottom, int32_t* out_n_surface, int32_t* out_status,
+                       uint32_t* out_counters, int32_t max_bounces)
+{
+    if (!env) return fail(PRT_ERR_ARG, "prt_shoot_fan_host: null environment");
+    if (n_rays <= 0) return n_rays == 0 ? PRT_SUCCESS : fail(PRT_ERR_ARG, "prt_shoot_fan_host: n_rays < 0");
+    PRT_CUDA(cudaSetDevice(env->device));
+    const bool save = n_save > 0 && out_traj && range_save;
+    const size_t n = (size_t)n_rays;
+    // one scratch allocation: inputs | outputs
+    size_t o_in = 0, in_bytes = (y0 ? 3 * n : n) * sizeof(double);
+    size_t o_rs = prt_align256(o_in + in_bytes);
+    size_t o_final = prt_align256(o_rs + (save ? (size_t)n_save * sizeof(double) : 0));
+    size_t o_nb = prt_align256(o_final + 3 * n * sizeof(double));
+    size_t o_ns = prt_align256(o_nb + n * sizeof(int32_t));
+    size_t o_st = prt_align256(o_ns + n * sizeof(int32_t));
+    size_t o_cnt = prt_align256(o_st + n * sizeof(int32_t));
+    size_t o_traj = prt_align256(o_cnt + (out_counters ? PRT_CNT_N * n * sizeof(uint32_t) : 0));
+    size_t total = o_traj + (save ? 3 * n * (size_t)n_save * sizeof(double) : 0);
+    unsigned char* d = nullptr;
+    PRT_CUDA(cudaMalloc(&d, total));
+    int rc = PRT_SUCCESS;
+    cudaError_t e = cudaMemcpy(d + o_in, y0 ? y0 : angles, in_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && save) e = cudaMemcpy(d + o_rs, range_save, (size_t)n_save * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = prt_shoot_fan(env, n_rays, y0 ? nullptr : (const double*)(d + o_in), y0 ? (const double*)(d + o_in) : nullptr,
+                           source_depth, source_range, receiver_range, rtol, atol, terminate_backwards,
+                           save ? n_save : 0, save ? (const double*)(d + o_rs) : nullptr,
+                           save ? (double*)(d + o_traj) : nullptr, (double*)(d + o_final), (int32_t*)(d + o_nb),
+                           (int32_t*)(d + o_ns), (int32_t*)(d + o_st), out_counters ? (uint32_t*)(d + o_cnt) : nullptr,
+                           max_bounces, nullptr);
+        if (rc == PRT_SUCCESS) {
+            e = cudaMemcpy(out_final, d + o_final, 3 * n * sizeof(double), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(out_n_bottom, d + o_nb, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(out_n_surface, d + o_ns, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) e = cudaMemcpy(out_status, d + o_st, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess && out_counters)
+                e = cudaMemcpy(out_counters, d + o_cnt, PRT_CNT_N * n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess && save)
+                e = cudaMemcpy(out_traj, d + o_traj, 3 * n * (size_t)n_save * sizeof(double), cudaMemcpyDeviceToHost);
+        }
+    }
+    cudaFree(d);
+    if (rc != PRT_SUCCESS) return rc;
+    if (e != cudaSuccess) return fail(PRT_ERR_CUDA, std::string("prt_shoot_fan_host: ") + cudaGetErrorString(e));
+    return PRT_SUCCESS;
+}
+
+int prt_count_brackets(int64_t n_rays, const double* z_end_dev, int32_t n_rcv, const double* receiver_depths_dev,
+                       int32_t* counts_dev, void* stream)
+{
+    if (n_rcv <= 0) return PRT_SUCCESS;
+    if (!z_end_dev || !receiver_depths_dev || !counts_dev) return fail(PRT_ERR_ARG, "prt_count_brackets: null pointer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PRT_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(int32_t) * (size_t)n_rcv, s));
+    if (n_rays < 2) return PRT_SUCCESS;
+    int64_t blocks = (n_rays - 1 + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    dim3 grid((unsigned)blocks, (unsigned)n_rcv);
+    prt_count_brackets_kernel<<<grid, 256, 0, s>>>(n_rays, z_end_dev, n_rcv, receiver_depths_dev, counts_dev);
+    g_launches.fetch_add(1);
+    PRT_CUDA(cudaGetLastError());
+    return PRT_SUCCESS;
+}
+
+int prt_fill_brackets(int64_t n_rays, const double* z_end_dev, const double* thetas_dev, int32_t n_rcv,
+                      const double* receiver_depths_dev, const int64_t* offsets_dev, double* br_z1_dev,
+                      double* br_z2_dev, double* br_th1_dev, double* br_th2_dev, double* br_rd_dev,
+                      int32_t* br_rcv_dev, int64_t* br_k_dev, void* stream)
+{
+    if (n_rcv <= 0 || n_rays < 2) return PRT_SUCCESS;
+    if (!z_end_dev || !thetas_dev || !receiver_depths_dev || !offsets_dev)
+        return fail(PRT_ERR_ARG, "prt_fill_brackets: null pointer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    prt_fill_brackets_kernel<<<(unsigned)n_rcv, 256, 0, s>>>(n_rays, z_end_dev, thetas_dev, n_rcv, receiver_depths_dev,
+                                                             offsets_dev, br_z1_dev, br_z2_dev, br_th1_dev, br_th2_dev,
+                                                             br_rd_dev, br_rcv_dev, br_k_dev);
+    g_launches.fetch_add(1);
+    PRT_CUDA(cudaGetLastError());
+    return PRT_SUCCESS;
+}
+
+int64_t prt_refine_workspace_bytes(int64_t n_br)
+{
+    if (n_br < 0) return 0;
+    size_t n = (size_t)n_br;
+    return (int64_t)(5 * prt_align256(n * sizeof(double)) + 4 * prt_align256(n * sizeof(int32_t)) + 256);
+}
+
+int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev, const double* z2_dev,
+                        const double* th1_dev, const double* th2_dev, const double* rd_dev, double source_depth,
+                        double source_range, double receiver_range, double rtol, double atol,
+                        int32_t terminate_backwards, double ztol, int32_t max_iter, double* out_theta_dev,
+                        double* out_final_dev, int32_t* out_n_bottom_dev, int32_t* out_n_surface_dev,
+                        int32_t* out_status_dev, int32_t* out_shots_dev, int32_t* out_ray_status_dev, void* work_dev,
+                        int32_t max_bounces, void* stream)
+{
+    if (!env) return fail(PRT_ERR_ARG, "prt_refine_brackets: null environment");
+    if (n_br < 0 || n_br > 0x7fffffff) return fail(PRT_ERR_ARG, "prt_refine_brackets: bad n_br");
+    if (n_br == 0) return PRT_SUCCESS;
+    if (!z1_dev || !z2_dev || !th1_dev || !th2_dev || !rd_dev || !out_theta_dev || !out_final_dev ||
+        !out_n_bottom_dev || !out_n_surface_dev || !out_status_dev || !out_shots_dev || !out_ray_status_dev || !work_dev)
+        return fail(PRT_ERR_ARG, "prt_refine_brackets: null pointer");
+    if (!(source_range < receiver_range))
+        return fail(PRT_ERR_ARG, "prt_refine_brackets: source_range must be < receiver_range");
+    PRT_CUDA(cudaSetDevice(env->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t n = (size_t)n_br;
+    unsigned char* w = static_cast<unsigned char*>(work_dev);
+    const size_t dsz = prt_align256(n * sizeof(double)), isz = prt_align256(n * sizeof(int32_t));
+    prt_refine_state S;
+    S.z1 = (double*)w; S.z2 = (double*)(w + dsz); S.th1 = (double*)(w + 2 * dsz); S.th2 = (double*)(w + 3 * dsz);
+    S.th = (double*)(w + 4 * dsz);
+    unsigned char* wi = w + 5 * dsz;
+    S.iter = (int32_t*)wi; S.shots = (int32_t*)(wi + isz); S.list_a = (int32_t*)(wi + 2 * isz);
+    S.list_b = (int32_t*)(wi + 3 * isz); S.counters = (int32_t*)(wi + 4 * isz);
+    prt_refine_params P;
+    P.n_br = n_br; P.rd = rd_dev; P.source_depth = source_depth; P.source_range = source_range;
+    P.receiver_range = receiver_range; P.rtol = rtol; P.atol = atol; P.ztol = ztol;
+    P.terminate_backwards = terminate_backwards; P.max_iter = max_iter;
+    P.max_bounces = max_bounces > 0 ? max_bounces : (1 << 20);
+    P.out_theta = out_theta_dev; P.out_final = out_final_dev; P.out_nb = out_n_bottom_dev; P.out_ns = out_n_surface_dev;
+    P.out_status = out_status_dev; P.out_shots = out_shots_dev; P.out_ray_status = out_ray_status_dev;
+    prt_refine_init_kernel<<<(unsigned)((n_br + 255) / 256), 256, 0, s>>>(S, n_br, z1_dev, z2_dev, th1_dev, th2_dev,
+                                                                          rd_dev, P);
+    g_launches.fetch_add(1);
+    PRT_CUDA(cudaGetLastError());
+    int32_t n_active = (int32_t)n_br;
+    int flip = 0;
+    // at most max_iter + 2 trial shots per bracket (eigenrays.py:265-268)
+    for (int round = 0; round < max_iter + 3 && n_active > 0; ++round) {
+        int32_t* list_in = flip ? S.list_b : S.list_a;
+        int32_t* list_out = flip ? S.list_a : S.list_b;
+        int32_t* n_in = S.counters + flip;
+        int32_t* n_out = S.counters + (1 - flip);
+        PRT_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int32_t), s));
+        const int block = pick_block(n_active, env->device);
+        const unsigned grid = (unsigned)((n_active + block - 1) / block);
+        prt_refine_round_kernel<<<grid, block, 0, s>>>(env->view, P, S, list_in, list_out, n_in, n_out);
+        g_launches.fetch_add(1);
+        PRT_CUDA(cudaGetLastError());
+        PRT_CUDA(cudaMemcpyAsync(&n_active, n_out, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        PRT_CUDA(cudaStreamSynchronize(s));
+        flip = 1 - flip;
+    }
+    return PRT_SUCCESS;
+}
+
+double prt_measure_fp64_peak(int device, int32_t iters)
+{
+    if (prt_device_count() <= device || device < 0) return -1.0;
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    double* out = nullptr;
+    if (cudaMalloc(&out, 8) != cudaSuccess) return -1.0;
+    const int threads = 512, blocks = sms * 4;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    prt_fp64_peak_kernel<<<blocks, threads>>>(out, 16, 1.0000001, 1e-9);  // warm-up
+    cudaEventRecord(a);
+    prt_fp64_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+    cudaEventRecord(b);
+    cudaError_t e = cudaEventSynchronize(b);
+    g_launches.fetch_add(2);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    if (e != cudaSuccess || ms <= 0.f) return -1.0;
+    double flops = 2.0 * 64.0 * (double)iters * (double)threads * (double)blocks;
+    return flops / (ms * 1e-3);
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// core_host.cpp -- TEST HARNESS: compiles the product's per-ray device routine (prt_core.h) for
+// the host with g++ so that `pytest -m "not gpu"` can compare it bit-for-bit with the CPU oracle
+// on a machine without a GPU.  Not part of the product: libprt.so never contains or calls this.
+#include <stdint.h>
+
+#include "../../pygenray_b200/csrc/prt_core.h"
+#include "../../pygenray_b200/csrc/prt_env_layout.h"
+
+extern "C" {
+
+struct hh_env {
+    prt_env_blob blob;
+    prt_env_view view;
+};
+
+__attribute__((visibility("default"))) void* hh_env_create(int n_r, int n_z, const double* rin, const double* zin,
+                                                            const double* cin, const double* cpin, int n_b,
+                                                            const double* depth_ranges, const double* depths,
+                                                            int n_ba, const double* ba_x, const double* ba_c)
+{
+    hh_env* e = new hh_env;
+    if (prt_env_pack(n_r, n_z, rin, zin, cin, cpin, n_b, depth_ranges, depths, n_ba, ba_x, ba_c, e->blob)) {
+        delete e;
+        return nullptr;
+    }
+    e->view = prt_env_rebase(e->blob.view, e->blob.bytes.data());
+    return e;
+}
+
+__attribute__((visibility("default"))) void hh_env_destroy(void* e) { delete static_cast<hh_env*>(e); }
+
+// same output layout as prt_shoot_fan: traj [3][n_rays][n_save], final [3][n_rays], counters [6][n_rays]
+__attribute__((visibility("default"))) int hh_shoot_fan(void* env, int64_t n_rays, const double* angles_deg,
+                                                         const double* y0s, double source_depth, double source_range,
+                                                         double receiver_range, double rtol, double atol,
+                                                         int terminate_backwards, int n_save, const double* range_save,
+                                                         double* out_traj, double* out_final, int32_t* out_nb,
+                                                         int32_t* out_ns, int32_t* out_status, uint32_t* out_counters,
+                                                         int max_bounces)
+{
+    const prt_env_view& E = static_cast<hh_env*>(env)->view;
+    for (int64_t i = 0; i < n_rays; ++i) {
+        double T, z, p;
+        if (y0s) {
+            T = y0s[3 * i]; z = y0s[3 * i + 1]; p = y0s[3 * i + 2];
+        } else {
+            prt_initial_state(E, source_depth, source_range, angles_deg[i], T, z, p);
+        }
+        prt_traj_sink sink{nullptr, nullptr, nullptr, 1};
+        prt_ray_result res;
+        uint32_t cnt[PRT_CNT_N];
+        if (out_traj && n_save > 0) {
+            sink.T = out_traj + ((size_t)0 * n_rays + i) * n_save;
+            sink.z = out_traj + ((size_t)1 * n_rays + i) * n_save;
+            sink.p = out_traj + ((size_t)2 * n_rays + i) * n_save;
+            for (int k = 0; k < n_save; ++k) sink.T[k] = sink.z[k] = sink.p[k] = NAN;
+            prt_integrate_ray<true>(E, T, z, p, source_range, receiver_range, rtol, atol, terminate_backwards != 0,
+                                    n_save, range_save, sink, max_bounces, res, cnt);
+        } else {
+            prt_integrate_ray<false>(E, T, z, p, source_range, receiver_range, rtol, atol, terminate_backwards != 0, 0,
+                                     nullptr, sink, max_bounces, res, cnt);
+        }
+        if (out_traj && n_save > 0 && res.status != PRT_RAY_OK)  // as prt_fan_kernel does for dropped rays
+            for (int k = 0; k < n_save; ++k) sink.T[k] = sink.z[k] = sink.p[k] = NAN;
+        out_final[0 * n_rays + i] = res.T;
+        out_final[1 * n_rays + i] = res.z;
+        out_final[2 * n_rays + i] = res.p;
+        out_nb[i] = res.n_bottom; out_ns[i] = res.n_surface; out_status[i] = res.status;
+        if (out_counters)
+            for (int k = 0; k < PRT_CNT_N; ++k) out_counters[(size_t)k * n_rays + i] = cnt[k];
+    }
+    return 0;
+}
+}
