@@ -40,6 +40,12 @@ extern "C" {
 
 #define PRT_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define PRT_API __attribute__((visibility("default")))
+#else
+#define PRT_API
+#endif
+
 /* return codes */
 #define PRT_SUCCESS 0
 #define PRT_ERR_ARG 1
@@ -73,11 +79,11 @@ extern "C" {
 
 typedef struct prt_env prt_env_t;
 
-int prt_abi_version(void);
-const char *prt_last_error(void);
+PRT_API int prt_abi_version(void);
+PRT_API const char *prt_last_error(void);
 
 /* number of visible CUDA devices (0 if none / no driver) */
-int prt_device_count(void);
+PRT_API int prt_device_count(void);
 
 /*
  * Stage one environment on `device`.  Inputs are HOST arrays exactly as returned by the
@@ -90,13 +96,13 @@ int prt_device_count(void);
  *   ba_x [n_ba]                spline breakpoints; ba_c [4][n_ba-1] coefficients, highest power
  *                              first, local variable (x - ba_x[i])
  */
-int prt_env_create(int device, int32_t n_r, int32_t n_z, const double *rin, const double *zin,
+PRT_API int prt_env_create(int device, int32_t n_r, int32_t n_z, const double *rin, const double *zin,
                    const double *cin, const double *cpin, int32_t n_b, const double *depth_ranges,
                    const double *depths, int32_t n_ba, const double *ba_x, const double *ba_c,
                    prt_env_t **out);
-int prt_env_destroy(prt_env_t *env);
+PRT_API int prt_env_destroy(prt_env_t *env);
 /* bytes of device memory held by the environment */
-int64_t prt_env_device_bytes(const prt_env_t *env);
+PRT_API int64_t prt_env_device_bytes(const prt_env_t *env);
 
 /*
  * Shoot a fan of n_rays launch angles from (source_range, source_depth) to receiver_range
@@ -111,23 +117,30 @@ int64_t prt_env_device_bytes(const prt_env_t *env);
  *   out_final_dev [3][n_rays]  exact final state (sols[-1].y[:, -1]); NaN for dropped rays
  *   out_n_bottom_dev, out_n_surface_dev, out_status_dev [n_rays] int32
  *   out_counters_dev [PRT_CNT_N][n_rays] uint32, or NULL
+ *   stored_convention          0: trajectory holds z, p as integrated (z positive down);
+ *                              1: holds -z, -p, the convention Ray/RayFan store (ray_objects.py:49-52)
+ *   out_p_sign_changes_dev [n_rays] int32 or NULL: number of sign changes of p along the saved
+ *                              grid, i.e. sum(diff(sign(ps)) != 0) of RayFan.compute_rayids
+ *                              (ray_objects.py:142-144); needs n_save > 0
  */
-int prt_shoot_fan(const prt_env_t *env, int64_t n_rays, const double *angles_dev, const double *y0_dev,
+PRT_API int prt_shoot_fan(const prt_env_t *env, int64_t n_rays, const double *angles_dev, const double *y0_dev,
                   double source_depth, double source_range, double receiver_range, double rtol, double atol,
                   int32_t terminate_backwards, int32_t n_save, const double *range_save_dev,
                   double *out_traj_dev, double *out_final_dev, int32_t *out_n_bottom_dev,
                   int32_t *out_n_surface_dev, int32_t *out_status_dev, uint32_t *out_counters_dev,
-                  int32_t max_bounces, void *stream);
+                  int32_t stored_convention, int32_t *out_p_sign_changes_dev, int32_t max_bounces,
+                  void *stream);
 
 /*
  * Same, HOST pointers in and out: stages the launch angles, runs the fan and copies the results
  * back (synchronous).  This is the call a non-Python host (C, Fortran, Julia via ccall) binds.
  */
-int prt_shoot_fan_host(const prt_env_t *env, int64_t n_rays, const double *angles, const double *y0,
+PRT_API int prt_shoot_fan_host(const prt_env_t *env, int64_t n_rays, const double *angles, const double *y0,
                        double source_depth, double source_range, double receiver_range, double rtol,
                        double atol, int32_t terminate_backwards, int32_t n_save, const double *range_save,
                        double *out_traj, double *out_final, int32_t *out_n_bottom, int32_t *out_n_surface,
-                       int32_t *out_status, uint32_t *out_counters, int32_t max_bounces);
+                       int32_t *out_status, uint32_t *out_counters, int32_t stored_convention,
+                       int32_t *out_p_sign_changes, int32_t max_bounces);
 
 /*
  * Eigenray bracketing (eigenrays.py:62-79): for every receiver depth, find adjacent surviving fan
@@ -139,9 +152,9 @@ int prt_shoot_fan_host(const prt_env_t *env, int64_t n_rays, const double *angle
  * offsets_dev[n_rcv] (caller), prt_fill_brackets writes, in (receiver, ray) order,
  *   br_z1/z2/th1/th2/rd [n_brackets] and br_rcv [n_brackets] (receiver index).
  */
-int prt_count_brackets(int64_t n_rays, const double *z_end_dev, int32_t n_rcv,
+PRT_API int prt_count_brackets(int64_t n_rays, const double *z_end_dev, int32_t n_rcv,
                        const double *receiver_depths_dev, int32_t *counts_dev, void *stream);
-int prt_fill_brackets(int64_t n_rays, const double *z_end_dev, const double *thetas_dev, int32_t n_rcv,
+PRT_API int prt_fill_brackets(int64_t n_rays, const double *z_end_dev, const double *thetas_dev, int32_t n_rcv,
                       const double *receiver_depths_dev, const int64_t *offsets_dev, double *br_z1_dev,
                       double *br_z2_dev, double *br_th1_dev, double *br_th2_dev, double *br_rd_dev,
                       int32_t *br_rcv_dev, int64_t *br_k_dev, void *stream);
@@ -156,8 +169,8 @@ int prt_fill_brackets(int64_t n_rays, const double *z_end_dev, const double *the
  *   out_shots_dev [n_br], out_ray_status_dev [n_br] (PRT_RAY_* of the dropped trial)
  * Synchronous with respect to the host (the round loop reads the active count back).
  */
-int64_t prt_refine_workspace_bytes(int64_t n_br);
-int prt_refine_brackets(const prt_env_t *env, int64_t n_br, const double *z1_dev, const double *z2_dev,
+PRT_API int64_t prt_refine_workspace_bytes(int64_t n_br);
+PRT_API int prt_refine_brackets(const prt_env_t *env, int64_t n_br, const double *z1_dev, const double *z2_dev,
                         const double *th1_dev, const double *th2_dev, const double *rd_dev,
                         double source_depth, double source_range, double receiver_range, double rtol,
                         double atol, int32_t terminate_backwards, double ztol, int32_t max_iter,
@@ -166,12 +179,12 @@ int prt_refine_brackets(const prt_env_t *env, int64_t n_br, const double *z1_dev
                         int32_t *out_ray_status_dev, void *work_dev, int32_t max_bounces, void *stream);
 
 /* number of kernels this library has launched in the calling process (monotonic; for bench.py) */
-int64_t prt_launch_count(void);
+PRT_API int64_t prt_launch_count(void);
 
 /* FP64 FMA-pipe microbenchmark: runs `iters` dependent-chain DFMA rounds on every SM and returns
  * the achieved FLOP/s (2 flops per FMA), or a negative value on error.  Used as the roofline
  * denominator of bench.py (MEASURED_PEAKS.json has no FP64 figure). */
-double prt_measure_fp64_peak(int device, int32_t iters);
+PRT_API double prt_measure_fp64_peak(int device, int32_t iters);
 
 #ifdef __cplusplus
 }

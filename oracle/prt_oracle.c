@@ -23,7 +23,10 @@
  * operation written below is one correctly rounded operation; fma() is used exactly where
  * written and nowhere else (compile with -ffp-contract=off); +,-,*,/,sqrt,fma only, plus the
  * three elementary functions det_pow_m02 / det_sin / det_asin defined in this file from those
- * operations.  The reference evaluates the same expressions through NumPy/BLAS dot products and
+ * operations; three divisions of the reference are written as multiplications by a correctly
+ * rounded reciprocal (interpolation weights, dense-output abscissa, fact/c^2 in derivsrd: marked
+ * "contract:" below), as LLVM fast-math is free to do for the reference's own Numba code.
+ * The reference evaluates the same expressions through NumPy/BLAS dot products and
  * LLVM fast-math code whose association is not specified, so agreement
  * with the reference is to tolerance, while agreement of the CUDA path with this file is
  * bit-for-bit.
@@ -210,8 +213,9 @@ static double bilinear_interp(double x, double y, const double *xg, int nx, cons
     if (i < 0) i = 0;
     if (j > ny - 2) j = ny - 2;
     if (j < 0) j = 0;
-    double wx = (x - xg[i]) / (xg[i + 1] - xg[i]);
-    double wy = (y - yg[j]) / (yg[j + 1] - yg[j]);
+    /* contract: the weight division is a multiplication by the correctly rounded cell reciprocal */
+    double wx = (x - xg[i]) * (1.0 / (xg[i + 1] - xg[i]));
+    double wy = (y - yg[j]) * (1.0 / (yg[j + 1] - yg[j]));
     double v00 = values[(size_t)i * ny + j];
     double v10 = values[(size_t)(i + 1) * ny + j];
     double v01 = values[(size_t)i * ny + j + 1];
@@ -230,7 +234,7 @@ static double linear_interp(double x, const double *xin, const double *yin, int 
     int i = searchsorted_left(xin, n, x) - 1;
     if (i > n - 2) i = n - 2;
     if (i < 0) i = 0;
-    double w = (x - xin[i]) / (xin[i + 1] - xin[i]);
+    double w = (x - xin[i]) * (1.0 / (xin[i + 1] - xin[i]));
     return fma(w, yin[i + 1], (1.0 - w) * yin[i]);
 }
 
@@ -251,10 +255,13 @@ static void derivsrd(const orc_env *E, double x, const double *y, double *dydx, 
     double c2 = c * c;
     double arg = fma(-c2, pz * pz, 1.0);
     if (arg <= 0.0) arg = 1e-30;
-    double fact = 1.0 / sqrt(arg);
-    dydx[0] = fact / c;
-    dydx[1] = (c * pz) * fact;
-    dydx[2] = ((-fact) * cp) / c2;
+    /* contract: fact / c^2 is formed once as u = 1 / (c^2 sqrt(arg)); then
+     * [fact/c, c*pz*fact, -fact*cp/c^2] = [c u, c^2 (c u) pz, -cp u] */
+    double u = 1.0 / (c2 * sqrt(arg));
+    double t1 = c * u;
+    dydx[0] = t1;
+    dydx[1] = (c2 * t1) * pz;
+    dydx[2] = (-cp) * u;
     cnt[CNT_NFEV]++;
 }
 
@@ -343,7 +350,7 @@ typedef struct {
 
 static void dense_eval(const dense_t *d, double t, double *y)
 {
-    double x = (t - d->t_old) / d->h;
+    double x = (t - d->t_old) * (1.0 / d->h); /* contract: division by h as a multiplication by 1/h */
     double p1 = x, p2 = p1 * x, p3 = p2 * x, p4 = p3 * x; /* np.cumprod */
     for (int k = 0; k < 3; ++k) {
         double acc = d->Q[k][0] * p1;

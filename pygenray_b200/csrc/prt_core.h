@@ -5,9 +5,10 @@
 // scipy.integrate.solve_ivp(RK45, rtol, atol=1e-6, 4 terminal events, dense_output=True) segments
 // (launch_rays.py:593-681; scipy 1.18.1 integrate/_ivp/{rk,ivp,common,base}.py) joined by specular
 // reflections.  The structure here is NOT the reference's: there is no solver object, no list of
-// interpolants and no post-hoc resampling -- the ray streams through registers, the sound-speed
-// lookup is shared between c and dc/dz, events reuse the sound speed of the FSAL stage, asin is
-// replaced by exact threshold tests, and save points are emitted while stepping.
+// interpolants and no post-hoc resampling -- the ray is a register-resident state machine
+// (prt_ray) whose phases a warp executes in lock step, the sound-speed lookup is shared between c
+// and dc/dz, events reuse the sound speed of the FSAL stage, asin is replaced by exact threshold
+// tests, and save points are emitted while stepping.
 //
 // Rounding contract ("PRT arithmetic"): IEEE binary64, every written
 // operation is one correctly rounded +,-,*,/,sqrt or fma; fma only where PRT_FMA is written
@@ -92,6 +93,9 @@ struct prt_env_view {
     const prt_d2* zpair;    // [n_z-1] {zin[j], zin[j+1]}
     const prt_d2* bxpair;   // [n_b-1] {depth_ranges[i], depth_ranges[i+1]}
     const prt_d2* bvpair;   // [n_b-1] {depths[i], depths[i+1]}
+    const double* rrecip;   // [n_r-1] 1 / (rin[i+1] - rin[i])
+    const double* zrecip;   // [n_z-1] 1 / (zin[j+1] - zin[j])
+    const double* brecip;   // [n_b-1] 1 / (depth_ranges[i+1] - depth_ranges[i])
     const double* ba_x;     // [n_ba] bottom-angle spline breakpoints
     const double* ba_c;     // [4][n_ba-1] PPoly coefficients, highest power first
     double r0, r_inv, z0, z_inv, b0, b_inv;  // cell-index guesses: (v - x0) * inv (any value is correct)
@@ -269,19 +273,21 @@ PRT_HD int prt_locate(const prt_d2* pair, int n, double x0, double inv, double v
 }
 
 // c(x, z) and dc/dz(x, z): bilinear_interp (integration_processes.py:101-174) evaluated ONCE for
-// both fields (the reference evaluates it twice with identical weights, :86-87).
+// both fields (the reference evaluates it twice with identical weights, :86-87).  The weight
+// divisions use the per-cell reciprocals 1/(x[i+1]-x[i]) tabulated at staging time.
 PRT_HD void prt_field(const prt_env_view& E, double x, double z, double& c, double& cz)
 {
     prt_d2 re, ze;
     int i = prt_locate(E.rpair, E.n_r, E.r0, E.r_inv, x, re);
     int j = prt_locate(E.zpair, E.n_z, E.z0, E.z_inv, z, ze);
     const prt_d2* g = E.grid + ((size_t)i * (size_t)E.n_z + (size_t)j);
+    double ir = prt_ld(E.rrecip + i), iz = prt_ld(E.zrecip + j);
     prt_d2 v00 = prt_ld2(g);
     prt_d2 v01 = prt_ld2(g + 1);
     prt_d2 v10 = prt_ld2(g + E.n_z);
     prt_d2 v11 = prt_ld2(g + E.n_z + 1);
-    double wx = (x - re.x) / (re.y - re.x);
-    double wy = (z - ze.x) / (ze.y - ze.x);
+    double wx = (x - re.x) * ir;
+    double wy = (z - ze.x) * iz;
     double ax = 1.0 - wx, ay = 1.0 - wy;
     double w00 = ax * ay, w10 = wx * ay, w01 = ax * wy, w11 = wx * wy;
     double a = w00 * v00.x;
@@ -302,11 +308,12 @@ PRT_HD double prt_bathy(const prt_env_view& E, double x)
     prt_d2 xe;
     int i = prt_locate(E.bxpair, E.n_b, E.b0, E.b_inv, x, xe);
     prt_d2 v = prt_ld2(E.bvpair + i);
-    double w = (x - xe.x) / (xe.y - xe.x);
+    double w = (x - xe.x) * prt_ld(E.brecip + i);
     return PRT_FMA(w, v.y, (1.0 - w) * v.x);
 }
 
-// derivsrd (integration_processes.py:26-98); also returns c for event reuse
+// derivsrd (integration_processes.py:26-98) with one square root and one reciprocal:
+//   u = 1 / (c^2 sqrt(arg));  dT = c u;  dz = c^2 dT p;  dp = -cz u          (also returns c)
 PRT_HD void prt_rhs(const prt_env_view& E, double x, double z, double p, double& dT, double& dz, double& dp,
                     double& c_out)
 {
@@ -315,10 +322,11 @@ PRT_HD void prt_rhs(const prt_env_view& E, double x, double z, double p, double&
     double c2 = c * c;
     double arg = PRT_FMA(-c2, p * p, 1.0);
     if (arg <= 0.0) arg = 1e-30;
-    double fact = 1.0 / sqrt(arg);
-    dT = fact / c;
-    dz = (c * p) * fact;
-    dp = ((-fact) * cz) / c2;
+    double u = 1.0 / (c2 * sqrt(arg));
+    double t1 = c * u;
+    dT = t1;
+    dz = (c2 * t1) * p;
+    dp = (-cz) * u;
     c_out = c;
 }
 
@@ -399,6 +407,7 @@ PRT_HD bool prt_event_one(const prt_env_view& E, int which, double x, double z, 
 #define C5 (8.0 / 9)
 
 #define PRT_SQRT3 1.7320508075688772
+#define PRT_EPS 2.220446049250313e-16
 
 PRT_HD double prt_rms3(double a, double b, double c)
 {
@@ -439,7 +448,7 @@ PRT_HD prt_q3 prt_dense_q(double k1, double k3, double k4, double k5, double k6,
     return q;
 }
 
-// RkDenseOutput._call_impl (scipy rk.py:715-737) for one component
+// RkDenseOutput._call_impl (scipy rk.py:715-737) for one component; xx = (t - t_old) * (1/h)
 PRT_HD double prt_dense_eval(double q0, const prt_q3& q, double h, double y_old, double p1, double p2, double p3,
                              double p4)
 {
@@ -507,17 +516,18 @@ PRT_HD int prt_argmin_from(const double* rs, int n, int start, double v)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Trajectory sink: stores save point i of this ray.  kernels pass a strided global-memory sink.
+// Trajectory sink: stores save point i of this ray.
 struct prt_traj_sink {
     double* T;       // &out_T[ray][0]
     double* z;
     double* p;
     int64_t stride;  // element stride between consecutive save points of one ray
+    double sgn;      // +1: ODE convention; -1: stored convention (-z, -p) of ray_objects.py:49-52
     PRT_HD void put(int i, double vT, double vz, double vp) const
     {
         T[(int64_t)i * stride] = vT;
-        z[(int64_t)i * stride] = vz;
-        p[(int64_t)i * stride] = vp;
+        z[(int64_t)i * stride] = vz * sgn;
+        p[(int64_t)i * stride] = vp * sgn;
     }
 };
 
@@ -526,290 +536,322 @@ struct prt_ray_result {
     int32_t n_bottom, n_surface, status;
 };
 
-//
-// The ray.  SAVE = emit the num_range_save resampling of _interpolate_ray while stepping.
-//
+// problem constants shared by every ray of a launch
+struct prt_shot {
+    double x_end, rtol, atol;
+    int32_t terminate_backwards, n_save, max_bounces;
+    const double* range_save;
+};
+
+// ---------------------------------------------------------------------------------------------
+// One ray as a small state machine.  The same per-ray arithmetic is driven either ray by ray
+// (prt_integrate_ray, used for host-side parity tests) or warp-synchronously (prt_integrate_warp
+// in prt_kernels.cu), where lanes always execute step attempts together and lanes that hit a
+// boundary wait for one another so that the event root searches also run together.
+enum { PRT_PH_INIT = 0, PRT_PH_STEP = 1, PRT_PH_ROOT = 2, PRT_PH_DONE = 3 };
+
 template <bool SAVE>
-PRT_HD void prt_integrate_ray(const prt_env_view& E, double T, double z, double p, double x0, double x_end,
-                              double rtol, double atol, bool terminate_backwards, int n_save,
-                              const double* range_save, const prt_traj_sink& sink, int max_bounces,
-                              prt_ray_result& res, uint32_t* cnt)
-{
-    if (rtol < 100.0 * 2.220446049250313e-16) rtol = 100.0 * 2.220446049250313e-16;  // validate_tol
-    double x = x0;
-    int n_surface = 0, n_bottom = 0, status = PRT_RAY_OK;
-    int cursor = 0;  // first save index not yet owned by a finished segment
-    uint32_t c_nfev = 0, c_att = 0, c_acc = 0, c_seg = 0, c_bis = 0, c_dense = 0;
+struct prt_ray {
+    // persistent ODE state (solver.t, solver.y, solver.f, solver.h_abs)
+    double t, T, z, p, f0, f1, f2, h_abs;
+    // last accepted step, valid between attempt() == accepted and advance()/finish_terminal()
+    double t_old, t_new, h, inv_h, yT, yz, yp, nf0, nf1, nf2;
+    prt_q3 qT, qz, qp;
+    double root;
+    int32_t g, active, event, n_ts, cursor, n_surface, n_bottom, status, phase;
+    bool rejected, finished;
+    uint32_t c_nfev, c_att, c_acc, c_seg, c_bis, c_dense;
 
-    while (x < x_end) {  // launch_rays.py:404 -- one iteration per solve_ivp segment
+    PRT_HD void start(double T0, double z0, double p0, double x0, const prt_shot& S)
+    {
+        t = x0; T = T0; z = z0; p = p0;
+        n_surface = n_bottom = 0;
+        status = PRT_RAY_OK;
+        cursor = 0;
+        c_nfev = c_att = c_acc = c_seg = c_bis = c_dense = 0;
+        event = -1; active = 0; finished = false; rejected = false;
+        phase = (x0 < S.x_end) ? PRT_PH_INIT : PRT_PH_DONE;  // launch_rays.py:404
+    }
+
+    // RK45.__init__ (rk.py:85-103) + select_initial_step (common.py:68-134) + g = [event(t0, y0)]
+    PRT_HD void seg_init(const prt_env_view& E, const prt_shot& S)
+    {
         ++c_seg;
-        // ---- RK45.__init__ (rk.py:85-103): f0 and select_initial_step (common.py:68-134)
-        double t = x;
-        double f0, f1, f2, c_here;
+        double c_here;
         prt_rhs(E, t, z, p, f0, f1, f2, c_here);
-        ++c_nfev;
-        int g = prt_events(E, t, z, p, c_here);  // g = [event(t0, y0)]  ivp.py:641
-        double h_abs;
-        {
-            double interval = fabs(x_end - t);
-            double s0 = PRT_FMA(fabs(T), rtol, atol), s1 = PRT_FMA(fabs(z), rtol, atol), s2 = PRT_FMA(fabs(p), rtol, atol);
-            double d0 = prt_rms3(T / s0, z / s1, p / s2);
-            double d1 = prt_rms3(f0 / s0, f1 / s1, f2 / s2);
-            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (0.01 * d0) / d1;
-            h0 = prt_py_min(h0, interval);
-            double g0, g1, g2, cc;
-            prt_rhs(E, t + h0, PRT_FMA(h0, f1, z), PRT_FMA(h0, f2, p), g0, g1, g2, cc);
-            ++c_nfev;
-            double d2 = prt_rms3((g0 - f0) / s0, (g1 - f1) / s1, (g2 - f2) / s2) / h0;
-            double h1;
-            if (d1 <= 1e-15 && d2 <= 1e-15) h1 = prt_py_max(1e-6, h0 * 1e-3);
-            else h1 = 1.0 / prt_pow_m02(0.01 / prt_py_max(d1, d2));
-            h_abs = prt_py_min(prt_py_min(100.0 * h0, h1), interval);
-        }
-        int n_ts = 1;             // len(ts) of this segment
-        int event = -1;           // terminal event of this segment
-        bool finished = false;
+        g = prt_events(E, t, z, p, c_here);
+        double interval = fabs(S.x_end - t);
+        double s0 = PRT_FMA(fabs(T), S.rtol, S.atol), s1 = PRT_FMA(fabs(z), S.rtol, S.atol),
+               s2 = PRT_FMA(fabs(p), S.rtol, S.atol);
+        double d0 = prt_rms3(T / s0, z / s1, p / s2);
+        double d1 = prt_rms3(f0 / s0, f1 / s1, f2 / s2);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (0.01 * d0) / d1;
+        h0 = prt_py_min(h0, interval);
+        double g0, g1, g2, cc;
+        prt_rhs(E, t + h0, PRT_FMA(h0, f1, z), PRT_FMA(h0, f2, p), g0, g1, g2, cc);
+        c_nfev += 2;
+        double d2 = prt_rms3((g0 - f0) / s0, (g1 - f1) / s1, (g2 - f2) / s2) / h0;
+        double h1;
+        if (d1 <= 1e-15 && d2 <= 1e-15) h1 = prt_py_max(1e-6, h0 * 1e-3);
+        else h1 = 1.0 / prt_pow_m02(0.01 / prt_py_max(d1, d2));
+        h_abs = prt_py_min(prt_py_min(100.0 * h0, h1), interval);
+        n_ts = 1;
+        event = -1;
+        rejected = false;
+        phase = PRT_PH_STEP;
+    }
 
-        for (;;) {  // ivp.py:659 -- one iteration per accepted step
-            // ---- _step_impl (rk.py:111-176)
-            double min_step = 10.0 * fabs(prt_next_up(t) - t);
-            if (h_abs < min_step) h_abs = min_step;
-            bool rejected = false, failed = false;
-            double h = 0.0, t_new = t, yT = T, yz = z, yp = p;
-            double k2T, k2z, k2p, k3T, k3z, k3p, k4T, k4z, k4p, k5T, k5z, k5p, k6T, k6z, k6p, k7T, k7z, k7p, c_new;
-            for (;;) {
-                if (h_abs < min_step) {
-                    failed = true;
-                    break;
-                }
-                ++c_att;
-                t_new = t + h_abs;
-                if (t_new - x_end > 0.0) t_new = x_end;
-                h = t_new - t;
-                h_abs = fabs(h);
-                double cc, a, b;
-                // stage 2
-                prt_rhs(E, PRT_FMA(C2, h, t), PRT_FMA(h, A21 * f1, z), PRT_FMA(h, A21 * f2, p), k2T, k2z, k2p, cc);
-                // stage 3
-                a = A31 * f1; a = PRT_FMA(A32, k2z, a);
-                b = A31 * f2; b = PRT_FMA(A32, k2p, b);
-                prt_rhs(E, PRT_FMA(C3, h, t), PRT_FMA(h, a, z), PRT_FMA(h, b, p), k3T, k3z, k3p, cc);
-                // stage 4
-                a = A41 * f1; a = PRT_FMA(A42, k2z, a); a = PRT_FMA(A43, k3z, a);
-                b = A41 * f2; b = PRT_FMA(A42, k2p, b); b = PRT_FMA(A43, k3p, b);
-                prt_rhs(E, PRT_FMA(C4, h, t), PRT_FMA(h, a, z), PRT_FMA(h, b, p), k4T, k4z, k4p, cc);
-                // stage 5
-                a = A51 * f1; a = PRT_FMA(A52, k2z, a); a = PRT_FMA(A53, k3z, a); a = PRT_FMA(A54, k4z, a);
-                b = A51 * f2; b = PRT_FMA(A52, k2p, b); b = PRT_FMA(A53, k3p, b); b = PRT_FMA(A54, k4p, b);
-                prt_rhs(E, PRT_FMA(C5, h, t), PRT_FMA(h, a, z), PRT_FMA(h, b, p), k5T, k5z, k5p, cc);
-                // stage 6 (c = 1)
-                a = A61 * f1; a = PRT_FMA(A62, k2z, a); a = PRT_FMA(A63, k3z, a); a = PRT_FMA(A64, k4z, a); a = PRT_FMA(A65, k5z, a);
-                b = A61 * f2; b = PRT_FMA(A62, k2p, b); b = PRT_FMA(A63, k3p, b); b = PRT_FMA(A64, k4p, b); b = PRT_FMA(A65, k5p, b);
-                prt_rhs(E, PRT_FMA(1.0, h, t), PRT_FMA(h, a, z), PRT_FMA(h, b, p), k6T, k6z, k6p, cc);
-                // y_new
-                double sT = B1 * f0; sT = PRT_FMA(B3, k3T, sT); sT = PRT_FMA(B4, k4T, sT); sT = PRT_FMA(B5, k5T, sT); sT = PRT_FMA(B6, k6T, sT);
-                double sz = B1 * f1; sz = PRT_FMA(B3, k3z, sz); sz = PRT_FMA(B4, k4z, sz); sz = PRT_FMA(B5, k5z, sz); sz = PRT_FMA(B6, k6z, sz);
-                double sp = B1 * f2; sp = PRT_FMA(B3, k3p, sp); sp = PRT_FMA(B4, k4p, sp); sp = PRT_FMA(B5, k5p, sp); sp = PRT_FMA(B6, k6p, sp);
-                yT = PRT_FMA(h, sT, T);
-                yz = PRT_FMA(h, sz, z);
-                yp = PRT_FMA(h, sp, p);
-                // f_new (FSAL stage 7)
-                prt_rhs(E, t + h, yz, yp, k7T, k7z, k7p, c_new);
-                c_nfev += 6;
-                // error norm (rk.py:105-109, 145-147)
-                double eT = E1 * f0; eT = PRT_FMA(E3, k3T, eT); eT = PRT_FMA(E4, k4T, eT); eT = PRT_FMA(E5, k5T, eT); eT = PRT_FMA(E6, k6T, eT); eT = PRT_FMA(E7, k7T, eT);
-                double ez = E1 * f1; ez = PRT_FMA(E3, k3z, ez); ez = PRT_FMA(E4, k4z, ez); ez = PRT_FMA(E5, k5z, ez); ez = PRT_FMA(E6, k6z, ez); ez = PRT_FMA(E7, k7z, ez);
-                double ep = E1 * f2; ep = PRT_FMA(E3, k3p, ep); ep = PRT_FMA(E4, k4p, ep); ep = PRT_FMA(E5, k5p, ep); ep = PRT_FMA(E6, k6p, ep); ep = PRT_FMA(E7, k7p, ep);
-                double scT = PRT_FMA(prt_np_maximum(fabs(T), fabs(yT)), rtol, atol);
-                double scz = PRT_FMA(prt_np_maximum(fabs(z), fabs(yz)), rtol, atol);
-                double scp = PRT_FMA(prt_np_maximum(fabs(p), fabs(yp)), rtol, atol);
-                double err = prt_rms3((eT * h) / scT, (ez * h) / scz, (ep * h) / scp);
-                if (err < 1.0) {
-                    double factor = (err == 0.0) ? 10.0 : prt_py_min(10.0, 0.9 * prt_pow_m02(err));
-                    if (rejected) factor = prt_py_min(1.0, factor);
-                    h_abs *= factor;
-                    break;
-                }
-                h_abs *= prt_py_max(0.2, 0.9 * prt_pow_m02(err));
-                rejected = true;
-            }
-            if (failed) {
+    // One attempt of _step_impl (rk.py:111-176).  Returns true when the step was accepted; then the
+    // step record (t_old .. nf2, events, dense output if needed) is filled in.
+    PRT_HD bool attempt(const prt_env_view& E, const prt_shot& S)
+    {
+        const double min_step = 10.0 * fabs(prt_next_up(t) - t);
+        if (rejected) {
+            if (h_abs < min_step) {  // TOO_SMALL_STEP -> solve_ivp status -1
                 status = PRT_RAY_STEP_TOO_SMALL;
-                break;
+                phase = PRT_PH_DONE;
+                return false;
             }
-            ++c_acc;
-            const double t_old = t;
-            finished = (t_new - x_end >= 0.0);  // base.py:205-206
-
-            // ---- events at the step end (ivp.py:678-699); c(t_new, y_new) comes from the FSAL stage,
-            // which was evaluated at t + h: identical unless the clipped step made t + h != t_new
-            if (t + h != t_new) {
-                double cz_unused;
-                prt_field(E, t_new, yz, c_new, cz_unused);
-            }
-            int g_new = prt_events(E, t_new, yz, yp, c_new);
-            // find_active_events (ivp.py:134-157): up for direction +1, up|down for direction 0
-            int up = (~g) & g_new, down = g & (~g_new);
-            int active = (up & (PRT_EV_SURFACE | PRT_EV_BOTTOM)) | ((up | down) & (PRT_EV_VERTICAL | PRT_EV_BBOX));
-            g = g_new;
-
-            // dense output is needed if an event fired or a save point lies in (t_old, t_new]
-            bool need_dense = (active != 0);
-            if (SAVE && !need_dense) need_dense = (cursor < n_save - 1) && (prt_ld(range_save + cursor) <= t_new);
-            prt_q3 qT = {0.0, 0.0, 0.0}, qz = qT, qp = qT;
-            if (need_dense) {
-                ++c_dense;
-                qT = prt_dense_q(f0, k3T, k4T, k5T, k6T, k7T);
-                qz = prt_dense_q(f1, k3z, k4z, k5z, k6z, k7z);
-                qp = prt_dense_q(f2, k3p, k4p, k5p, k6p, k7p);
-            }
-
-            bool terminal = false, popped = false;
-            double root = t_new;
-            if (active) {
-                // handle_events (ivp.py:80-131): every event is terminal -> earliest root, ties to
-                // the lower event index.  solve_event_equation = brentq on a +-1 function = bisection.
-                double best_root = 0.0;
-                int best = -1;
-                for (int e = 0; e < 4 && status == PRT_RAY_OK; ++e) {
-                    if (!(active & (1 << e))) continue;
-                    // brentq(f, t_old, t_new, xtol=4eps, rtol=4eps, maxiter=100)
-                    double xpre = t_old, xcur = t_new, xblk = 0.0;
-                    bool fpre, fcur, fblk = false;
-                    {
-                        // f(t_old): x = 0 -> y_old exactly;  f(t_new): x = (t_new - t_old)/h
-                        fpre = prt_event_one(E, e, t_old, PRT_FMA(h, 0.0, z), PRT_FMA(h, 0.0, p));
-                        double xx = (t_new - t_old) / h;
-                        double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
-                        fcur = prt_event_one(E, e, t_new, prt_dense_eval(f1, qz, h, z, p1, p2, p3, p4),
-                                             prt_dense_eval(f2, qp, h, p, p1, p2, p3, p4));
-                        c_bis += 2;
-                    }
-                    if (fpre == fcur) {
-                        status = PRT_RAY_BRENTQ_SIGN;
-                        break;
-                    }
-                    double rootv = 0.0;
-                    bool converged = false;
-                    for (int i = 0; i < 100; ++i) {
-                        if (fpre != fcur) {
-                            xblk = xpre;
-                            fblk = fpre;
-                        }
-                        // |f| == 1 always: the "fabs(fblk) < fabs(fcur)" swap never happens
-                        double delta = (4 * 2.220446049250313e-16 + 4 * 2.220446049250313e-16 * fabs(xcur)) / 2;
-                        double sbis = (xblk - xcur) / 2;
-                        if (fabs(sbis) < delta) {
-                            rootv = xcur;
-                            converged = true;
-                            break;
-                        }
-                        // fabs(fcur) < fabs(fpre) is never true -> always bisect
-                        xpre = xcur;
-                        fpre = fcur;
-                        if (fabs(sbis) > delta) xcur += sbis;
-                        else xcur += (sbis > 0 ? delta : -delta);
-                        double xx = (xcur - t_old) / h;
-                        double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
-                        fcur = prt_event_one(E, e, xcur, prt_dense_eval(f1, qz, h, z, p1, p2, p3, p4),
-                                             prt_dense_eval(f2, qp, h, p, p1, p2, p3, p4));
-                        ++c_bis;
-                        (void)fblk;
-                    }
-                    if (!converged) {
-                        status = PRT_RAY_BRENTQ_ITER;
-                        break;
-                    }
-                    if (best < 0 || rootv < best_root) {
-                        best = e;
-                        best_root = rootv;
-                    }
-                }
-                if (status != PRT_RAY_OK) break;
-                event = best;
-                root = best_root;
-                terminal = true;
-                popped = (n_ts > 1) && (root == t_old);  // donot_append, ivp.py:701-710
-            }
-
-            // ---- _interpolate_ray (launch_rays.py:745-784), streamed
-            if (SAVE) {
-                int ub = n_save - 1;
-                if (terminal) {
-                    int start = cursor > 0 ? cursor - 1 : 0;
-                    ub = prt_argmin_from(range_save, n_save, start, root);  // idx2
-                }
-                if (!popped) {
-                    while (cursor < ub) {
-                        double rsv = prt_ld(range_save + cursor);
-                        if (!terminal && !(rsv <= t_new)) break;
-                        double xx = (rsv - t_old) / h;
-                        double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
-                        sink.put(cursor, prt_dense_eval(f0, qT, h, T, p1, p2, p3, p4),
-                                 prt_dense_eval(f1, qz, h, z, p1, p2, p3, p4),
-                                 prt_dense_eval(f2, qp, h, p, p1, p2, p3, p4));
-                        ++cursor;
-                    }
-                }
-                if (terminal) cursor = ub;  // the next segment owns indices >= idx2
-            }
-
-            // ---- advance the state
-            if (terminal) {
-                if (!popped) {
-                    double xx = (root - t_old) / h;
-                    double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
-                    double nT = prt_dense_eval(f0, qT, h, T, p1, p2, p3, p4);
-                    double nz = prt_dense_eval(f1, qz, h, z, p1, p2, p3, p4);
-                    double np_ = prt_dense_eval(f2, qp, h, p, p1, p2, p3, p4);
-                    T = nT; z = nz; p = np_;
-                }  // else: sol.y[:, -1] stays the state at t_old
-                t = root;
-                break;
-            }
-            T = yT; z = yz; p = yp;
-            f0 = k7T; f1 = k7z; f2 = k7p;
-            t = t_new;
-            ++n_ts;
-            if (finished) break;
+        } else if (h_abs < min_step) {
+            h_abs = min_step;
         }
-        if (status != PRT_RAY_OK) break;
-        if (event < 0) break;  // reached x_end (sol.status == 0), launch_rays.py:425-426
+        ++c_att;
+        double tn = t + h_abs;
+        if (tn - S.x_end > 0.0) tn = S.x_end;
+        const double hh = tn - t;
+        h_abs = fabs(hh);
+        double k2T, k2z, k2p, k3T, k3z, k3p, k4T, k4z, k4p, k5T, k5z, k5p, k6T, k6z, k6p, k7T, k7z, k7p, cc, c_new;
+        double a, b;
+        prt_rhs(E, PRT_FMA(C2, hh, t), PRT_FMA(hh, A21 * f1, z), PRT_FMA(hh, A21 * f2, p), k2T, k2z, k2p, cc);
+        a = A31 * f1; a = PRT_FMA(A32, k2z, a);
+        b = A31 * f2; b = PRT_FMA(A32, k2p, b);
+        prt_rhs(E, PRT_FMA(C3, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), k3T, k3z, k3p, cc);
+        a = A41 * f1; a = PRT_FMA(A42, k2z, a); a = PRT_FMA(A43, k3z, a);
+        b = A41 * f2; b = PRT_FMA(A42, k2p, b); b = PRT_FMA(A43, k3p, b);
+        prt_rhs(E, PRT_FMA(C4, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), k4T, k4z, k4p, cc);
+        a = A51 * f1; a = PRT_FMA(A52, k2z, a); a = PRT_FMA(A53, k3z, a); a = PRT_FMA(A54, k4z, a);
+        b = A51 * f2; b = PRT_FMA(A52, k2p, b); b = PRT_FMA(A53, k3p, b); b = PRT_FMA(A54, k4p, b);
+        prt_rhs(E, PRT_FMA(C5, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), k5T, k5z, k5p, cc);
+        a = A61 * f1; a = PRT_FMA(A62, k2z, a); a = PRT_FMA(A63, k3z, a); a = PRT_FMA(A64, k4z, a); a = PRT_FMA(A65, k5z, a);
+        b = A61 * f2; b = PRT_FMA(A62, k2p, b); b = PRT_FMA(A63, k3p, b); b = PRT_FMA(A64, k4p, b); b = PRT_FMA(A65, k5p, b);
+        prt_rhs(E, t + hh, PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), k6T, k6z, k6p, cc);
+        double sT = B1 * f0; sT = PRT_FMA(B3, k3T, sT); sT = PRT_FMA(B4, k4T, sT); sT = PRT_FMA(B5, k5T, sT); sT = PRT_FMA(B6, k6T, sT);
+        double sz = B1 * f1; sz = PRT_FMA(B3, k3z, sz); sz = PRT_FMA(B4, k4z, sz); sz = PRT_FMA(B5, k5z, sz); sz = PRT_FMA(B6, k6z, sz);
+        double sp = B1 * f2; sp = PRT_FMA(B3, k3p, sp); sp = PRT_FMA(B4, k4p, sp); sp = PRT_FMA(B5, k5p, sp); sp = PRT_FMA(B6, k6p, sp);
+        const double nT = PRT_FMA(hh, sT, T), nz = PRT_FMA(hh, sz, z), np_ = PRT_FMA(hh, sp, p);
+        prt_rhs(E, t + hh, nz, np_, k7T, k7z, k7p, c_new);  // f_new (FSAL)
+        c_nfev += 6;
+        double eT = E1 * f0; eT = PRT_FMA(E3, k3T, eT); eT = PRT_FMA(E4, k4T, eT); eT = PRT_FMA(E5, k5T, eT); eT = PRT_FMA(E6, k6T, eT); eT = PRT_FMA(E7, k7T, eT);
+        double ez = E1 * f1; ez = PRT_FMA(E3, k3z, ez); ez = PRT_FMA(E4, k4z, ez); ez = PRT_FMA(E5, k5z, ez); ez = PRT_FMA(E6, k6z, ez); ez = PRT_FMA(E7, k7z, ez);
+        double ep = E1 * f2; ep = PRT_FMA(E3, k3p, ep); ep = PRT_FMA(E4, k4p, ep); ep = PRT_FMA(E5, k5p, ep); ep = PRT_FMA(E6, k6p, ep); ep = PRT_FMA(E7, k7p, ep);
+        const double scT = PRT_FMA(prt_np_maximum(fabs(T), fabs(nT)), S.rtol, S.atol);
+        const double scz = PRT_FMA(prt_np_maximum(fabs(z), fabs(nz)), S.rtol, S.atol);
+        const double scp = PRT_FMA(prt_np_maximum(fabs(p), fabs(np_)), S.rtol, S.atol);
+        const double err = prt_rms3((eT * hh) / scT, (ez * hh) / scz, (ep * hh) / scp);
+        if (!(err < 1.0)) {
+            h_abs *= prt_py_max(0.2, 0.9 * prt_pow_m02(err));
+            rejected = true;
+            return false;
+        }
+        double factor = (err == 0.0) ? 10.0 : prt_py_min(10.0, 0.9 * prt_pow_m02(err));
+        if (rejected) factor = prt_py_min(1.0, factor);
+        h_abs *= factor;
+        rejected = false;
+        ++c_acc;
+        t_old = t; t_new = tn; h = hh;
+        yT = nT; yz = nz; yp = np_;
+        nf0 = k7T; nf1 = k7z; nf2 = k7p;
+        finished = (tn - S.x_end >= 0.0);  // base.py:205-206
+        // events at the step end (ivp.py:678-699); c(t_new, y_new) comes from the FSAL stage, which was
+        // evaluated at t + h: identical unless the clipped step made t + h != t_new
+        if (t + hh != tn) {
+            double cz_unused;
+            prt_field(E, tn, nz, c_new, cz_unused);
+        }
+        const int g_new = prt_events(E, tn, nz, np_, c_new);
+        // find_active_events (ivp.py:134-157): up for direction +1, up|down for direction 0
+        const int up = (~g) & g_new, down = g & (~g_new);
+        active = (up & (PRT_EV_SURFACE | PRT_EV_BOTTOM)) | ((up | down) & (PRT_EV_VERTICAL | PRT_EV_BBOX));
+        g = g_new;
+        bool need_dense = (active != 0);
+        if (SAVE && !need_dense) need_dense = (cursor < S.n_save - 1) && (prt_ld(S.range_save + cursor) <= tn);
+        if (need_dense) {
+            ++c_dense;
+            qT = prt_dense_q(f0, k3T, k4T, k5T, k6T, k7T);
+            qz = prt_dense_q(f1, k3z, k4z, k5z, k6z, k7z);
+            qp = prt_dense_q(f2, k3p, k4p, k5p, k6p, k7p);
+            inv_h = 1.0 / hh;
+        }
+        return true;
+    }
 
-        // ---- bounce (launch_rays.py:432-480)
-        if (event == 2) { status = PRT_RAY_VERTICAL; break; }
-        if (event == 3) { status = PRT_RAY_BBOX; break; }
-        x = t;
+    PRT_HD void emit(const prt_traj_sink& sink, int i, double rsv) const
+    {
+        const double xx = (rsv - t_old) * inv_h;
+        const double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
+        sink.put(i, prt_dense_eval(f0, qT, h, T, p1, p2, p3, p4), prt_dense_eval(f1, qz, h, z, p1, p2, p3, p4),
+                 prt_dense_eval(f2, qp, h, p, p1, p2, p3, p4));
+    }
+
+    // accepted step without an event: stream the save points it owns, then move on
+    PRT_HD void advance(const prt_shot& S, const prt_traj_sink& sink)
+    {
+        if (SAVE) {
+            const int ub = S.n_save - 1;
+            while (cursor < ub) {
+                const double rsv = prt_ld(S.range_save + cursor);
+                if (!(rsv <= t_new)) break;
+                emit(sink, cursor, rsv);
+                ++cursor;
+            }
+        }
+        T = yT; z = yz; p = yp;
+        f0 = nf0; f1 = nf1; f2 = nf2;
+        t = t_new;
+        ++n_ts;
+        if (finished) phase = PRT_PH_DONE;  // sol.status == 0, launch_rays.py:425-426
+    }
+
+    PRT_HD bool event_at(const prt_env_view& E, int e, double x) const
+    {
+        const double xx = (x - t_old) * inv_h;
+        const double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
+        return prt_event_one(E, e, x, prt_dense_eval(f1, qz, h, z, p1, p2, p3, p4),
+                             prt_dense_eval(f2, qp, h, p, p1, p2, p3, p4));
+    }
+
+    // handle_events (ivp.py:80-131): every event is terminal -> earliest root, ties to the lower
+    // event index.  solve_event_equation = brentq(xtol = rtol = 4 eps, maxiter 100) on a +-1
+    // function, which degenerates to bisection (|f| is always 1).
+    PRT_HD void solve_roots(const prt_env_view& E)
+    {
+        double best_root = 0.0;
+        int best = -1;
+        for (int e = 0; e < 4; ++e) {
+            if (!(active & (1 << e))) continue;
+            double xpre = t_old, xcur = t_new, xblk = 0.0;
+            bool fpre = event_at(E, e, t_old), fcur = event_at(E, e, t_new);
+            c_bis += 2;
+            if (fpre == fcur) {
+                status = PRT_RAY_BRENTQ_SIGN;
+                return;
+            }
+            bool converged = false;
+            for (int i = 0; i < 100; ++i) {
+                if (fpre != fcur) xblk = xpre;
+                const double delta = (4 * PRT_EPS + 4 * PRT_EPS * fabs(xcur)) / 2;
+                const double sbis = (xblk - xcur) / 2;
+                if (fabs(sbis) < delta) {
+                    converged = true;
+                    break;
+                }
+                xpre = xcur;
+                fpre = fcur;
+                if (fabs(sbis) > delta) xcur += sbis;
+                else xcur += (sbis > 0 ? delta : -delta);
+                fcur = event_at(E, e, xcur);
+                ++c_bis;
+            }
+            if (!converged) {
+                status = PRT_RAY_BRENTQ_ITER;
+                return;
+            }
+            if (best < 0 || xcur < best_root) {
+                best = e;
+                best_root = xcur;
+            }
+        }
+        event = best;
+        root = best_root;
+    }
+
+    // terminal step: _interpolate_ray bookkeeping for the finished segment (launch_rays.py:745-784),
+    // state at the event, then the reflection (launch_rays.py:432-480)
+    PRT_HD void finish_terminal(const prt_env_view& E, const prt_shot& S, const prt_traj_sink& sink)
+    {
+        if (status != PRT_RAY_OK) {
+            phase = PRT_PH_DONE;
+            return;
+        }
+        const bool popped = (n_ts > 1) && (root == t_old);  // donot_append, ivp.py:701-710
+        if (SAVE) {
+            const int start = cursor > 0 ? cursor - 1 : 0;
+            const int ub = prt_argmin_from(S.range_save, S.n_save, start, root);  // idx2
+            if (!popped) {
+                while (cursor < ub) {
+                    emit(sink, cursor, prt_ld(S.range_save + cursor));
+                    ++cursor;
+                }
+            }
+            cursor = ub;  // the next segment owns indices >= idx2
+        }
+        if (!popped) {
+            const double xx = (root - t_old) * inv_h;
+            const double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
+            const double nT = prt_dense_eval(f0, qT, h, T, p1, p2, p3, p4);
+            const double nz = prt_dense_eval(f1, qz, h, z, p1, p2, p3, p4);
+            const double np_ = prt_dense_eval(f2, qp, h, p, p1, p2, p3, p4);
+            T = nT; z = nz; p = np_;
+        }  // else: sol.y[:, -1] stays the state at t_old
+        t = root;
+        phase = PRT_PH_DONE;
+        if (event == 2) { status = PRT_RAY_VERTICAL; return; }
+        if (event == 3) { status = PRT_RAY_BBOX; return; }
         double c, cz;
-        prt_field(E, x, z, c, cz);
-        double theta = prt_asin(p * c) * PRT_RAD2DEG;  // ray_angle
+        prt_field(E, t, z, c, cz);
+        const double theta = prt_asin(p * c) * PRT_RAD2DEG;  // ray_angle
         double theta_bounce;
         if (event == 0) {
             theta_bounce = -theta;
             ++n_surface;
         } else {
             bool oob;
-            double beta = prt_bottom_angle(E, x, oob);
-            if (oob) { status = PRT_RAY_BOTTOM_OOB; break; }
+            const double beta = prt_bottom_angle(E, t, oob);
+            if (oob) { status = PRT_RAY_BOTTOM_OOB; return; }
             theta_bounce = 2.0 * beta - theta;
             ++n_bottom;
         }
-        if (terminate_backwards && (fabs(theta_bounce) > 90.0)) { status = PRT_RAY_BACKWARDS; break; }
+        if (S.terminate_backwards && (fabs(theta_bounce) > 90.0)) { status = PRT_RAY_BACKWARDS; return; }
         p = prt_sin(theta_bounce * PRT_DEG2RAD) / c;
-        if (n_surface + n_bottom >= max_bounces) { status = PRT_RAY_MAX_BOUNCES; break; }
+        if (n_surface + n_bottom >= S.max_bounces) { status = PRT_RAY_MAX_BOUNCES; return; }
+        if (t < S.x_end) phase = PRT_PH_INIT;  // launch_rays.py:404
     }
 
-    if (status == PRT_RAY_OK) {
-        if (SAVE && n_save > 0) sink.put(n_save - 1, T, z, p);  // exact final state, launch_rays.py:772-775
-        res.T = T; res.z = z; res.p = p;
-    } else {
-        res.T = NAN; res.z = NAN; res.p = NAN;
+    PRT_HD void result(const prt_shot& S, const prt_traj_sink& sink, prt_ray_result& res, uint32_t* cnt) const
+    {
+        if (status == PRT_RAY_OK) {
+            if (SAVE && S.n_save > 0) sink.put(S.n_save - 1, T, z, p);  // exact final state, launch_rays.py:772-775
+            res.T = T; res.z = z; res.p = p;
+        } else {
+            res.T = NAN; res.z = NAN; res.p = NAN;
+        }
+        res.n_bottom = n_bottom;
+        res.n_surface = n_surface;
+        res.status = status;
+        if (cnt) {
+            cnt[PRT_CNT_NFEV] = c_nfev; cnt[PRT_CNT_ATTEMPTS] = c_att; cnt[PRT_CNT_ACCEPTED] = c_acc;
+            cnt[PRT_CNT_SEGMENTS] = c_seg; cnt[PRT_CNT_BISECT] = c_bis; cnt[PRT_CNT_DENSE] = c_dense;
+        }
     }
-    res.n_bottom = n_bottom;
-    res.n_surface = n_surface;
-    res.status = status;
-    if (cnt) {
-        cnt[PRT_CNT_NFEV] = c_nfev; cnt[PRT_CNT_ATTEMPTS] = c_att; cnt[PRT_CNT_ACCEPTED] = c_acc;
-        cnt[PRT_CNT_SEGMENTS] = c_seg; cnt[PRT_CNT_BISECT] = c_bis; cnt[PRT_CNT_DENSE] = c_dense;
+};
+
+// ray-by-ray driver (host parity harness; also the semantic definition of the warp driver)
+template <bool SAVE>
+PRT_HD void prt_integrate_ray(const prt_env_view& E, double T, double z, double p, double x0, prt_shot S,
+                              const prt_traj_sink& sink, prt_ray_result& res, uint32_t* cnt)
+{
+    if (S.rtol < 100.0 * PRT_EPS) S.rtol = 100.0 * PRT_EPS;  // validate_tol, common.py:44-60
+    prt_ray<SAVE> r;
+    r.start(T, z, p, x0, S);
+    while (r.phase != PRT_PH_DONE) {
+        if (r.phase == PRT_PH_INIT) r.seg_init(E, S);
+        if (!r.attempt(E, S)) continue;
+        if (r.active) {
+            r.solve_roots(E);
+            r.finish_terminal(E, S, sink);
+        } else {
+            r.advance(S, sink);
+        }
     }
+    r.result(S, sink, res, cnt);
 }

@@ -5,6 +5,7 @@
 // contiguous, 256-byte-aligned blob laid out for 16-byte loads:
 //   grid   [n_r][n_z] {c, dc/dz}   -- both fields of a node in one LDG.128
 //   rpair  [n_r-1] {r[i], r[i+1]}  -- both edges of a cell in one LDG.128 (same for z, bathymetry)
+//   rrecip [n_r-1] 1/(r[i+1]-r[i]) -- interpolation weights without a division (same for z, bathymetry)
 // and a prt_env_view whose pointers are offsets into the blob until prt_env_rebase() is applied.
 #pragma once
 #include <stdint.h>
@@ -30,6 +31,11 @@ static inline void prt_pack_pairs(prt_d2* dst, const double* a, int n)
     }
 }
 
+static inline void prt_pack_recip(double* dst, const double* a, int n)
+{
+    for (int i = 0; i < n - 1; ++i) dst[i] = 1.0 / (a[i + 1] - a[i]);
+}
+
 static inline double prt_inv_mean_step(const double* a, int n)
 {
     double span = a[n - 1] - a[0];
@@ -48,7 +54,10 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
     size_t o_zpair = o_rpair + prt_align256(sizeof(prt_d2) * (size_t)(n_r - 1));
     size_t o_bx = o_zpair + prt_align256(sizeof(prt_d2) * (size_t)(n_z - 1));
     size_t o_bv = o_bx + prt_align256(sizeof(prt_d2) * (size_t)(n_b - 1));
-    size_t o_bax = o_bv + prt_align256(sizeof(prt_d2) * (size_t)(n_b - 1));
+    size_t o_rrec = o_bv + prt_align256(sizeof(prt_d2) * (size_t)(n_b - 1));
+    size_t o_zrec = o_rrec + prt_align256(sizeof(double) * (size_t)(n_r - 1));
+    size_t o_brec = o_zrec + prt_align256(sizeof(double) * (size_t)(n_z - 1));
+    size_t o_bax = o_brec + prt_align256(sizeof(double) * (size_t)(n_b - 1));
     size_t o_bac = o_bax + prt_align256(sizeof(double) * (size_t)n_ba);
     size_t total = o_bac + prt_align256(sizeof(double) * 4 * (size_t)(n_ba - 1));
     out.bytes.assign(total, 0);
@@ -63,6 +72,9 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
     prt_pack_pairs(reinterpret_cast<prt_d2*>(base + o_zpair), zin, n_z);
     prt_pack_pairs(reinterpret_cast<prt_d2*>(base + o_bx), depth_ranges, n_b);
     prt_pack_pairs(reinterpret_cast<prt_d2*>(base + o_bv), depths, n_b);
+    prt_pack_recip(reinterpret_cast<double*>(base + o_rrec), rin, n_r);
+    prt_pack_recip(reinterpret_cast<double*>(base + o_zrec), zin, n_z);
+    prt_pack_recip(reinterpret_cast<double*>(base + o_brec), depth_ranges, n_b);
     memcpy(base + o_bax, ba_x, sizeof(double) * n_ba);
     memcpy(base + o_bac, ba_c, sizeof(double) * 4 * (size_t)(n_ba - 1));
 
@@ -73,6 +85,9 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
     v.zpair = reinterpret_cast<const prt_d2*>(o_zpair);
     v.bxpair = reinterpret_cast<const prt_d2*>(o_bx);
     v.bvpair = reinterpret_cast<const prt_d2*>(o_bv);
+    v.rrecip = reinterpret_cast<const double*>(o_rrec);
+    v.zrecip = reinterpret_cast<const double*>(o_zrec);
+    v.brecip = reinterpret_cast<const double*>(o_brec);
     v.ba_x = reinterpret_cast<const double*>(o_bax);
     v.ba_c = reinterpret_cast<const double*>(o_bac);
     v.r0 = rin[0]; v.r_inv = prt_inv_mean_step(rin, n_r);
@@ -97,6 +112,9 @@ static inline prt_env_view prt_env_rebase(const prt_env_view& view, const void* 
     v.zpair = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.zpair));
     v.bxpair = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.bxpair));
     v.bvpair = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.bvpair));
+    v.rrecip = reinterpret_cast<const double*>(b + reinterpret_cast<size_t>(view.rrecip));
+    v.zrecip = reinterpret_cast<const double*>(b + reinterpret_cast<size_t>(view.zrecip));
+    v.brecip = reinterpret_cast<const double*>(b + reinterpret_cast<size_t>(view.brecip));
     v.ba_x = reinterpret_cast<const double*>(b + reinterpret_cast<size_t>(view.ba_x));
     v.ba_c = reinterpret_cast<const double*>(b + reinterpret_cast<size_t>(view.ba_c));
     return v;

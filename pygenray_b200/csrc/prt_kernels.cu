@@ -11,6 +11,7 @@
 // stays L1/L2 resident (DESIGN.md sections 2 and 5).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -60,35 +61,101 @@ struct prt_fan_params {
     int32_t* out_status;
     uint32_t* out_counters;
     int32_t max_bounces;
+    int32_t stored_convention;
+    int32_t park_wait;
 };
+
+// Lanes that hit a boundary wait (at most this many step attempts of the other lanes) so that the
+// event root searches of a warp run together; tunable for experiments via PRT_PARK_WAIT.
+static int g_park_wait = -1;
+static int park_wait_setting()
+{
+    if (g_park_wait < 0) {
+        const char* e = getenv("PRT_PARK_WAIT");
+        g_park_wait = e ? atoi(e) : 8;
+        if (g_park_wait < 0) g_park_wait = 0;
+    }
+    return g_park_wait;
+}
+
+// Warp-synchronous driver of 32 rays (semantics = prt_integrate_ray for each lane; only the
+// interleaving differs, so results are bit-identical):
+//   * every iteration all stepping lanes make exactly ONE RK45 attempt together, accepted or not
+//     (no lane re-runs the stage code alone after a rejection);
+//   * a lane whose accepted step fired an event parks; the bisection root search, the reflection
+//     and the next segment's start-up run once for all parked lanes, when no lane is left stepping
+//     or the oldest parked lane has waited `park_wait` iterations (neighbouring launch angles
+//     reach a boundary within a few steps of each other).
+template <bool SAVE>
+__device__ __forceinline__ void prt_integrate_warp(const prt_env_view& E, prt_ray<SAVE>& r, const prt_shot& S,
+                                                   const prt_traj_sink& sink, int park_wait)
+{
+    const unsigned full = 0xffffffffu;
+    int waited = 0;
+    for (;;) {
+        if (!__any_sync(full, r.phase != PRT_PH_DONE)) break;
+        if (r.phase == PRT_PH_INIT) r.seg_init(E, S);
+        __syncwarp(full);
+        if (r.phase == PRT_PH_STEP) {
+            if (r.attempt(E, S)) {
+                if (r.active) r.phase = PRT_PH_ROOT;
+                else r.advance(S, sink);
+            }
+        }
+        __syncwarp(full);
+        const unsigned parked = __ballot_sync(full, r.phase == PRT_PH_ROOT);
+        if (parked) {
+            const unsigned stepping = __ballot_sync(full, r.phase == PRT_PH_STEP);
+            ++waited;
+            if (!stepping || waited > park_wait) {
+                if (r.phase == PRT_PH_ROOT) {
+                    r.solve_roots(E);
+                    r.finish_terminal(E, S, sink);
+                }
+                waited = 0;
+            }
+        }
+    }
+}
 
 template <bool SAVE>
 __global__ void __launch_bounds__(128) prt_fan_kernel(const __grid_constant__ prt_env_view E,
                                                       const __grid_constant__ prt_fan_params P)
 {
     const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ray >= P.n_rays) return;
-    double T, z, p;
-    if (P.y0) {
-        T = P.y0[3 * ray];
-        z = P.y0[3 * ray + 1];
-        p = P.y0[3 * ray + 2];
-    } else {
-        prt_initial_state(E, P.source_depth, P.source_range, P.angles[ray], T, z, p);
+    const bool live = ray < P.n_rays;  // whole warps stay in the kernel: the driver is warp-synchronous
+    prt_shot S;
+    S.x_end = P.receiver_range; S.rtol = P.rtol; S.atol = P.atol;
+    S.terminate_backwards = P.terminate_backwards; S.n_save = P.n_save; S.max_bounces = P.max_bounces;
+    S.range_save = P.range_save;
+    double T = 0.0, z = 0.0, p = 0.0;
+    if (live) {
+        if (P.y0) {
+            T = P.y0[3 * ray];
+            z = P.y0[3 * ray + 1];
+            p = P.y0[3 * ray + 2];
+        } else {
+            prt_initial_state(E, P.source_depth, P.source_range, P.angles[ray], T, z, p);
+        }
     }
     prt_traj_sink sink;
     sink.stride = 1;
+    sink.sgn = P.stored_convention ? -1.0 : 1.0;
     sink.T = sink.z = sink.p = nullptr;
-    if (SAVE) {
+    if (SAVE && live) {
         const size_t plane = (size_t)P.n_rays * (size_t)P.n_save;
         sink.T = P.out_traj + (size_t)ray * (size_t)P.n_save;
         sink.z = sink.T + plane;
         sink.p = sink.z + plane;
     }
+    prt_ray<SAVE> r;
+    r.start(T, z, p, P.source_range, S);
+    if (!live) r.phase = PRT_PH_DONE;
+    prt_integrate_warp<SAVE>(E, r, S, sink, P.park_wait);
+    if (!live) return;
     prt_ray_result res;
     uint32_t cnt[PRT_CNT_N];
-    prt_integrate_ray<SAVE>(E, T, z, p, P.source_range, P.receiver_range, P.rtol, P.atol,
-                            P.terminate_backwards != 0, P.n_save, P.range_save, sink, P.max_bounces, res, cnt);
+    r.result(S, sink, res, cnt);
     if (SAVE && res.status != PRT_RAY_OK) {
         // the reference returns None for a dropped ray; leave no half-written trajectory behind
         for (int i = 0; i < P.n_save; ++i) sink.put(i, NAN, NAN, NAN);
@@ -103,6 +170,24 @@ __global__ void __launch_bounds__(128) prt_fan_kernel(const __grid_constant__ pr
 #pragma unroll
         for (int k = 0; k < PRT_CNT_N; ++k) P.out_counters[(size_t)k * P.n_rays + ray] = cnt[k];
     }
+}
+
+// sum(diff(sign(p)) != 0) along the saved grid, one warp per ray (ray_objects.py:142-144)
+__global__ void prt_sign_changes_kernel(int64_t n_rays, int32_t n_save, const double* __restrict__ p_plane,
+                                        int32_t* __restrict__ out)
+{
+    const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (ray >= n_rays) return;
+    const double* p = p_plane + (size_t)ray * (size_t)n_save;
+    int local = 0;
+    for (int i = lane; i < n_save - 1; i += 32) {
+        double a = p[i], b = p[i + 1];
+        double sa = (double)((a > 0.0) - (a < 0.0)), sb = (double)((b > 0.0) - (b < 0.0));
+        local += ((a != a) || (b != b) || (sb - sa != 0.0)) ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if (lane == 0) out[ray] = local;
 }
 
 static int pick_block(int64_t n_units, int device)
@@ -196,7 +281,7 @@ struct prt_refine_params {
     int64_t n_br;
     const double* rd;
     double source_depth, source_range, receiver_range, rtol, atol, ztol;
-    int32_t terminate_backwards, max_iter, max_bounces;
+    int32_t terminate_backwards, max_iter, max_bounces, park_wait;
     double* out_theta;
     double* out_final;
     int32_t *out_nb, *out_ns, *out_status, *out_shots, *out_ray_status;
@@ -241,18 +326,27 @@ __global__ void __launch_bounds__(128) prt_refine_round_kernel(const __grid_cons
 {
     const int n_active = *n_in;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_active) return;
-    const int b = list_in[idx];
-    const double rd = P.rd[b];
-    double th = S.th[b];
-    double T, z, p;
-    prt_initial_state(E, P.source_depth, P.source_range, -th, T, z, p);  // shoot_ray negates, launch_rays.py:251
+    const bool live = idx < n_active;
+    const int b = live ? list_in[idx] : 0;
+    const double rd = live ? P.rd[b] : 0.0;
+    const double th = live ? S.th[b] : 0.0;
+    prt_shot shot;
+    shot.x_end = P.receiver_range; shot.rtol = P.rtol; shot.atol = P.atol;
+    shot.terminate_backwards = P.terminate_backwards; shot.n_save = 0; shot.max_bounces = P.max_bounces;
+    shot.range_save = nullptr;
+    double T = 0.0, z = 0.0, p = 0.0;
+    if (live) prt_initial_state(E, P.source_depth, P.source_range, -th, T, z, p);  // shoot_ray negates, launch_rays.py:251
     prt_traj_sink sink;
     sink.T = sink.z = sink.p = nullptr;
     sink.stride = 1;
+    sink.sgn = 1.0;
+    prt_ray<false> r;
+    r.start(T, z, p, P.source_range, shot);
+    if (!live) r.phase = PRT_PH_DONE;
+    prt_integrate_warp<false>(E, r, shot, sink, P.park_wait);
+    if (!live) return;
     prt_ray_result res;
-    prt_integrate_ray<false>(E, T, z, p, P.source_range, P.receiver_range, P.rtol, P.atol,
-                             P.terminate_backwards != 0, 0, nullptr, sink, P.max_bounces, res, nullptr);
+    r.result(shot, sink, res, nullptr);
     const int shots = ++S.shots[b];
     P.out_shots[b] = shots;
     if (res.status != PRT_RAY_OK) {  // ray is None, eigenrays.py:241-245
@@ -371,7 +465,8 @@ int prt_shoot_fan(const prt_env_t* env, int64_t n_rays, const double* angles_dev
                   double source_depth, double source_range, double receiver_range, double rtol, double atol,
                   int32_t terminate_backwards, int32_t n_save, const double* range_save_dev, double* out_traj_dev,
                   double* out_final_dev, int32_t* out_n_bottom_dev, int32_t* out_n_surface_dev,
-                  int32_t* out_status_dev, uint32_t* out_counters_dev, int32_t max_bounces, void* stream)
+                  int32_t* out_status_dev, uint32_t* out_counters_dev, int32_t stored_convention,
+                  int32_t* out_p_sign_changes_dev, int32_t max_bounces, void* stream)
 {
     if (!env) return fail(PRT_ERR_ARG, "prt_shoot_fan: null environment");
     if (n_rays < 0) return fail(PRT_ERR_ARG, "prt_shoot_fan: n_rays < 0");
@@ -392,6 +487,9 @@ int prt_shoot_fan(const prt_env_t* env, int64_t n_rays, const double* angles_dev
     P.range_save = range_save_dev; P.out_traj = out_traj_dev; P.out_final = out_final_dev;
     P.out_nb = out_n_bottom_dev; P.out_ns = out_n_surface_dev; P.out_status = out_status_dev;
     P.out_counters = out_counters_dev; P.max_bounces = max_bounces > 0 ? max_bounces : (1 << 20);
+    P.stored_convention = stored_convention;
+    P.park_wait = park_wait_setting();
+    if (P.rtol < 100.0 * PRT_EPS) P.rtol = 100.0 * PRT_EPS;  // validate_tol (scipy common.py:44-60)
     const int block = pick_block(n_rays, env->device);
     const unsigned grid = (unsigned)((n_rays + block - 1) / block);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -399,6 +497,14 @@ int prt_shoot_fan(const prt_env_t* env, int64_t n_rays, const double* angles_dev
     else prt_fan_kernel<false><<<grid, block, 0, s>>>(env->view, P);
     g_launches.fetch_add(1);
     PRT_CUDA(cudaGetLastError());
+    if (out_p_sign_changes_dev) {
+        if (!save) return fail(PRT_ERR_ARG, "prt_shoot_fan: out_p_sign_changes_dev needs n_save > 0");
+        const double* p_plane = out_traj_dev + 2 * (size_t)n_rays * (size_t)n_save;
+        const unsigned g2 = (unsigned)((n_rays * 32 + 255) / 256);
+        prt_sign_changes_kernel<<<g2, 256, 0, s>>>(n_rays, n_save, p_plane, out_p_sign_changes_dev);
+        g_launches.fetch_add(1);
+        PRT_CUDA(cudaGetLastError());
+    }
     return PRT_SUCCESS;
 }
 
@@ -406,7 +512,8 @@ int prt_shoot_fan_host(const prt_env_t* env, int64_t n_rays, const double* angle
                        double source_depth, double source_range, double receiver_range, double rtol, double atol,
                        int32_t terminate_backwards, int32_t n_save, const double* range_save, double* out_traj,
                        double* out_final, int32_t* out_n_bottom, int32_t* out_n_surface, int32_t* out_status,
-                       uint32_t* out_counters, int32_t max_bounces)
+                       uint32_t* out_counters, int32_t stored_convention, int32_t* out_p_sign_changes,
+                       int32_t max_bounces)
 {
     if (!env) return fail(PRT_ERR_ARG, "prt_shoot_fan_host: null environment");
     if (n_rays <= 0) return n_rays == 0 ? PRT_SUCCESS : fail(PRT_ERR_ARG, "prt_shoot_fan_host: n_rays < 0");
@@ -421,7 +528,8 @@ int prt_shoot_fan_host(const prt_env_t* env, int64_t n_rays, const double* angle
     size_t o_ns = prt_align256(o_nb + n * sizeof(int32_t));
     size_t o_st = prt_align256(o_ns + n * sizeof(int32_t));
     size_t o_cnt = prt_align256(o_st + n * sizeof(int32_t));
-    size_t o_traj = prt_align256(o_cnt + (out_counters ? PRT_CNT_N * n * sizeof(uint32_t) : 0));
+    size_t o_flip = prt_align256(o_cnt + (out_counters ? PRT_CNT_N * n * sizeof(uint32_t) : 0));
+    size_t o_traj = prt_align256(o_flip + n * sizeof(int32_t));
     size_t total = o_traj + (save ? 3 * n * (size_t)n_save * sizeof(double) : 0);
     unsigned char* d = nullptr;
     PRT_CUDA(cudaMalloc(&d, total));
@@ -434,6 +542,7 @@ int prt_shoot_fan_host(const prt_env_t* env, int64_t n_rays, const double* angle
                            save ? n_save : 0, save ? (const double*)(d + o_rs) : nullptr,
                            save ? (double*)(d + o_traj) : nullptr, (double*)(d + o_final), (int32_t*)(d + o_nb),
                            (int32_t*)(d + o_ns), (int32_t*)(d + o_st), out_counters ? (uint32_t*)(d + o_cnt) : nullptr,
+                           stored_convention, (save && out_p_sign_changes) ? (int32_t*)(d + o_flip) : nullptr,
                            max_bounces, nullptr);
         if (rc == PRT_SUCCESS) {
             e = cudaMemcpy(out_final, d + o_final, 3 * n * sizeof(double), cudaMemcpyDeviceToHost);
@@ -442,6 +551,8 @@ int prt_shoot_fan_host(const prt_env_t* env, int64_t n_rays, const double* angle
             if (e == cudaSuccess) e = cudaMemcpy(out_status, d + o_st, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
             if (e == cudaSuccess && out_counters)
                 e = cudaMemcpy(out_counters, d + o_cnt, PRT_CNT_N * n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess && save && out_p_sign_changes)
+                e = cudaMemcpy(out_p_sign_changes, d + o_flip, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
             if (e == cudaSuccess && save)
                 e = cudaMemcpy(out_traj, d + o_traj, 3 * n * (size_t)n_save * sizeof(double), cudaMemcpyDeviceToHost);
         }
@@ -525,6 +636,8 @@ int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev
     P.receiver_range = receiver_range; P.rtol = rtol; P.atol = atol; P.ztol = ztol;
     P.terminate_backwards = terminate_backwards; P.max_iter = max_iter;
     P.max_bounces = max_bounces > 0 ? max_bounces : (1 << 20);
+    P.park_wait = park_wait_setting();
+    if (P.rtol < 100.0 * PRT_EPS) P.rtol = 100.0 * PRT_EPS;
     P.out_theta = out_theta_dev; P.out_final = out_final_dev; P.out_nb = out_n_bottom_dev; P.out_ns = out_n_surface_dev;
     P.out_status = out_status_dev; P.out_shots = out_shots_dev; P.out_ray_status = out_ray_status_dev;
     prt_refine_init_kernel<<<(unsigned)((n_br + 255) / 256), 256, 0, s>>>(S, n_br, z1_dev, z2_dev, th1_dev, th2_dev,

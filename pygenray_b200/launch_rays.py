@@ -1,0 +1,356 @@
+"""Ray-fan shooting: host layer over libprt.so.
+
+Public entry points keep the reference's signatures, defaults, sign conventions and error
+behaviour (/root/reference/src/pygenray/launch_rays.py): :func:`shoot_rays` (:11-200),
+:func:`shoot_ray` (:203-322), plus the array-level seam :func:`_unpack_envi` (:717-742) and
+:func:`_mirror_envi_arrays` (:684-714).  The per-ray integration (``_shoot_ray_array`` +
+``_interpolate_ray``, :325-484, 745-784) runs on the GPU for all launch angles at once
+(:func:`shoot_fan_arrays` -> ``prt_shoot_fan``); the reference's multiprocessing pool and shared
+memory (:133-198) have no equivalent here.  There is no CPU path: without libprt.so and a CUDA
+device every call raises.
+"""
+import ctypes as C
+import zlib
+
+import numpy as np
+from scipy.interpolate import CubicSpline
+
+from . import _lib, _xr
+from .ray_objects import Ray, RayFan
+
+__all__ = ["shoot_rays", "shoot_ray", "shoot_fan_arrays", "DeviceEnvironment", "_unpack_envi",
+           "_mirror_envi_arrays", "bottom_angle_ppoly"]
+
+ATOL = 1e-6  # scipy.integrate.solve_ivp default, never overridden by the reference (launch_rays.py:670-679)
+
+# shoot_rays() with fewer than 70 angles negates the launch angles and then calls shoot_ray(), which
+# negates them again (launch_rays.py:64-67, 94-117, 251): user angle a is integrated with internal
+# angle +a, whereas the >= 70 branch integrates -a.  The reference's own golden fixture pins this
+# behaviour (tests/test_physics.py:313-316), so it is reproduced by default.
+REPLICATE_SMALL_FAN_SIGN_QUIRK = True
+_SMALL_FAN = 70
+
+
+# ---------------------------------------------------------------------------------------------
+# environment -> arrays -> device
+def _unpack_envi(environment, flatearth=True):
+    """The seven arrays the integrator consumes: cin, cpin, rin, zin, depths, depth_ranges, bottom_angles."""
+    if flatearth:
+        if not hasattr(environment, "sound_speed_fe"):
+            raise Exception(
+                "Flat earth transformation has not been applied. Set `flat_earth_transform=True` when creating "
+                "the OceanEnvironment2D object."
+            )
+        ss, bathy = environment.sound_speed_fe, environment.bathymetry_fe
+    else:
+        ss, bathy = environment.sound_speed, environment.bathymetry
+    cin = np.array(_xr.values_of(ss))
+    cpin = np.array(_xr.differentiate(ss, "depth"))
+    rin = np.array(_xr.coord_of(ss, "range"))
+    zin = np.array(_xr.coord_of(ss, "depth"))
+    depths = np.array(_xr.values_of(bathy))
+    depth_ranges = np.array(_xr.coord_of(bathy, "range"))
+    bottom_angles = np.array(environment.bottom_angle)
+    return cin, cpin, rin, zin, depths, depth_ranges, bottom_angles
+
+
+def _mirror_envi_arrays(cin, cpin, rin, depths, depth_ranges, bottom_angles):
+    """Reflect the environment about the range axis (x' = -x) so a backwards shot runs forwards."""
+    return (cin[::-1, :], cpin[::-1, :], -rin[::-1], depths[::-1], -depth_ranges[::-1], -bottom_angles[::-1])
+
+
+def _check_monotonic(rin, zin, depth_ranges):
+    if not np.all(np.diff(rin) >= 0):
+        raise Exception("Sound speed range coordinates must be monotonically increasing.")
+    if not np.all(np.diff(zin) >= 0):
+        raise Exception("Sound speed depth coordinates must be monotonically increasing.")
+    if not np.all(np.diff(depth_ranges) >= 0):
+        raise Exception("Bathymetry range coordinates must be monotonically increasing.")
+
+
+def bottom_angle_ppoly(depth_ranges, bottom_angles):
+    """Not-a-knot cubic spline of the bottom angle as piecewise-polynomial coefficients.
+
+    Stands for ``scipy.interpolate.interp1d(depth_ranges, bottom_angles, kind="cubic")`` which
+    ``_shoot_ray_array`` rebuilds for every ray (launch_rays.py:397-399): the same interpolant,
+    expressed in the local power basis so the device evaluates it with three FMAs.
+    Returns ``(x[n], c[4][n-1])`` with the highest power first.
+    """
+    x = np.asarray(depth_ranges, dtype=np.float64)
+    y = np.asarray(bottom_angles, dtype=np.float64)
+    if x.shape[0] < 4:
+        raise ValueError("x and y arrays must have at least 4 entries")  # interp1d(kind="cubic")
+    cs = CubicSpline(x, y, bc_type="not-a-knot")
+    return np.ascontiguousarray(cs.x), np.ascontiguousarray(cs.c)
+
+
+def _as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class DeviceEnvironment:
+    """One environment staged in B200 HBM (``prt_env_create``): interleaved {c, dc/dz} grid etc."""
+
+    def __init__(self, cin, cpin, rin, zin, depths, depth_ranges, bottom_angles, device=None):
+        L = _lib.require_gpu()
+        import torch  # noqa: PLC0415
+
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = int(device)
+        cin, cpin, rin, zin = _as_f64(cin), _as_f64(cpin), _as_f64(rin), _as_f64(zin)
+        depths, depth_ranges = _as_f64(depths), _as_f64(depth_ranges)
+        if cin.ndim != 2 or cin.shape != (rin.shape[0], zin.shape[0]) or cpin.shape != cin.shape:
+            raise ValueError(
+                f"sound speed must be a [range][depth] array matching its coordinates, got {cin.shape} for "
+                f"{rin.shape[0]} ranges x {zin.shape[0]} depths"
+            )
+        ba_x, ba_c = bottom_angle_ppoly(depth_ranges, bottom_angles)
+        handle = C.c_void_p()
+        rc = L.prt_env_create(
+            self.device, rin.shape[0], zin.shape[0], rin.ctypes.data, zin.ctypes.data, cin.ctypes.data,
+            cpin.ctypes.data, depths.shape[0], depth_ranges.ctypes.data, depths.ctypes.data, ba_x.shape[0],
+            ba_x.ctypes.data, ba_c.ctypes.data, C.byref(handle),
+        )
+        _lib.check(rc, "prt_env_create")
+        self._h = handle
+        self.c_source_args = (rin, zin, cin)
+        self.n_r, self.n_z = rin.shape[0], zin.shape[0]
+        self.device_bytes = int(L.prt_env_device_bytes(handle))
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise _lib.PrtError("DeviceEnvironment was destroyed")
+        return self._h
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            try:
+                _lib.load().prt_env_destroy(self._h)
+            finally:
+                self._h = None
+
+    def __del__(self):  # pragma: no cover - interpreter shutdown ordering
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def _fingerprint(*arrays):
+    crc = 0
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        crc = zlib.crc32(a.view(np.uint8).reshape(-1), crc)
+        crc = zlib.crc32(repr(a.shape).encode(), crc)
+    return crc
+
+
+def _device_environment(environment, flatearth, backwards, device=None):
+    """Unpack (+ mirror) the environment and stage it once per (content, orientation, device)."""
+    import torch  # noqa: PLC0415
+
+    cin, cpin, rin, zin, depths, depth_ranges, bottom_angles = _unpack_envi(environment, flatearth=flatearth)
+    _check_monotonic(rin, zin, depth_ranges)
+    if backwards:
+        cin, cpin, rin, depths, depth_ranges, bottom_angles = _mirror_envi_arrays(
+            cin, cpin, rin, depths, depth_ranges, bottom_angles
+        )
+    if device is None:
+        _lib.require_gpu()
+        device = torch.cuda.current_device()
+    key = (bool(flatearth), bool(backwards), int(device),
+           _fingerprint(cin, rin, zin, depths, depth_ranges, bottom_angles))
+    cache = environment.__dict__.setdefault("_prt_device_cache", {})
+    denv = cache.get(key)
+    if denv is None:
+        denv = DeviceEnvironment(cin, cpin, rin, zin, depths, depth_ranges, bottom_angles, device=device)
+        if len(cache) >= 4:
+            cache.pop(next(iter(cache))).close()
+        cache[key] = denv
+    return denv
+
+
+# ---------------------------------------------------------------------------------------------
+# the batched seam
+def shoot_fan_arrays(denv, source_depth, source_range, receiver_range, angles=None, y0s=None,
+                     num_range_save=0, rtol=1e-9, terminate_backwards=True, counters=False,
+                     stored_convention=False, ray_id_counts=False, max_bounces=_lib.DEFAULT_MAX_BOUNCES,
+                     to_host=True):
+    """Shoot ``n`` rays on the GPU.  ``angles`` are INTERNAL launch angles [deg] (positive = downwards).
+
+    Returns a dict: ``final (3,n)`` [T, z, p], ``n_bottom``, ``n_surface``, ``status`` (n,), and, when
+    ``num_range_save > 0``, ``range_save (N,)`` and ``traj (3,n,N)``; optional ``counters (6,n)`` and
+    ``p_sign_changes (n,)``.  z and p are in the ODE convention (z positive down) unless
+    ``stored_convention`` (then the trajectory holds -z and -p as ``Ray`` stores them).  Arrays are
+    numpy (pinned-memory copies) when ``to_host`` else CUDA tensors.
+    """
+    L = _lib.require_gpu()
+    import torch  # noqa: PLC0415
+
+    if not (source_range < receiver_range):
+        raise ValueError("shoot_fan_arrays integrates forwards: mirror the environment for backwards shots")
+    dev = torch.device("cuda", denv.device)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream()
+        if y0s is not None:
+            y0_h = torch.from_numpy(_as_f64(y0s).reshape(-1, 3))
+            n = y0_h.shape[0]
+            y0_d = y0_h.pin_memory().to(dev, non_blocking=True) if n else y0_h.to(dev)
+            ang_d = None
+        else:
+            ang_h = torch.from_numpy(_as_f64(np.atleast_1d(angles)).reshape(-1))
+            n = ang_h.shape[0]
+            ang_d = ang_h.pin_memory().to(dev, non_blocking=True) if n else ang_h.to(dev)
+            y0_d = None
+        n_save = int(num_range_save) if num_range_save else 0
+        out = {}
+        rs_d = traj_d = None
+        if n_save:
+            rs_np = np.linspace(source_range, receiver_range, n_save)
+            rs_d = torch.from_numpy(rs_np).to(dev)
+            traj_d = torch.empty((3, n, n_save), dtype=torch.float64, device=dev)
+            out["range_save"] = rs_np
+        final_d = torch.empty((3, n), dtype=torch.float64, device=dev)
+        nb_d = torch.empty(n, dtype=torch.int32, device=dev)
+        ns_d = torch.empty(n, dtype=torch.int32, device=dev)
+        st_d = torch.empty(n, dtype=torch.int32, device=dev)
+        cnt_d = torch.empty((_lib.N_COUNTERS, n), dtype=torch.int32, device=dev) if counters else None
+        flips_d = torch.empty(n, dtype=torch.int32, device=dev) if (ray_id_counts and n_save) else None
+
+        def ptr(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+
+        if n:
+            rc = L.prt_shoot_fan(
+                denv.handle, n, ptr(ang_d), ptr(y0_d), float(source_depth), float(source_range),
+                float(receiver_range), float(rtol), ATOL, int(bool(terminate_backwards)), n_save, ptr(rs_d),
+                ptr(traj_d), ptr(final_d), ptr(nb_d), ptr(ns_d), ptr(st_d), ptr(cnt_d),
+                int(bool(stored_convention)), ptr(flips_d), int(max_bounces), C.c_void_p(stream.cuda_stream),
+            )
+            _lib.check(rc, "prt_shoot_fan")
+        dev_out = dict(final=final_d, n_bottom=nb_d, n_surface=ns_d, status=st_d)
+        if traj_d is not None:
+            dev_out["traj"] = traj_d
+        if cnt_d is not None:
+            dev_out["counters"] = cnt_d
+        if flips_d is not None:
+            dev_out["p_sign_changes"] = flips_d
+        if not to_host:
+            out.update(dev_out)
+            return out
+        host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in dev_out.items()}
+        for k, v in dev_out.items():
+            host[k].copy_(v, non_blocking=True)
+        stream.synchronize()
+        out.update({k: v.numpy() for k, v in host.items()})
+    return out
+
+
+_RAISING = {
+    5: (ValueError, "A value in x_new is outside the interpolation range of the bottom-angle spline."),
+    6: (ValueError, "f(a) and f(b) must have different signs"),
+    7: (RuntimeError, "Failed to converge after 100 iterations."),
+}
+
+
+def _debug_print(status):
+    if status == 1:
+        print("Integration failed with message: Required step size is less than spacing between numbers.")
+    elif status == 2:
+        print("ray is vertical, terminating integration")
+    elif status == 3:
+        print("ray left bounding box, terminating integration")
+    elif status == 4:
+        print("ray bounced backwards, terminating integration")
+
+
+def _fan_from_device(res, stored_thetas, source_depth, backwards, keep):
+    """RayFan (stored sign convention) of the surviving rays ``keep`` of a stored-convention result."""
+    traj = res["traj"]
+    rs = -res["range_save"] if backwards else res["range_save"]
+    if keep.all():
+        ts, zs, ps = traj[0], traj[1], traj[2]
+    else:
+        ts, zs, ps = traj[0][keep], traj[1][keep], traj[2][keep]
+    m = ts.shape[0]
+    rs2 = np.broadcast_to(rs, (m, rs.shape[0]))
+    fan = RayFan.__new__(RayFan)
+    fan.thetas = np.asarray(stored_thetas, dtype=np.float64)[keep]
+    fan.rs, fan.ts, fan.zs, fan.ps = rs2, ts, zs, ps
+    fan.n_botts = res["n_bottom"][keep].astype(np.int64)
+    fan.n_surfs = res["n_surface"][keep].astype(np.int64)
+    fan.source_depths = np.full(m, source_depth)
+    flips = res.get("p_sign_changes")
+    if flips is not None and m > 0:
+        numbers = flips[keep] * np.sign(fan.thetas)
+        free = (fan.n_botts == 0) & (fan.n_surfs == 0)
+        fan.ray_ids = np.array([str(v) if f else f"{v}b" for v, f in zip(numbers, free)])
+    else:
+        fan.compute_rayids()
+    return fan
+
+
+def shoot_rays(source_depth, source_range, launch_angles, receiver_range, num_range_save, environment,
+               rtol=1e-9, terminate_backwards=True, n_processes=None, debug=True, flatearth=True):
+    """Integrate a fan of rays; same call as ``pygenray.shoot_rays``.  Returns a :class:`RayFan`.
+
+    ``n_processes`` is accepted and ignored (the fan is one GPU launch).  Dropped rays (vertical,
+    left the sound-speed grid, bounced backwards, step size underflow) are absent from the fan.
+    """
+    if type(launch_angles) is list:
+        launch_angles = np.array(launch_angles)
+    launch_angles = -np.asarray(launch_angles, dtype=np.float64)  # sign flip #1 (launch_rays.py:64-67)
+    small = launch_angles.shape[0] < _SMALL_FAN
+    backwards = receiver_range < source_range
+    denv = _device_environment(environment, flatearth, backwards)
+    src_i, rcv_i = (-source_range, -receiver_range) if backwards else (source_range, receiver_range)
+
+    if small and REPLICATE_SMALL_FAN_SIGN_QUIRK:
+        internal = -launch_angles  # shoot_ray() flips again (launch_rays.py:251)
+        stored = internal          # Ray.launch_angle = internal angle (launch_rays.py:313-320)
+    else:
+        internal = launch_angles
+        stored = -launch_angles    # ray.launch_angle = -launch_angles[k] (launch_rays.py:180-182)
+
+    res = shoot_fan_arrays(denv, source_depth, src_i, rcv_i, angles=internal, num_range_save=num_range_save,
+                           rtol=rtol, terminate_backwards=terminate_backwards, stored_convention=True,
+                           ray_id_counts=True)
+    status = res["status"]
+    if small:
+        for k in range(status.shape[0]):  # sequential branch: exceptions propagate, drops may print
+            st = int(status[k])
+            if st in _RAISING:
+                exc, msg = _RAISING[st]
+                raise exc(msg)
+            if debug and st != 0:
+                _debug_print(st)
+    return _fan_from_device(res, stored, source_depth, backwards, status == 0)
+
+
+def shoot_ray(source_depth, source_range, launch_angle, receiver_range, num_range_save, environment,
+              rtol=1e-9, terminate_backwards=True, debug=True, flatearth=True):
+    """Integrate one ray; same call as ``pygenray.shoot_ray``.  Returns a :class:`Ray` or ``None``.
+
+    ``Ray.launch_angle`` holds the INTERNAL angle (= -launch_angle), as in the reference.
+    """
+    launch_angle = -launch_angle
+    backwards = receiver_range < source_range
+    denv = _device_environment(environment, flatearth, backwards)
+    src_i, rcv_i = (-source_range, -receiver_range) if backwards else (source_range, receiver_range)
+    res = shoot_fan_arrays(denv, source_depth, src_i, rcv_i, angles=[launch_angle],
+                           num_range_save=num_range_save, rtol=rtol, terminate_backwards=terminate_backwards)
+    st = int(res["status"][0])
+    if st in _RAISING:
+        exc, msg = _RAISING[st]
+        raise exc(msg)
+    if st != 0:
+        if debug:
+            _debug_print(st)
+        return None
+    r = res["range_save"]
+    if backwards:
+        r = -r
+    return Ray(r, res["traj"][:, 0, :], int(res["n_bottom"][0]), int(res["n_surface"][0]), launch_angle,
+               source_depth)

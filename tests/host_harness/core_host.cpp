@@ -46,19 +46,21 @@ __attribute__((visibility("default"))) int hh_shoot_fan(void* env, int64_t n_ray
         } else {
             prt_initial_state(E, source_depth, source_range, angles_deg[i], T, z, p);
         }
-        prt_traj_sink sink{nullptr, nullptr, nullptr, 1};
+        prt_traj_sink sink{nullptr, nullptr, nullptr, 1, 1.0};
         prt_ray_result res;
         uint32_t cnt[PRT_CNT_N];
+        prt_shot S;
+        S.x_end = receiver_range; S.rtol = rtol; S.atol = atol; S.terminate_backwards = terminate_backwards;
+        S.n_save = 0; S.max_bounces = max_bounces; S.range_save = nullptr;
         if (out_traj && n_save > 0) {
             sink.T = out_traj + ((size_t)0 * n_rays + i) * n_save;
             sink.z = out_traj + ((size_t)1 * n_rays + i) * n_save;
             sink.p = out_traj + ((size_t)2 * n_rays + i) * n_save;
             for (int k = 0; k < n_save; ++k) sink.T[k] = sink.z[k] = sink.p[k] = NAN;
-            prt_integrate_ray<true>(E, T, z, p, source_range, receiver_range, rtol, atol, terminate_backwards != 0,
-                                    n_save, range_save, sink, max_bounces, res, cnt);
+            S.n_save = n_save; S.range_save = range_save;
+            prt_integrate_ray<true>(E, T, z, p, source_range, S, sink, res, cnt);
         } else {
-            prt_integrate_ray<false>(E, T, z, p, source_range, receiver_range, rtol, atol, terminate_backwards != 0, 0,
-                                     nullptr, sink, max_bounces, res, cnt);
+            prt_integrate_ray<false>(E, T, z, p, source_range, S, sink, res, cnt);
         }
         if (out_traj && n_save > 0 && res.status != PRT_RAY_OK)  // as prt_fan_kernel does for dropped rays
             for (int k = 0; k < n_save; ++k) sink.T[k] = sink.z[k] = sink.p[k] = NAN;

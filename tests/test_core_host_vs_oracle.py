@@ -1,0 +1,96 @@
+"""CPU-side bit parity: the product's per-ray routine (prt_core.h, compiled for the host by
+tests/host_harness) against the independent plain-C oracle, on the same seeded inputs.
+
+These run without a GPU; the `-m gpu` tests repeat them through libprt.so on the device.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_same_fan, make_env, oracle_env_from
+from oracle import cases
+from oracle import oracle as orc
+
+
+def _both(harness, oenv, zs, r0, R, angles, n_save, **kw):
+    rs = None if not n_save else np.linspace(r0, R, n_save)
+    o = orc.shoot_fan(oenv, zs, r0, R, angles_deg=angles, range_save=rs, **kw)
+    h = harness.shoot_fan(oenv, zs, r0, R, angles, range_save=rs, **kw)
+    return o, h
+
+
+def test_config1_munk_flat_earth(harness):
+    import pygenray_b200 as pr
+
+    oenv = oracle_env_from(pr.OceanEnvironment2D(), True)
+    o, h = _both(harness, oenv, 1000.0, 0.0, 100e3, np.linspace(-12, 12, 101), 1001)
+    assert (o["status"] == 0).all() and o["n_bottom"].sum() == 0
+    assert_same_fan(o, h, "config 1")
+
+
+def test_bounces_fine_grid(harness):
+    import pygenray_b200 as pr
+
+    oenv = oracle_env_from(pr.OceanEnvironment2D(), True)
+    o, h = _both(harness, oenv, 1000.0, 0.0, 100e3, np.linspace(-40, 40, 161), 401)
+    assert o["n_bottom"].sum() > 100 and o["n_surface"].sum() > 100
+    assert_same_fan(o, h, "steep rays on the 1 m grid")
+
+
+def test_config2_range_dependent(harness):
+    oenv = oracle_env_from(make_env(cases.config2_arrays()), False)
+    o, h = _both(harness, oenv, 1000.0, 0.0, 500e3, np.linspace(-15, 15, 151), 201)
+    assert_same_fan(o, h, "config 2")
+
+
+def test_dropped_rays_and_status_codes(harness):
+    """Near-vertical, bbox-leaving and backwards-bouncing rays: statuses and NaN fills agree."""
+    oenv = oracle_env_from(make_env(cases.config2_arrays()), False)
+    o, h = _both(harness, oenv, 50.0, 0.0, 500e3, np.linspace(-89.5, 89.5, 90), 301)
+    assert set(np.unique(o["status"])) >= {0, 2, 4}
+    assert_same_fan(o, h, "status codes")
+
+
+def test_arrival_only_equals_saved_final(harness):
+    oenv = oracle_env_from(make_env(cases.config2_arrays()), False)
+    ang = np.linspace(-15, 15, 41)
+    a = harness.shoot_fan(oenv, 1000.0, 0.0, 300e3, ang)
+    b = harness.shoot_fan(oenv, 1000.0, 0.0, 300e3, ang, range_save=np.linspace(0, 300e3, 77))
+    assert np.array_equal(a["final"], b["final"], equal_nan=True)
+    assert np.array_equal(b["traj"][:, :, -1], b["final"], equal_nan=True)
+
+
+@pytest.mark.parametrize("rtol", [1e-6, 1e-12, 1e-15])
+def test_tolerances(harness, rtol):
+    """rtol below 100 eps is clamped (validate_tol); loose and tight tolerances walk the same code."""
+    oenv = oracle_env_from(make_env(cases.config2_arrays()), False)
+    o, h = _both(harness, oenv, 800.0, 0.0, 80e3, np.linspace(-14, 14, 15), 50, rtol=rtol)
+    assert_same_fan(o, h, f"rtol={rtol}")
+
+
+def test_terminate_backwards_false(harness):
+    oenv = oracle_env_from(make_env(cases.config2_arrays()), False)
+    o, h = _both(harness, oenv, 50.0, 0.0, 200e3, np.linspace(-80, 80, 33), 101, terminate_backwards=False)
+    assert_same_fan(o, h, "terminate_backwards=False")
+
+
+def test_nonuniform_grid_and_short_bathymetry(harness):
+    """Irregular range/depth grids exercise the hunt + bisection cell search; a bathymetry grid that
+    ends before the receiver makes bottom bounces leave the spline (BOTTOM_OOB)."""
+    rng = np.random.default_rng(7)
+    a = cases.config2_arrays(n_r=60, n_z=120, R=2e5)
+    r = np.sort(np.concatenate(([0.0, 2e5], rng.uniform(0, 2e5, 58))))
+    z = np.sort(np.concatenate(([0.0, 5500.0], rng.uniform(0, 5500.0, 118))))
+    c = np.array([cases.munk_ssp(z, 1300 - 200 * ri / 2e5) for ri in r])
+    a.update(r=r, z=z, c=c, bathy_r=np.linspace(0, 1.2e5, 30), bathy=np.linspace(4000, 4300, 30))
+    oenv = oracle_env_from(make_env(a), False)
+    o, h = _both(harness, oenv, 700.0, 0.0, 2e5, np.linspace(-20, 20, 81), 150)
+    assert (o["status"] == 5).any()
+    assert_same_fan(o, h, "non-uniform grid")
+
+
+def test_backwards_mirrored_environment(harness):
+    a = cases.config2_arrays()
+    oenv = oracle_env_from(make_env(a), False, mirror=True)
+    o, h = _both(harness, oenv, 300.0, -4e5, -1e5, np.linspace(-15, 15, 31), 120)
+    assert (o["status"] == 0).any()
+    assert_same_fan(o, h, "mirrored environment, negative ranges")

