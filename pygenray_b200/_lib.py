@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprt.so")
+LIB_PATH = os.environ.get("PRT_LIB_PATH") or os.path.join(_HERE, "libprt.so")  # override: build variants
 
 PRT_SUCCESS = 0
 RAY_STATUS = {

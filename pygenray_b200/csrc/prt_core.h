@@ -237,6 +237,23 @@ PRT_HD_NOINLINE double prt_asin(double x)
 // (integration_processes.py:152-157, 221-224), returning the cell edges {a[k], a[k+1]} with it.
 // Guess from the mean spacing, hunt a few cells, bisect as a fallback: result is exact for any
 // sorted grid; the guess only affects speed.
+// cold path of prt_locate: lower_bound over the n nodes (node i = pair[i].x, node n-1 = pair[n-2].y)
+PRT_HD_NOINLINE int prt_locate_bisect(const prt_d2* pair, int n, double v)
+{
+    const int m = n - 2;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = lo + ((hi - lo) >> 1);
+        double a = (mid <= m) ? prt_ld(&pair[mid].x) : prt_ld(&pair[m].y);
+        if (a < v) lo = mid + 1;
+        else hi = mid;
+    }
+    int g = lo - 1;
+    g = g > m ? m : g;
+    g = g < 0 ? 0 : g;
+    return g;
+}
+
 PRT_HD int prt_locate(const prt_d2* pair, int n, double x0, double inv, double v, prt_d2& edges)
 {
     const int m = n - 2;
@@ -249,25 +266,18 @@ PRT_HD int prt_locate(const prt_d2* pair, int n, double x0, double inv, double v
     double gf = (v - x0) * inv;
     g = (gf > 0.0) ? ((gf < (double)m) ? (int)gf : m) : 0;
     edges = prt_ld2(pair + g);
-    int it = 0;
-    for (;;) {
-        if (g > 0 && !(edges.x < v)) --g;
-        else if (g < m && edges.y < v) ++g;
-        else return g;
+#if defined(PRT_UNROLL_HUNT)
+#pragma unroll
+#else
+#pragma unroll 1  // measured: same speed as unrolled, a third less code (profiles/r01_variants.md)
+#endif
+    for (int it = 0; it < 4; ++it) {
+        const int step = (g > 0 && !(edges.x < v)) ? -1 : ((g < m && edges.y < v) ? 1 : 0);
+        if (step == 0) return g;
+        g += step;
         edges = prt_ld2(pair + g);
-        if (++it == 6) break;
     }
-    // fallback: lower_bound over the n nodes (node i = pair[i].x, node n-1 = pair[m].y)
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        int mid = lo + ((hi - lo) >> 1);
-        double a = (mid <= m) ? prt_ld(&pair[mid].x) : prt_ld(&pair[m].y);
-        if (a < v) lo = mid + 1;
-        else hi = mid;
-    }
-    g = lo - 1;
-    g = g > m ? m : g;
-    g = g < 0 ? 0 : g;
+    g = prt_locate_bisect(pair, n, v);
     edges = prt_ld2(pair + g);
     return g;
 }
@@ -275,7 +285,12 @@ PRT_HD int prt_locate(const prt_d2* pair, int n, double x0, double inv, double v
 // c(x, z) and dc/dz(x, z): bilinear_interp (integration_processes.py:101-174) evaluated ONCE for
 // both fields (the reference evaluates it twice with identical weights, :86-87).  The weight
 // divisions use the per-cell reciprocals 1/(x[i+1]-x[i]) tabulated at staging time.
-PRT_HD void prt_field(const prt_env_view& E, double x, double z, double& c, double& cz)
+#if defined(PRT_FIELD_NOINLINE)
+PRT_HD_NOINLINE
+#else
+PRT_HD
+#endif
+void prt_field(const prt_env_view& E, double x, double z, double& c, double& cz)
 {
     prt_d2 re, ze;
     int i = prt_locate(E.rpair, E.n_r, E.r0, E.r_inv, x, re);
@@ -620,6 +635,65 @@ struct prt_ray {
         if (tn - S.x_end > 0.0) tn = S.x_end;
         const double hh = tn - t;
         h_abs = fabs(hh);
+#if defined(PRT_ROLL_STAGES)
+        // rk_step (rk.py:14-71).  The six stage evaluations share ONE copy of the right-hand side: a
+        // rolled loop whose body switches on the stage number (warp-uniform, so no divergence) keeps
+        // the hot loop inside the instruction cache; the stage values stay in named registers.
+        double k2z = 0, k2p = 0, k3T = 0, k3z = 0, k3p = 0, k4T = 0, k4z = 0, k4p = 0, k5T = 0, k5z = 0, k5p = 0;
+        double k6T = 0, k6z = 0, k6p = 0, k7T = 0, k7z = 0, k7p = 0, c_new = 0;
+        double nT = 0, nz = 0, np_ = 0;
+#pragma unroll 1
+        for (int s = 2; s <= 7; ++s) {
+            double xs, a, b;
+            switch (s) {
+            case 2:
+                xs = PRT_FMA(C2, hh, t);
+                a = A21 * f1;
+                b = A21 * f2;
+                break;
+            case 3:
+                xs = PRT_FMA(C3, hh, t);
+                a = A31 * f1; a = PRT_FMA(A32, k2z, a);
+                b = A31 * f2; b = PRT_FMA(A32, k2p, b);
+                break;
+            case 4:
+                xs = PRT_FMA(C4, hh, t);
+                a = A41 * f1; a = PRT_FMA(A42, k2z, a); a = PRT_FMA(A43, k3z, a);
+                b = A41 * f2; b = PRT_FMA(A42, k2p, b); b = PRT_FMA(A43, k3p, b);
+                break;
+            case 5:
+                xs = PRT_FMA(C5, hh, t);
+                a = A51 * f1; a = PRT_FMA(A52, k2z, a); a = PRT_FMA(A53, k3z, a); a = PRT_FMA(A54, k4z, a);
+                b = A51 * f2; b = PRT_FMA(A52, k2p, b); b = PRT_FMA(A53, k3p, b); b = PRT_FMA(A54, k4p, b);
+                break;
+            case 6:
+                xs = t + hh;
+                a = A61 * f1; a = PRT_FMA(A62, k2z, a); a = PRT_FMA(A63, k3z, a); a = PRT_FMA(A64, k4z, a); a = PRT_FMA(A65, k5z, a);
+                b = A61 * f2; b = PRT_FMA(A62, k2p, b); b = PRT_FMA(A63, k3p, b); b = PRT_FMA(A64, k4p, b); b = PRT_FMA(A65, k5p, b);
+                break;
+            default: {  // 7: y_new, then f_new (FSAL)
+                xs = t + hh;
+                double sT = B1 * f0; sT = PRT_FMA(B3, k3T, sT); sT = PRT_FMA(B4, k4T, sT); sT = PRT_FMA(B5, k5T, sT); sT = PRT_FMA(B6, k6T, sT);
+                a = B1 * f1; a = PRT_FMA(B3, k3z, a); a = PRT_FMA(B4, k4z, a); a = PRT_FMA(B5, k5z, a); a = PRT_FMA(B6, k6z, a);
+                b = B1 * f2; b = PRT_FMA(B3, k3p, b); b = PRT_FMA(B4, k4p, b); b = PRT_FMA(B5, k5p, b); b = PRT_FMA(B6, k6p, b);
+                nT = PRT_FMA(hh, sT, T);
+                break;
+            }
+            }
+            const double zs = PRT_FMA(hh, a, z), ps = PRT_FMA(hh, b, p);
+            double dT, dz, dp, cc;
+            prt_rhs(E, xs, zs, ps, dT, dz, dp, cc);
+            switch (s) {
+            case 2: k2z = dz; k2p = dp; break;
+            case 3: k3T = dT; k3z = dz; k3p = dp; break;
+            case 4: k4T = dT; k4z = dz; k4p = dp; break;
+            case 5: k5T = dT; k5z = dz; k5p = dp; break;
+            case 6: k6T = dT; k6z = dz; k6p = dp; break;
+            default: k7T = dT; k7z = dz; k7p = dp; c_new = cc; nz = zs; np_ = ps; break;
+            }
+        }
+#else
+        // rk_step (rk.py:14-71), fully unrolled: six inlined right-hand sides
         double k2T, k2z, k2p, k3T, k3z, k3p, k4T, k4z, k4p, k5T, k5z, k5p, k6T, k6z, k6p, k7T, k7z, k7p, cc, c_new;
         double a, b;
         prt_rhs(E, PRT_FMA(C2, hh, t), PRT_FMA(hh, A21 * f1, z), PRT_FMA(hh, A21 * f2, p), k2T, k2z, k2p, cc);
@@ -640,6 +714,8 @@ struct prt_ray {
         double sp = B1 * f2; sp = PRT_FMA(B3, k3p, sp); sp = PRT_FMA(B4, k4p, sp); sp = PRT_FMA(B5, k5p, sp); sp = PRT_FMA(B6, k6p, sp);
         const double nT = PRT_FMA(hh, sT, T), nz = PRT_FMA(hh, sz, z), np_ = PRT_FMA(hh, sp, p);
         prt_rhs(E, t + hh, nz, np_, k7T, k7z, k7p, c_new);  // f_new (FSAL)
+        (void)k2T;
+#endif
         c_nfev += 6;
         double eT = E1 * f0; eT = PRT_FMA(E3, k3T, eT); eT = PRT_FMA(E4, k4T, eT); eT = PRT_FMA(E5, k5T, eT); eT = PRT_FMA(E6, k6T, eT); eT = PRT_FMA(E7, k7T, eT);
         double ez = E1 * f1; ez = PRT_FMA(E3, k3z, ez); ez = PRT_FMA(E4, k4z, ez); ez = PRT_FMA(E5, k5z, ez); ez = PRT_FMA(E6, k6z, ez); ez = PRT_FMA(E7, k7z, ez);

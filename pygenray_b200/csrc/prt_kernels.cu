@@ -118,8 +118,14 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_env_view& E, prt_ra
     }
 }
 
+// 4 resident blocks of 128 threads per SM = 128 registers per thread.  Measured on B200 (1M-ray fan):
+// 3 blocks / 142 regs, no spills: 160 ms; 4 blocks / 128 regs, ~100 B spilled: 100 ms; 5 blocks / 96
+// regs, ~300 B spilled: 98 ms (profiles/r01_variants.md) -- occupancy beats spill-free code here.
+#ifndef PRT_MIN_BLOCKS
+#define PRT_MIN_BLOCKS 4
+#endif
 template <bool SAVE>
-__global__ void __launch_bounds__(128) prt_fan_kernel(const __grid_constant__ prt_env_view E,
+__global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_fan_kernel(const __grid_constant__ prt_env_view E,
                                                       const __grid_constant__ prt_fan_params P)
 {
     const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,7 +324,7 @@ __global__ void prt_refine_init_kernel(prt_refine_state S, int64_t n_br, const d
     P.out_ray_status[b] = 0;
 }
 
-__global__ void __launch_bounds__(128) prt_refine_round_kernel(const __grid_constant__ prt_env_view E,
+__global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_refine_round_kernel(const __grid_constant__ prt_env_view E,
                                                                const __grid_constant__ prt_refine_params P,
                                                                prt_refine_state S, const int32_t* __restrict__ list_in,
                                                                int32_t* __restrict__ list_out, const int32_t* n_in,

@@ -1,0 +1,225 @@
+"""GPU parity: libprt.so (sm_100a kernels, called through the C ABI) against the CPU oracle, bit for bit,
+on the same seeded inputs; then the public API against the reference's golden vectors, and
+size-independent properties at BASELINE.json's full sizes.  Run with `-m gpu` on a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import assert_same_fan, golden, make_env, oracle_env_from
+from oracle import cases
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pr():
+    import pygenray_b200 as pr_
+
+    pr_._lib.require_gpu()
+    return pr_
+
+
+def _gpu_fan(pr, env, flatearth, zs, r0, R, angles, n_save, mirror=False, **kw):
+    arrs = pr._unpack_envi(env, flatearth=flatearth)
+    if mirror:
+        cin, cpin, rin, depths, dr, ba = pr._mirror_envi_arrays(arrs[0], arrs[1], arrs[2], arrs[4], arrs[5], arrs[6])
+        arrs = (cin, cpin, rin, arrs[3], depths, dr, ba)
+    denv = pr.DeviceEnvironment(*arrs)
+    res = pr.shoot_fan_arrays(denv, zs, r0, R, angles=angles, num_range_save=n_save, counters=True, **kw)
+    out = dict(final=res["final"].T.copy(), n_bottom=res["n_bottom"], n_surface=res["n_surface"],
+               status=res["status"], counters=res["counters"].T.astype(np.int64),
+               traj=np.transpose(res["traj"], (1, 0, 2)) if n_save else None)
+    denv.close()
+    return out
+
+
+def _oracle_fan(env, flatearth, zs, r0, R, angles, n_save, mirror=False, **kw):
+    oenv = oracle_env_from(env, flatearth, mirror=mirror)
+    rs = np.linspace(r0, R, n_save) if n_save else None
+    return orc.shoot_fan(oenv, zs, r0, R, angles_deg=angles, range_save=rs, **kw)
+
+
+CASES = {
+    "config1_munk": dict(env="default", flat=True, zs=1000.0, r0=0.0, R=100e3, ang=np.linspace(-12, 12, 101), n=1001),
+    "steep_bouncing_1m_grid": dict(env="default", flat=True, zs=1000.0, r0=0.0, R=100e3, ang=np.linspace(-40, 40, 321), n=401),
+    "config2_range_dependent": dict(env="cfg2", flat=False, zs=1000.0, r0=0.0, R=500e3, ang=np.linspace(-15, 15, 1000), n=201),
+    "status_codes": dict(env="cfg2", flat=False, zs=50.0, r0=0.0, R=500e3, ang=np.linspace(-89.5, 89.5, 180), n=301),
+    "arrival_only": dict(env="cfg2", flat=False, zs=1000.0, r0=0.0, R=500e3, ang=np.linspace(-15, 15, 777), n=0),
+    "mirrored": dict(env="cfg2", flat=False, zs=300.0, r0=-4e5, R=-1e5, ang=np.linspace(-15, 15, 97), n=120, mirror=True),
+    "single_ray": dict(env="cfg2", flat=False, zs=1000.0, r0=0.0, R=200e3, ang=np.array([7.5]), n=33),
+    "ragged_33_rays": dict(env="cfg2", flat=False, zs=1000.0, r0=0.0, R=200e3, ang=np.linspace(-14, 14, 33), n=2),
+}
+
+
+def _env(pr, name):
+    return pr.OceanEnvironment2D() if name == "default" else make_env(cases.config2_arrays())
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fan_bit_identical_to_oracle(pr, name):
+    c = CASES[name]
+    env = _env(pr, c["env"])
+    g = _gpu_fan(pr, env, c["flat"], c["zs"], c["r0"], c["R"], c["ang"], c["n"], mirror=c.get("mirror", False))
+    o = _oracle_fan(env, c["flat"], c["zs"], c["r0"], c["R"], c["ang"], c["n"], mirror=c.get("mirror", False))
+    assert_same_fan(o, g, name)
+
+
+@pytest.mark.parametrize("rtol,tb", [(1e-6, True), (1e-12, True), (1e-9, False)])
+def test_fan_options_bit_identical(pr, rtol, tb):
+    env = make_env(cases.config2_arrays())
+    ang = np.linspace(-80, 80, 65)
+    g = _gpu_fan(pr, env, False, 50.0, 0.0, 150e3, ang, 64, rtol=rtol, terminate_backwards=tb)
+    o = _oracle_fan(env, False, 50.0, 0.0, 150e3, ang, 64, rtol=rtol, terminate_backwards=tb)
+    assert_same_fan(o, g, f"rtol={rtol} terminate_backwards={tb}")
+
+
+def test_empty_fan_and_argument_errors(pr):
+    env = make_env(cases.config2_arrays())
+    denv = pr.DeviceEnvironment(*pr._unpack_envi(env, flatearth=False))
+    res = pr.shoot_fan_arrays(denv, 1000.0, 0.0, 1e5, angles=np.array([]), num_range_save=11)
+    assert res["final"].shape == (3, 0) and res["traj"].shape == (3, 0, 11)
+    with pytest.raises(ValueError):
+        pr.shoot_fan_arrays(denv, 1000.0, 1e5, 0.0, angles=[1.0])
+    L = pr._lib.load()
+    assert L.prt_shoot_fan(denv.handle, 4, None, None, 0.0, 0.0, 1.0, 1e-9, 1e-6, 1, 0, None, None, None, None, None,
+                           None, None, 0, None, 0, None) == 1  # PRT_ERR_ARG
+    assert b"angles_dev" in L.prt_last_error()
+
+
+def test_host_pointer_entry_point(pr):
+    """prt_shoot_fan_host: the call a non-Python host binds (host arrays in/out)."""
+    env = make_env(cases.config2_arrays())
+    arrs = pr._unpack_envi(env, flatearth=False)
+    denv = pr.DeviceEnvironment(*arrs)
+    L = pr._lib.load()
+    ang = np.linspace(-15, 15, 257)
+    n, n_save = len(ang), 50
+    rs = np.linspace(0, 3e5, n_save)
+    traj = np.empty((3, n, n_save)); fin = np.empty((3, n)); nb = np.zeros(n, np.int32); ns = np.zeros(n, np.int32)
+    st = np.zeros(n, np.int32); cnt = np.zeros((6, n), np.uint32); flips = np.zeros(n, np.int32)
+    rc = L.prt_shoot_fan_host(denv.handle, n, ang.ctypes.data, None, 1000.0, 0.0, 3e5, 1e-9, 1e-6, 1, n_save,
+                              rs.ctypes.data, traj.ctypes.data, fin.ctypes.data, nb.ctypes.data, ns.ctypes.data,
+                              st.ctypes.data, cnt.ctypes.data, 0, flips.ctypes.data, 0)
+    assert rc == 0, L.prt_last_error()
+    o = _oracle_fan(env, False, 1000.0, 0.0, 3e5, ang, n_save)
+    g = dict(final=fin.T.copy(), n_bottom=nb, n_surface=ns, status=st, counters=cnt.T.astype(np.int64),
+             traj=np.transpose(traj, (1, 0, 2)))
+    assert_same_fan(o, g, "prt_shoot_fan_host")
+    ok = st == 0
+    assert np.array_equal(flips[ok], np.sum(np.diff(np.sign(traj[2][ok])) != 0, axis=1))
+
+
+# ---- public API vs the reference's golden vectors ------------------------------------------------
+def test_shoot_rays_config1_against_reference_fan(pr):
+    g = golden("ref_cfg1_jit.npz")
+    fan = pr.shoot_rays(1000.0, 0.0, g["user_angles"], 100e3, 101, pr.OceanEnvironment2D(), rtol=1e-9, debug=False)
+    assert np.array_equal(fan.thetas, g["fan_thetas"]) and np.array_equal(fan.rs, g["fan_rs"])
+    assert np.array_equal(fan.n_botts, g["fan_n_botts"]) and np.array_equal(fan.n_surfs, g["fan_n_surfs"])
+    assert np.array_equal(fan.ray_ids, g["fan_ray_ids"])
+    assert np.abs(fan.ts - g["fan_ts"]).max() < 1e-9      # north star: 1e-6 s
+    assert np.abs(fan.zs - g["fan_zs"]).max() < 1e-5      # north star: 1e-3 m
+    assert np.abs(fan.ps - g["fan_ps"]).max() * 1500 < 1e-9  # north star: 1e-6 rad
+    assert np.array_equal(fan.source_depths, g["fan_source_depths"])
+
+
+def test_shoot_rays_small_fan_reference_fixture(pr):
+    """< 70 angles: the double sign flip of the reference, pinned by its own regression fixture."""
+    g = golden("ref_fixture_jit.npz")
+    z = np.linspace(0.0, 6000.0, 400); r = np.linspace(0.0, 50e3, 30)
+    env = make_env(dict(c=np.outer(np.ones(30), cases.munk_ssp(z)), r=r, z=z, bathy=np.full(30, 5000.0), bathy_r=r))
+    fan = pr.shoot_rays(1300.0, 0.0, [-8.0, -4.0, 0.0, 4.0, 8.0], 50e3, 50, env, n_processes=1, debug=False,
+                        flatearth=False)
+    np.testing.assert_allclose(fan.ts, g["fixture_ts"], atol=1e-5)  # see test_oracle_vs_reference.py for 1e-5
+    np.testing.assert_allclose(fan.zs, g["fixture_zs"], atol=0.1)
+    np.testing.assert_allclose(fan.ps, g["fixture_ps"], atol=0.1)
+    np.testing.assert_array_equal(fan.n_botts, g["fixture_n_botts"])
+    np.testing.assert_array_equal(fan.n_surfs, g["fixture_n_surfs"])
+    assert np.array_equal(fan.thetas, g["fan_thetas"]) and np.array_equal(fan.ray_ids, g["fan_ray_ids"])
+
+
+def test_shoot_ray_conventions_and_drops(pr):
+    g = golden("ref_physics_jit.npz")
+    z = np.linspace(0.0, 6000.0, 600); r = np.linspace(0.0, 100e3, 50)
+    env = make_env(dict(c=np.outer(np.ones(50), cases.munk_ssp(z)), r=r, z=z, bathy=np.full(50, 5000.0), bathy_r=r))
+    ray = pr.shoot_ray(1000.0, 0.0, -5.0, 100e3, 200, env, rtol=1e-9, flatearth=False, debug=False)
+    assert ray.launch_angle == float(g["D_5_la"]) == 5.0
+    assert np.array_equal(ray.r, g["D_5_r"]) and ray.n_bottom == 0 and ray.n_surface == 0
+    assert np.abs(ray.t - g["D_5_t"]).max() < 1e-4 and np.abs(ray.z - g["D_5_z"]).max() < 0.5
+    z5 = np.linspace(0.0, 6000.0, 600); r5 = np.linspace(0.0, 50e3, 50)
+    env5 = make_env(dict(c=np.outer(np.ones(50), cases.munk_ssp(z5)), r=r5, z=z5, bathy=np.full(50, 5000.0), bathy_r=r5))
+    assert pr.shoot_ray(1000.0, 0.0, -90.0, 10e3, 50, env5, rtol=1e-6, flatearth=False, debug=False) is None
+    assert bool(g["F_munk_-90.0_none"])
+    # backwards shot: end points exact (reference test G)
+    zc = np.linspace(0.0, 5000.0, 200); rc = np.linspace(0.0, 100e3, 20)
+    envc = make_env(dict(c=np.full((20, 200), 1500.0), r=rc, z=zc, bathy=np.full(20, 4500.0), bathy_r=rc))
+    ray = pr.shoot_ray(200.0, 30e3, -10.0, 0.0, 60, envc, rtol=1e-9, flatearth=False, debug=False)
+    assert ray.r[0] == 30e3 and ray.r[-1] == 0.0
+    assert np.abs(ray.t - g["G_const_t"]).max() < 1e-9 and np.abs(ray.z - g["G_const_z"]).max() < 1e-6
+    with pytest.raises(Exception, match="monotonically"):
+        bad = make_env(dict(c=np.full((20, 200), 1500.0), r=rc[::-1], z=zc, bathy=np.full(20, 4500.0), bathy_r=rc))
+        pr.shoot_ray(200.0, 0.0, -10.0, 1e4, 10, bad, flatearth=False)
+
+
+def test_find_eigenrays_against_reference(pr):
+    g = golden("ref_eigen_jit.npz")
+    env = pr.OceanEnvironment2D()
+    fan = pr.shoot_rays(1000.0, 0.0, np.linspace(-12, 12, 101), 100e3, 101, env, rtol=1e-9, debug=False)
+    rds = [float(v) for v in g["receiver_depths"]]
+    er = pr.find_eigenrays(fan, rds, 1000.0, 0.0, 100e3, 101, env, ztol=1e-3, max_iter=20, debug=False)
+    for i, rd in enumerate(rds):
+        assert er.num_eigenrays[rd] == int(g[f"e{i}_num"]) and er.num_eigenrays_found[i] == int(g[f"e{i}_found"])
+        assert np.abs(np.radians(er.launch_angles[i] - g[f"e{i}_launch"])).max() < 1e-6
+        assert np.abs(er.ts[i][:, -1] - g[f"e{i}_ts"][:, -1]).max() < 1e-6
+        assert np.abs(er.zs[i][:, -1] + rd).max() < 1e-3
+        assert np.array_equal(er.ray_id[i], g[f"e{i}_ray_id"]) and np.array_equal(er.ray_id_int[i], g[f"e{i}_ray_id_int"])
+        assert np.array_equal(er.n_botts[i], g[f"e{i}_nb"]) and np.array_equal(er.n_surfs[i], g[f"e{i}_ns"])
+        assert np.abs(np.radians(er.received_angles[i] - g[f"e{i}_recv"])).max() < 1e-6
+        assert np.array_equal(er.rs[i], g[f"e{i}_rs"])
+
+
+def test_eigenray_refinement_bit_identical_to_oracle(pr):
+    """Brackets over 16 receiver depths on the range-dependent grid; device regula falsi == oracle."""
+    env = make_env(cases.config2_arrays())
+    fan = pr.shoot_rays(1000.0, 0.0, np.linspace(-14, 14, 400), 300e3, 31, env, rtol=1e-9, debug=False, flatearth=False)
+    rds = np.linspace(300.0, 4000.0, 16)
+    denv = pr.DeviceEnvironment(*pr._unpack_envi(env, flatearth=False))
+    br, counts = pr.find_brackets(fan.zs[:, -1], fan.thetas, rds)
+    # bracketing == numpy restatement of eigenrays.py:62-79
+    exp = [np.where(np.diff(np.sign(fan.zs[:, -1] + rd)))[0] for rd in rds]
+    assert np.array_equal(counts, [len(k) for k in exp])
+    assert np.array_equal(br["k"].cpu().numpy(), np.concatenate(exp))
+    ref = pr.refine_brackets(denv, br, 1000.0, 0.0, 300e3, ztol=1e-3, max_iter=20)
+    host = {k: v.cpu().numpy() for k, v in br.items()}
+    o = orc.refine_brackets(oracle_env_from(env, False), host["z1"], host["z2"], host["th1"], host["th2"], host["rd"],
+                            1000.0, 0.0, 300e3, ztol=1e-3, max_iter=20)
+    assert np.array_equal(ref["status"].cpu().numpy(), o["status"])
+    assert np.array_equal(ref["shots"].cpu().numpy(), o["shots"])
+    assert np.array_equal(ref["theta"].cpu().numpy(), o["theta"], equal_nan=True)
+    assert np.array_equal(ref["final"].cpu().numpy().T, o["final"], equal_nan=True)
+    assert (o["status"] == 0).sum() > 20
+
+
+# ---- full-size properties (BASELINE.json sizes; no oracle pass over the whole set) -----------------
+def test_config2_full_size_properties(pr):
+    env = make_env(cases.config2_arrays())
+    arrs = pr._unpack_envi(env, flatearth=False)
+    denv = pr.DeviceEnvironment(*arrs)
+    ang = np.linspace(-15, 15, 10000)
+    a = pr.shoot_fan_arrays(denv, 1000.0, 0.0, 500e3, angles=ang, num_range_save=1001, counters=True)
+    b = pr.shoot_fan_arrays(denv, 1000.0, 0.0, 500e3, angles=ang[::-1].copy(), num_range_save=0)
+    # determinism + independence of rays: reversing the fan order permutes the arrival table
+    assert np.array_equal(a["final"], b["final"][:, ::-1], equal_nan=True)
+    assert np.array_equal(a["status"], b["status"][::-1])
+    ok = a["status"] == 0
+    assert ok.mean() > 0.98
+    # last save column is the exact final state; travel time increases along every surviving ray
+    assert np.array_equal(a["traj"][:, ok, -1], a["final"][:, ok])
+    assert (np.diff(a["traj"][0][ok], axis=1) > 0).all()
+    assert not np.isnan(a["traj"][:, ok]).any() and np.isnan(a["traj"][:, ~ok]).all()
+    # a 200-ray subsample against the oracle, bit for bit
+    sub = np.arange(0, 10000, 50)
+    o = _oracle_fan(env, False, 1000.0, 0.0, 500e3, ang[sub], 1001)
+    assert np.array_equal(np.transpose(a["traj"][:, sub], (1, 0, 2)), o["traj"], equal_nan=True)
+    assert np.array_equal(a["n_bottom"][sub], o["n_bottom"]) and np.array_equal(a["n_surface"][sub], o["n_surface"])
