@@ -49,10 +49,14 @@ def workload(name, rank=0, world=1):
         a = cases.config2_arrays()
         n, lim, R, ns, flat = 10000, 15.0, 500e3, 1001, False
         label = "cfg2: range-dependent 200x500 gridded SSP + seamount bathymetry, 10k rays +-15deg, 500 km, 1001 save pts"
+    # weak scaling: an N x n-ray fan dealt to the ranks in cyclic blocks of 32 angles (pygenray_b200.dist)
+    from pygenray_b200.dist import shard_indices
+
     all_angles = np.linspace(-lim, lim, n * world)
+    mine = shard_indices(n * world, rank, world)
     return dict(arrays=a, flatearth=flat, source_depth=1000.0, source_range=0.0, receiver_range=R,
-                angles=np.ascontiguousarray(all_angles[rank::world]), n_save=ns, label=label, name=name,
-                rays_per_gpu=n)
+                angles=np.ascontiguousarray(all_angles[mine]), n_total=n * world, n_save=ns, label=label,
+                name=name, rays_per_gpu=n)
 
 
 def make_env(pr, a, flat):
@@ -192,8 +196,7 @@ def run_b200(args):
     st_d = torch.empty(n, dtype=torch.int32, device=dev)
     cnt_d = torch.empty((6, n), dtype=torch.int32, device=dev)
     flips_d = torch.empty(n, dtype=torch.int32, device=dev) if n_save else None
-    table_d = torch.empty((n, 6), dtype=torch.float64, device=dev)  # arrival record: T z p nb ns status
-    gathered = torch.empty((world * n, 6), dtype=torch.float64, device=dev) if world > 1 else None
+    from pygenray_b200 import dist as pdist
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
@@ -205,12 +208,9 @@ def run_b200(args):
                              w["receiver_range"], 1e-9, 1e-6, 1, n_save, p(rs_d), p(traj_d), p(final_d), p(nb_d),
                              p(ns_d), p(st_d), p(cnt_d), 1, p(flips_d), 1 << 20, C.c_void_p(stream.cuda_stream))
         _lib.check(rc, "prt_shoot_fan")
-        if world > 1:  # the path's only exchange: gather the arrival tables (36 B/ray payload)
-            table_d[:, :3] = final_d.t()
-            table_d[:, 3] = nb_d
-            table_d[:, 4] = ns_d
-            table_d[:, 5] = st_d
-            dist.all_gather_into_tensor(gathered, table_d)
+        if world > 1:  # the path's only exchange: all-gather the arrival records (6 doubles per ray)
+            rec = pdist.records_from_result(dict(final=final_d, n_bottom=nb_d, n_surface=ns_d, status=st_d))
+            pdist.all_gather_arrivals(rec, w["n_total"], rank, world)
 
     def barrier():
         if world > 1:

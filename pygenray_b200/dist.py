@@ -1,0 +1,82 @@
+"""Multi-GPU fan shooting: one process per GPU (torchrun), launch angles sharded, arrival tables gathered.
+
+The reference's only parallelism is a multiprocessing pool over launch angles
+(/root/reference/src/pygenray/launch_rays.py:133-164); rays never exchange data, so the fan shards
+with no data-path collective.  Launch angles are dealt to ranks in cyclic blocks of 32 (one warp of
+neighbouring angles stays together, cost per ray grows with |angle| so contiguous chunks would
+imbalance), every rank stages its own copy of the environment (<= tens of MB), and the only
+collective is ONE all-gather of the fixed-size arrival records (T, z, p, n_bottom, n_surface, status:
+6 doubles per ray) over NCCL/NVLink.  Trajectories stay sharded on the GPU that produced them.
+Eigenray bracketing needs neighbouring rays in angle order, so it runs on the gathered table.
+"""
+import numpy as np
+
+__all__ = ["shard_indices", "all_gather_arrivals", "shoot_fan_sharded", "RECORD_WIDTH"]
+
+BLOCK = 32
+RECORD_WIDTH = 6  # T, z, p, n_bottom, n_surface, status
+
+
+def shard_indices(n_rays, rank, world, block=BLOCK):
+    """Indices of the rays owned by ``rank``: blocks of ``block`` consecutive angles dealt round-robin."""
+    idx = np.arange(n_rays, dtype=np.int64)
+    return idx[(idx // block) % world == rank]
+
+
+def shard_sizes(n_rays, world, block=BLOCK):
+    return [int(shard_indices(n_rays, r, world, block).shape[0]) for r in range(world)]
+
+
+def all_gather_arrivals(local_records, n_rays, rank, world, block=BLOCK, group=None):
+    """All-gather the per-rank arrival records and put them back in launch-angle order.
+
+    ``local_records``: float64 tensor [n_local, RECORD_WIDTH] on the rank's device (CUDA with NCCL, CPU
+    with gloo).  Returns a [n_rays, RECORD_WIDTH] tensor on the same device, identical on every rank.
+    """
+    import torch  # noqa: PLC0415
+    import torch.distributed as dist  # noqa: PLC0415
+
+    sizes = shard_sizes(n_rays, world, block)
+    assert local_records.shape[0] == sizes[rank], "local shard has the wrong number of rays"
+    if world == 1:
+        return local_records
+    pad = max(sizes)
+    buf = torch.zeros((pad, RECORD_WIDTH), dtype=torch.float64, device=local_records.device)
+    buf[: sizes[rank]] = local_records
+    gathered = torch.empty((world * pad, RECORD_WIDTH), dtype=torch.float64, device=local_records.device)
+    dist.all_gather_into_tensor(gathered, buf, group=group)
+    out = torch.empty((n_rays, RECORD_WIDTH), dtype=torch.float64, device=local_records.device)
+    for r in range(world):
+        idx = torch.from_numpy(shard_indices(n_rays, r, world, block)).to(local_records.device)
+        out[idx] = gathered[r * pad: r * pad + sizes[r]]
+    return out
+
+
+def records_from_result(res):
+    """[n, 6] float64 arrival records from a shoot_fan_arrays(to_host=False) result (device tensors)."""
+    import torch  # noqa: PLC0415
+
+    final = res["final"]
+    rec = torch.empty((final.shape[1], RECORD_WIDTH), dtype=torch.float64, device=final.device)
+    rec[:, :3] = final.t()
+    rec[:, 3] = res["n_bottom"]
+    rec[:, 4] = res["n_surface"]
+    rec[:, 5] = res["status"]
+    return rec
+
+
+def shoot_fan_sharded(denv, source_depth, source_range, receiver_range, angles, rank, world, **kwargs):
+    """Shoot this rank's share of ``angles`` (internal angles, full fan on every rank) and all-gather.
+
+    Returns ``(table, local)``: the gathered [n_rays, 6] arrival table (device tensor, same on all ranks)
+    and this rank's own shoot_fan_arrays result (trajectories stay local).  ``kwargs`` go to
+    :func:`pygenray_b200.shoot_fan_arrays`.
+    """
+    from .launch_rays import shoot_fan_arrays  # noqa: PLC0415
+
+    angles = np.ascontiguousarray(angles, dtype=np.float64)
+    mine = shard_indices(angles.shape[0], rank, world)
+    kwargs["to_host"] = False
+    local = shoot_fan_arrays(denv, source_depth, source_range, receiver_range, angles=angles[mine], **kwargs)
+    table = all_gather_arrivals(records_from_result(local), angles.shape[0], rank, world)
+    return table, local

@@ -121,31 +121,29 @@ def find_eigenrays(rays, receiver_depths, source_depth, source_range, receiver_r
     # final shot of the converged launch angles with the save grid: shoot_ray(theta) -> internal -theta,
     # and find_eigenrays flips Ray.launch_angle back to theta (launch_rays.py:251, eigenrays.py:247-250)
     ok = status == _lib.EIG_CONVERGED
+    ok_pos = np.flatnonzero(ok)  # bracket index of each re-shot ray
     res = shoot_fan_arrays(denv, source_depth, src_i, rcv_i, angles=-theta[ok], num_range_save=num_range_save,
                            rtol=rtol, terminate_backwards=terminate_backwards, stored_convention=True,
                            ray_id_counts=True)
-    ok_index = np.cumsum(ok) - 1  # position of bracket b among the converged ones
+    alive = res["status"] == 0  # deterministic re-shot of a converged trial: always OK
 
     erays_dict, num_eigenrays, num_found, failed = {}, {}, {}, {}
     offsets = np.concatenate(([0], np.cumsum(counts)))
     for ridx, receiver_depth in enumerate(receiver_depths):
         lo, hi = int(offsets[ridx]), int(offsets[ridx + 1])
         num_eigenrays[receiver_depth] = hi - lo
-        sel = np.arange(lo, hi)
-        good = sel[ok[lo:hi]]
-        keep = np.zeros(res["status"].shape[0], dtype=bool)
-        keep[ok_index[good]] = True
-        keep &= res["status"] == 0
-        stored_thetas = np.full(res["status"].shape[0], np.nan)
-        stored_thetas[ok_index[good]] = theta[good]
-        erays_dict[ridx] = _fan_from_device(res, stored_thetas, source_depth, backwards, keep)
+        rows = np.flatnonzero((ok_pos >= lo) & (ok_pos < hi) & alive)  # rows of `res` of this receiver
+        sub = {k: (v[:, rows] if k in ("final", "traj") else (v[rows] if k != "range_save" else v))
+               for k, v in res.items()}
+        sub["kept"] = np.arange(rows.shape[0])
+        erays_dict[ridx] = _fan_from_device(sub, theta[ok_pos[rows]], source_depth, backwards)
         failed[ridx] = []
-        for b in sel[~ok[lo:hi]]:
+        for b in np.arange(lo, hi)[~ok[lo:hi]]:
             if trial_theta_failed[b]:
                 print(f"Failed to find eigen ray for receiver depth {rd_all[b]} [m]: a trial ray was dropped")
             # the Pool branch of the reference (> 5 brackets) reports every failure with the LAST
             # bracket's angles (stale loop index, eigenrays.py:160-164); the sequential one is exact
             j = hi - 1 if (hi - lo) > _POOL_THRESHOLD else b
             failed[ridx].append((th1[j], th2[j]))
-        num_found[ridx] = int(keep.sum())
+        num_found[ridx] = int(rows.shape[0])
     return EigenRays(receiver_depths, erays_dict, environment, num_eigenrays, num_found, failed)

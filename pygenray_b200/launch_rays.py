@@ -177,14 +177,15 @@ def _device_environment(environment, flatearth, backwards, device=None):
 def shoot_fan_arrays(denv, source_depth, source_range, receiver_range, angles=None, y0s=None,
                      num_range_save=0, rtol=1e-9, terminate_backwards=True, counters=False,
                      stored_convention=False, ray_id_counts=False, max_bounces=_lib.DEFAULT_MAX_BOUNCES,
-                     to_host=True):
+                     to_host=True, compact=False):
     """Shoot ``n`` rays on the GPU.  ``angles`` are INTERNAL launch angles [deg] (positive = downwards).
 
     Returns a dict: ``final (3,n)`` [T, z, p], ``n_bottom``, ``n_surface``, ``status`` (n,), and, when
     ``num_range_save > 0``, ``range_save (N,)`` and ``traj (3,n,N)``; optional ``counters (6,n)`` and
     ``p_sign_changes (n,)``.  z and p are in the ODE convention (z positive down) unless
     ``stored_convention`` (then the trajectory holds -z and -p as ``Ray`` stores them).  Arrays are
-    numpy (pinned-memory copies) when ``to_host`` else CUDA tensors.
+    numpy (pinned-memory copies) when ``to_host`` else CUDA tensors.  ``compact`` drops the rays whose
+    status is not OK on the device before anything is copied (``kept`` = their indices in the input).
     """
     L = _lib.require_gpu()
     import torch  # noqa: PLC0415
@@ -237,6 +238,12 @@ def shoot_fan_arrays(denv, source_depth, source_range, receiver_range, angles=No
             dev_out["counters"] = cnt_d
         if flips_d is not None:
             dev_out["p_sign_changes"] = flips_d
+        if compact:
+            kept = torch.nonzero(st_d == 0).squeeze(1)
+            if kept.shape[0] < n:
+                dev_out = {k: (v.index_select(1, kept) if k in ("final", "traj", "counters") else v[kept])
+                           for k, v in dev_out.items()}
+            dev_out["kept"] = kept
         if not to_host:
             out.update(dev_out)
             return out
@@ -266,29 +273,22 @@ def _debug_print(status):
         print("ray bounced backwards, terminating integration")
 
 
-def _fan_from_device(res, stored_thetas, source_depth, backwards, keep):
-    """RayFan (stored sign convention) of the surviving rays ``keep`` of a stored-convention result."""
+def _fan_from_device(res, stored_thetas, source_depth, backwards):
+    """RayFan (stored sign convention) from a COMPACTED stored-convention result (survivors only)."""
     traj = res["traj"]
     rs = -res["range_save"] if backwards else res["range_save"]
-    if keep.all():
-        ts, zs, ps = traj[0], traj[1], traj[2]
-    else:
-        ts, zs, ps = traj[0][keep], traj[1][keep], traj[2][keep]
-    m = ts.shape[0]
-    rs2 = np.broadcast_to(rs, (m, rs.shape[0]))
+    kept = res["kept"]
+    m = traj.shape[1]
     fan = RayFan.__new__(RayFan)
-    fan.thetas = np.asarray(stored_thetas, dtype=np.float64)[keep]
-    fan.rs, fan.ts, fan.zs, fan.ps = rs2, ts, zs, ps
-    fan.n_botts = res["n_bottom"][keep].astype(np.int64)
-    fan.n_surfs = res["n_surface"][keep].astype(np.int64)
+    fan.thetas = np.asarray(stored_thetas, dtype=np.float64)[kept]
+    fan.rs = np.broadcast_to(rs, (m, rs.shape[0]))  # every ray shares the save grid (read-only view)
+    fan.ts, fan.zs, fan.ps = traj[0], traj[1], traj[2]
+    fan.n_botts = res["n_bottom"].astype(np.int64)
+    fan.n_surfs = res["n_surface"].astype(np.int64)
     fan.source_depths = np.full(m, source_depth)
     flips = res.get("p_sign_changes")
-    if flips is not None and m > 0:
-        numbers = flips[keep] * np.sign(fan.thetas)
-        free = (fan.n_botts == 0) & (fan.n_surfs == 0)
-        fan.ray_ids = np.array([str(v) if f else f"{v}b" for v, f in zip(numbers, free)])
-    else:
-        fan.compute_rayids()
+    if flips is not None:
+        fan._ray_id_numbers = flips * np.sign(fan.thetas)  # strings are built on first access of .ray_ids
     return fan
 
 
@@ -316,7 +316,7 @@ def shoot_rays(source_depth, source_range, launch_angles, receiver_range, num_ra
 
     res = shoot_fan_arrays(denv, source_depth, src_i, rcv_i, angles=internal, num_range_save=num_range_save,
                            rtol=rtol, terminate_backwards=terminate_backwards, stored_convention=True,
-                           ray_id_counts=True)
+                           ray_id_counts=True, compact=not small)
     status = res["status"]
     if small:
         for k in range(status.shape[0]):  # sequential branch: exceptions propagate, drops may print
@@ -326,7 +326,12 @@ def shoot_rays(source_depth, source_range, launch_angles, receiver_range, num_ra
                 raise exc(msg)
             if debug and st != 0:
                 _debug_print(st)
-    return _fan_from_device(res, stored, source_depth, backwards, status == 0)
+        kept = np.flatnonzero(status == 0)
+        if kept.shape[0] < status.shape[0]:
+            res = {k: (v[:, kept] if k in ("final", "traj") else (v[kept] if k != "range_save" else v))
+                   for k, v in res.items()}
+        res["kept"] = kept
+    return _fan_from_device(res, stored, source_depth, backwards)
 
 
 def shoot_ray(source_depth, source_range, launch_angle, receiver_range, num_range_save, environment,

@@ -77,9 +77,22 @@ class RayFan:
         if self.rs.ndim != 2 or self.rs.shape[0] == 0:
             self.ray_ids = np.array([], dtype=str)
             return
-        numbers = _ray_id_numbers(self.ps, self.thetas)
+        numbers = getattr(self, "_ray_id_numbers", None)  # counted on the device when the fan came from there
+        if numbers is None:
+            numbers = _ray_id_numbers(self.ps, self.thetas)
         free = (self.n_botts == 0) & (self.n_surfs == 0)
         self.ray_ids = np.array([str(n) if f else f"{n}b" for n, f in zip(numbers, free)])
+
+    @property
+    def ray_ids(self):
+        """Ray identifiers ('-3.0', '4.0b', ...), built lazily for fans assembled from device arrays."""
+        if self.__dict__.get("_ray_ids") is None:
+            self.compute_rayids()
+        return self.__dict__["_ray_ids"]
+
+    @ray_ids.setter
+    def ray_ids(self, value):
+        self.__dict__["_ray_ids"] = value
 
     # ---- container protocol -------------------------------------------------------------
     def __len__(self):
