@@ -63,6 +63,7 @@ struct prt_fan_params {
     int32_t max_bounces;
     int32_t stored_convention;
     int32_t park_wait;
+    int32_t lanes;  // rays per warp (32, 16, 8, 4, 2 or 1): small fans use partly filled warps, see pick_lanes()
 };
 
 // Lanes that hit a boundary wait (at most this many step attempts of the other lanes) so that the
@@ -72,7 +73,7 @@ static int park_wait_setting()
 {
     if (g_park_wait < 0) {
         const char* e = getenv("PRT_PARK_WAIT");
-        g_park_wait = e ? atoi(e) : 8;
+        g_park_wait = e ? atoi(e) : 16;  // measured best on B200 (profiles/r01_variants.md)
         if (g_park_wait < 0) g_park_wait = 0;
     }
     return g_park_wait;
@@ -128,8 +129,11 @@ template <bool SAVE>
 __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_fan_kernel(const __grid_constant__ prt_env_view E,
                                                       const __grid_constant__ prt_fan_params P)
 {
-    const int64_t ray = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = ray < P.n_rays;  // whole warps stay in the kernel: the driver is warp-synchronous
+    // P.lanes rays per warp (lanes >= P.lanes idle); whole warps stay in the kernel: the driver is warp-synchronous
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t ray = warp * P.lanes + lane;
+    const bool live = (lane < P.lanes) && (ray < P.n_rays);
     prt_shot S;
     S.x_end = P.receiver_range; S.rtol = P.rtol; S.atol = P.atol;
     S.terminate_backwards = P.terminate_backwards; S.n_save = P.n_save; S.max_bounces = P.max_bounces;
@@ -196,14 +200,25 @@ __global__ void prt_sign_changes_kernel(int64_t n_rays, int32_t n_save, const do
     if (lane == 0) out[ray] = local;
 }
 
-static int pick_block(int64_t n_units, int device)
+// Rays per warp.  The ray ODE is one long dependent FP64 chain (~20 cycles per DFMA on B200), so a
+// warp alone on a scheduler keeps the FP64 pipe ~5 % busy whatever its lane count.  A fan too small
+// to give every scheduler several full warps is therefore spread over MORE, partly filled warps
+// (fewer rays per warp) until the resident-warp capacity of the chip is used: latency hiding by
+// thread-level parallelism instead of idle schedulers.  Large fans use full warps.
+static int pick_lanes(int64_t n_units, int device)
 {
-    // spread small fans over all SMs: one warp per block until every SM has 4 warps
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("PRT_LANES");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (n_units <= (int64_t)sms * 4 * 32) return 32;
-    if (n_units <= (int64_t)sms * 8 * 64) return 64;
-    return 128;
+    const int64_t capacity = (int64_t)sms * PRT_MIN_BLOCKS * 4;  // resident warps (128-thread blocks)
+    int lanes = 32;
+    while (lanes > 2 && (n_units + lanes / 2 - 1) / (lanes / 2) <= capacity) lanes /= 2;
+    return lanes;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -287,7 +302,7 @@ struct prt_refine_params {
     int64_t n_br;
     const double* rd;
     double source_depth, source_range, receiver_range, rtol, atol, ztol;
-    int32_t terminate_backwards, max_iter, max_bounces, park_wait;
+    int32_t terminate_backwards, max_iter, max_bounces, park_wait, lanes;
     double* out_theta;
     double* out_final;
     int32_t *out_nb, *out_ns, *out_status, *out_shots, *out_ray_status;
@@ -331,8 +346,9 @@ __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_refine_round_kernel(c
                                                                int32_t* n_out)
 {
     const int n_active = *n_in;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = idx < n_active;
+    const int lane = threadIdx.x & 31;
+    const int idx = (int)(((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * P.lanes + lane);
+    const bool live = (lane < P.lanes) && (idx < n_active);
     const int b = live ? list_in[idx] : 0;
     const double rd = live ? P.rd[b] : 0.0;
     const double th = live ? S.th[b] : 0.0;
@@ -496,8 +512,10 @@ int prt_shoot_fan(const prt_env_t* env, int64_t n_rays, const double* angles_dev
     P.stored_convention = stored_convention;
     P.park_wait = park_wait_setting();
     if (P.rtol < 100.0 * PRT_EPS) P.rtol = 100.0 * PRT_EPS;  // validate_tol (scipy common.py:44-60)
-    const int block = pick_block(n_rays, env->device);
-    const unsigned grid = (unsigned)((n_rays + block - 1) / block);
+    P.lanes = pick_lanes(n_rays, env->device);
+    const int block = 128;
+    const int64_t n_warps = (n_rays + P.lanes - 1) / P.lanes;
+    const unsigned grid = (unsigned)((n_warps * 32 + block - 1) / block);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (save) prt_fan_kernel<true><<<grid, block, 0, s>>>(env->view, P);
     else prt_fan_kernel<false><<<grid, block, 0, s>>>(env->view, P);
@@ -659,8 +677,10 @@ int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev
         int32_t* n_in = S.counters + flip;
         int32_t* n_out = S.counters + (1 - flip);
         PRT_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int32_t), s));
-        const int block = pick_block(n_active, env->device);
-        const unsigned grid = (unsigned)((n_active + block - 1) / block);
+        P.lanes = pick_lanes(n_active, env->device);
+        const int block = 128;
+        const int64_t n_warps = ((int64_t)n_active + P.lanes - 1) / P.lanes;
+        const unsigned grid = (unsigned)((n_warps * 32 + block - 1) / block);
         prt_refine_round_kernel<<<grid, block, 0, s>>>(env->view, P, S, list_in, list_out, n_in, n_out);
         g_launches.fetch_add(1);
         PRT_CUDA(cudaGetLastError());
