@@ -237,10 +237,12 @@ PRT_HD_NOINLINE double prt_asin(double x)
 // (integration_processes.py:152-157, 221-224), returning the cell edges {a[k], a[k+1]} with it.
 // Guess from the mean spacing, hunt a few cells, bisect as a fallback: result is exact for any
 // sorted grid; the guess only affects speed.
-// cold path of prt_locate: lower_bound over the n nodes (node i = pair[i].x, node n-1 = pair[n-2].y)
-PRT_HD_NOINLINE int prt_locate_bisect(const prt_d2* pair, int n, double v)
+// cold path of prt_locate (NaN, grids far from uniform): lower_bound over the n nodes
+// (node i = pair[i].x, node n-1 = pair[n-2].y)
+PRT_HD_NOINLINE int prt_locate_slow(const prt_d2* pair, int n, double v)
 {
     const int m = n - 2;
+    if (v != v) return m;  // NaN sorts last in np.searchsorted
     int lo = 0, hi = n;
     while (lo < hi) {
         int mid = lo + ((hi - lo) >> 1);
@@ -254,30 +256,30 @@ PRT_HD_NOINLINE int prt_locate_bisect(const prt_d2* pair, int n, double v)
     return g;
 }
 
+#if defined(__CUDA_ARCH__)
+#define PRT_D2I(x) __double2int_rz(x)  // saturating; NaN -> 0
+#else
+#define PRT_D2I(x) (((x) != (x)) ? 0 : ((x) >= 2147483647.0 ? 2147483647 : ((x) <= -2147483648.0 ? (-2147483647 - 1) : (int)(x))))
+#endif
+
+// Fast path: guess the cell from the mean spacing, load its edges, verify; one neighbour step for
+// gently non-uniform grids (flat-earth depths); anything else goes to the cold path.  The result is
+// exactly clamp(searchsorted_left - 1) whatever the guess; cell g is right iff
+//   (g == 0 || a[g] < v) && (g == n-2 || v <= a[g+1])      (false for NaN unless the grid has one cell)
 PRT_HD int prt_locate(const prt_d2* pair, int n, double x0, double inv, double v, prt_d2& edges)
 {
     const int m = n - 2;
-    int g;
-    if (v != v) {
-        g = m;  // NaN sorts last in np.searchsorted
-        edges = prt_ld2(pair + g);
-        return g;
-    }
-    double gf = (v - x0) * inv;
-    g = (gf > 0.0) ? ((gf < (double)m) ? (int)gf : m) : 0;
+    int g = PRT_D2I((v - x0) * inv);
+    g = g < 0 ? 0 : g;
+    g = g > m ? m : g;
     edges = prt_ld2(pair + g);
-#if defined(PRT_UNROLL_HUNT)
-#pragma unroll
-#else
-#pragma unroll 1  // measured: same speed as unrolled, a third less code (profiles/r01_variants.md)
-#endif
-    for (int it = 0; it < 4; ++it) {
-        const int step = (g > 0 && !(edges.x < v)) ? -1 : ((g < m && edges.y < v) ? 1 : 0);
-        if (step == 0) return g;
-        g += step;
-        edges = prt_ld2(pair + g);
-    }
-    g = prt_locate_bisect(pair, n, v);
+    if ((g == 0 || edges.x < v) && (g == m || v <= edges.y)) return g;
+    g += (edges.x < v) ? 1 : -1;  // failed on the upper edge -> one cell up, else one cell down
+    g = g < 0 ? 0 : g;
+    g = g > m ? m : g;
+    edges = prt_ld2(pair + g);
+    if ((g == 0 || edges.x < v) && (g == m || v <= edges.y)) return g;
+    g = prt_locate_slow(pair, n, v);
     edges = prt_ld2(pair + g);
     return g;
 }
