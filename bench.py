@@ -45,6 +45,16 @@ def workload(name, rank=0, world=1):
         a = cases.config3_arrays()
         n, lim, R, ns, flat = 1 << 20, 15.0, 1000e3, 0, False
         label = "cfg3: Munk + internal waves 2001x1201 grid, 1,048,576 rays +-15deg, 1000 km, arrival table only"
+    elif name == "cfg5":
+        n_env = 128  # per GPU (1024 realisations over 8 GPUs)
+        a = cases.config2_arrays()
+        a["c_stack"] = np.stack([cases.config5_realisation(rank * n_env + i)["c"] for i in range(n_env)])
+        n, lim, R, ns, flat = 4096, 15.0, 500e3, 0, False
+        label = ("cfg5: tomography ensemble, 128 perturbed realisations (per GPU) of the 200x500 grid x 4096 rays "
+                 "+-15deg, 500 km, arrival tables only")
+        return dict(arrays=a, flatearth=flat, source_depth=1000.0, source_range=0.0, receiver_range=R,
+                    angles=np.linspace(-lim, lim, n), n_total=n * n_env * world, n_save=ns, label=label, name=name,
+                    rays_per_gpu=n * n_env, n_env=n_env)
     else:
         a = cases.config2_arrays()
         n, lim, R, ns, flat = 10000, 15.0, 500e3, 1001, False
@@ -179,9 +189,15 @@ def run_b200(args):
     w = workload(args.workload, rank, world)
     env = make_env(pr, w["arrays"], w["flatearth"])
     arrs = pr._unpack_envi(env, flatearth=w["flatearth"])
-    denv = pr.DeviceEnvironment(*arrs, device=local_rank)
+    n_env = w.get("n_env", 0)
+    if n_env:
+        stack = w["arrays"]["c_stack"]
+        cp_stack = np.gradient(stack, arrs[3], axis=2)
+        denv = pr.DeviceEnsemble(stack, cp_stack, *arrs[2:], device=local_rank)
+    else:
+        denv = pr.DeviceEnvironment(*arrs, device=local_rank)
     angles = w["angles"]
-    n = len(angles)
+    n = len(angles) * max(n_env, 1)
     R_km = abs(w["receiver_range"] - w["source_range"]) / 1e3
     n_save = w["n_save"]
 
@@ -203,14 +219,24 @@ def run_b200(args):
     def p(t):
         return None if t is None else C.c_void_p(t.data_ptr())
 
+    def launch(flips):
+        if n_env:
+            return L.prt_shoot_ensemble(denv.handle, n_env, len(angles), p(ang_d), w["source_depth"], w["source_range"],
+                                        w["receiver_range"], 1e-9, 1e-6, 1, n_save, p(rs_d), p(traj_d), p(final_d),
+                                        p(nb_d), p(ns_d), p(st_d), p(cnt_d), 1, flips, 1 << 20,
+                                        C.c_void_p(stream.cuda_stream))
+        return L.prt_shoot_fan(denv.handle, n, p(ang_d), None, w["source_depth"], w["source_range"],
+                               w["receiver_range"], 1e-9, 1e-6, 1, n_save, p(rs_d), p(traj_d), p(final_d), p(nb_d),
+                               p(ns_d), p(st_d), p(cnt_d), 1, flips, 1 << 20, C.c_void_p(stream.cuda_stream))
+
     def device_step():
-        rc = L.prt_shoot_fan(denv.handle, n, p(ang_d), None, w["source_depth"], w["source_range"],
-                             w["receiver_range"], 1e-9, 1e-6, 1, n_save, p(rs_d), p(traj_d), p(final_d), p(nb_d),
-                             p(ns_d), p(st_d), p(cnt_d), 1, p(flips_d), 1 << 20, C.c_void_p(stream.cuda_stream))
-        _lib.check(rc, "prt_shoot_fan")
+        _lib.check(launch(p(flips_d)), "prt_shoot_fan")
         if world > 1:  # the path's only exchange: all-gather the arrival records (6 doubles per ray)
             rec = pdist.records_from_result(dict(final=final_d, n_bottom=nb_d, n_surface=ns_d, status=st_d))
-            pdist.all_gather_arrivals(rec, w["n_total"], rank, world)
+            if n_env:  # ensembles shard by realisation: plain concatenation
+                dist.all_gather_into_tensor(torch.empty((world * n, 6), dtype=torch.float64, device=dev), rec)
+            else:
+                pdist.all_gather_arrivals(rec, w["n_total"], rank, world)
 
     def barrier():
         if world > 1:
@@ -257,9 +283,7 @@ def run_b200(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record(stream)
-        rc = L.prt_shoot_fan(denv.handle, n, p(ang_d), None, w["source_depth"], w["source_range"],
-                             w["receiver_range"], 1e-9, 1e-6, 1, n_save, p(rs_d), p(traj_d), p(final_d), p(nb_d),
-                             p(ns_d), p(st_d), p(cnt_d), 1, None, 1 << 20, C.c_void_p(stream.cuda_stream))
+        rc = launch(None)
         e1.record(stream)
         torch.cuda.synchronize()
         _lib.check(rc, "prt_shoot_fan")
@@ -281,6 +305,9 @@ def run_b200(args):
             fan = pr.shoot_rays(w["source_depth"], w["source_range"], -angles, w["receiver_range"], n_save, env,
                                 rtol=1e-9, debug=False, flatearth=w["flatearth"])
             n_ok = len(fan)
+        elif n_env:
+            res = pr.shoot_ensemble_arrays(denv, w["source_depth"], w["source_range"], w["receiver_range"], angles)
+            n_ok = int((res["status"] == 0).sum())
         else:
             res = pr.shoot_fan_arrays(denv, w["source_depth"], w["source_range"], w["receiver_range"], angles=angles)
             n_ok = int((res["status"] == 0).sum())
@@ -349,7 +376,7 @@ def run_b200(args):
 
     if rank == 0:
         # CPU oracle on the same workload (bounded: the whole 10k fan takes seconds in C)
-        sub = angles if n <= 20000 else angles[:: n // 4096]
+        sub = angles if len(angles) <= 20000 else angles[:: len(angles) // 4096]
         cpu_v, cpu_dt, cores = time_oracle(w, sub)
         line = {
             "metric": "ray_km_per_s", "value": value, "unit": "ray-km/s", "n_gpus": world, "steps": args.steps,
@@ -368,7 +395,9 @@ def run_b200(args):
             "cpu_baseline": {"value": cpu_v, "unit": "ray-km/s", "cores": cores, "kind": "port",
                              "sample": f"{len(sub)} rays of the same fan, {cpu_dt:.1f} s, oracle/prt_oracle.c"},
             "e2e": {"value": e2e_value, "unit": "ray-km/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "api": "pygenray_b200.shoot_rays"},
+                    "d2h_bytes_per_step": int(d2h),
+                    "api": "pygenray_b200.shoot_rays" if n_save else
+                           ("pygenray_b200.shoot_ensemble_arrays" if n_env else "pygenray_b200.shoot_fan_arrays")},
             "gpu_launches": int(launches), "clocks": clocks,
             "work": {"rays_ok": int(ok_t.item()), "nfev": int(cnt[0].sum()), "attempts": int(cnt[1].sum()),
                      "accepted": int(cnt[2].sum()), "segments": int(cnt[3].sum()), "bisect": int(cnt[4].sum()),
@@ -387,7 +416,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg5"])
     ap.add_argument("--no-eigen", action="store_true", help="skip the eigenrays/s leg")
     ap.add_argument("--ref-rays", type=int, default=0, help="reference arm: sub-sample the fan to about this many rays")
     args = ap.parse_args()

@@ -100,6 +100,15 @@ PRT_API int prt_env_create(int device, int32_t n_r, int32_t n_z, const double *r
                    const double *cin, const double *cpin, int32_t n_b, const double *depth_ranges,
                    const double *depths, int32_t n_ba, const double *ba_x, const double *ba_c,
                    prt_env_t **out);
+/*
+ * Tomography ensembles (BASELINE config 5): n_env realisations of the sound-speed field on ONE grid
+ * geometry and bathymetry.  cin, cpin are [n_env][n_r][n_z]; everything else as prt_env_create.
+ * The handle is used with prt_shoot_ensemble and destroyed with prt_env_destroy.
+ */
+PRT_API int prt_ensemble_create(int device, int32_t n_env, int32_t n_r, int32_t n_z, const double *rin,
+                                const double *zin, const double *cin, const double *cpin, int32_t n_b,
+                                const double *depth_ranges, const double *depths, int32_t n_ba,
+                                const double *ba_x, const double *ba_c, prt_env_t **out);
 PRT_API int prt_env_destroy(prt_env_t *env);
 /* bytes of device memory held by the environment */
 PRT_API int64_t prt_env_device_bytes(const prt_env_t *env);
@@ -130,6 +139,20 @@ PRT_API int prt_shoot_fan(const prt_env_t *env, int64_t n_rays, const double *an
                   int32_t *out_n_surface_dev, int32_t *out_status_dev, uint32_t *out_counters_dev,
                   int32_t stored_convention, int32_t *out_p_sign_changes_dev, int32_t max_bounces,
                   void *stream);
+
+/*
+ * One launch over the first n_env realisations of an ensemble handle: the same rays_per_env launch
+ * angles (angles_dev[rays_per_env]) are shot through every realisation.  Outputs are laid out as for a
+ * fan of n_env * rays_per_env rays, realisation-major (ray = env * rays_per_env + k).  The reference
+ * would loop shoot_rays over environments (one process pool each).
+ */
+PRT_API int prt_shoot_ensemble(const prt_env_t *env, int32_t n_env, int64_t rays_per_env, const double *angles_dev,
+                               double source_depth, double source_range, double receiver_range, double rtol,
+                               double atol, int32_t terminate_backwards, int32_t n_save,
+                               const double *range_save_dev, double *out_traj_dev, double *out_final_dev,
+                               int32_t *out_n_bottom_dev, int32_t *out_n_surface_dev, int32_t *out_status_dev,
+                               uint32_t *out_counters_dev, int32_t stored_convention,
+                               int32_t *out_p_sign_changes_dev, int32_t max_bounces, void *stream);
 
 /*
  * Same, HOST pointers in and out: stages the launch angles, runs the fan and copies the results

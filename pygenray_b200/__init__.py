@@ -11,13 +11,14 @@ There is no CPU fallback: without the built library and a CUDA device the comput
 from . import _lib
 from .eigenrays import find_brackets, find_eigenrays, refine_brackets
 from .environment import DataArray, OceanEnvironment2D, eflat, munk_ssp
-from .launch_rays import (DeviceEnvironment, _mirror_envi_arrays, _unpack_envi, bottom_angle_ppoly,
-                          shoot_fan_arrays, shoot_ray, shoot_rays)
+from .launch_rays import (DeviceEnsemble, DeviceEnvironment, _mirror_envi_arrays, _unpack_envi,
+                          bottom_angle_ppoly, shoot_ensemble_arrays, shoot_fan_arrays, shoot_ray, shoot_rays)
 from .ray_objects import EigenRays, Ray, RayFan
 
 __all__ = [
     "OceanEnvironment2D", "DataArray", "munk_ssp", "eflat", "shoot_rays", "shoot_ray", "find_eigenrays",
-    "Ray", "RayFan", "EigenRays", "shoot_fan_arrays", "find_brackets", "refine_brackets", "DeviceEnvironment",
+    "Ray", "RayFan", "EigenRays", "shoot_fan_arrays", "shoot_ensemble_arrays", "find_brackets", "refine_brackets", "DeviceEnvironment",
+    "DeviceEnsemble",
     "bottom_angle_ppoly", "_unpack_envi", "_mirror_envi_arrays",
 ]
 __version__ = "0.1.0"

@@ -21,7 +21,8 @@ N_COUNTERS = 6
 DEFAULT_MAX_BOUNCES = 1 << 20
 
 EXPORTS = (
-    "prt_abi_version", "prt_last_error", "prt_device_count", "prt_env_create", "prt_env_destroy",
+    "prt_abi_version", "prt_last_error", "prt_device_count", "prt_env_create", "prt_ensemble_create",
+    "prt_shoot_ensemble", "prt_env_destroy",
     "prt_env_device_bytes", "prt_shoot_fan", "prt_shoot_fan_host", "prt_count_brackets", "prt_fill_brackets",
     "prt_refine_workspace_bytes", "prt_refine_brackets", "prt_launch_count", "prt_measure_fp64_peak",
 )
@@ -51,6 +52,8 @@ def load():
     L.prt_device_count.restype = C.c_int
     L.prt_env_create.restype = C.c_int
     L.prt_env_create.argtypes = [C.c_int, i32, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, C.POINTER(vp)]
+    L.prt_ensemble_create.restype = C.c_int
+    L.prt_ensemble_create.argtypes = [C.c_int, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, C.POINTER(vp)]
     L.prt_env_destroy.restype = C.c_int
     L.prt_env_destroy.argtypes = [vp]
     L.prt_env_device_bytes.restype = i64
@@ -58,6 +61,8 @@ def load():
     fan_tail = [d, d, d, d, d, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32]
     L.prt_shoot_fan.restype = C.c_int
     L.prt_shoot_fan.argtypes = [vp, i64, vp, vp] + fan_tail + [vp]
+    L.prt_shoot_ensemble.restype = C.c_int
+    L.prt_shoot_ensemble.argtypes = [vp, i32, i64, vp] + fan_tail + [vp]
     L.prt_shoot_fan_host.restype = C.c_int
     L.prt_shoot_fan_host.argtypes = [vp, i64, vp, vp] + fan_tail
     L.prt_count_brackets.restype = C.c_int

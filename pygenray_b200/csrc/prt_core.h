@@ -98,6 +98,8 @@ struct prt_env_view {
     const double* brecip;   // [n_b-1] 1 / (depth_ranges[i+1] - depth_ranges[i])
     const double* ba_x;     // [n_ba] bottom-angle spline breakpoints
     const double* ba_c;     // [4][n_ba-1] PPoly coefficients, highest power first
+    int64_t grid_stride;    // ensembles: nodes between consecutive realisations' grids (0 for one environment)
+    int32_t n_env;          // number of realisations sharing the coordinate tables (1 for one environment)
     double r0, r_inv, z0, z_inv, b0, b_inv;  // cell-index guesses: (v - x0) * inv (any value is correct)
     double bb_zmax, bb_zmin, bb_rmin, bb_rmax;  // zin[-1]+1e-6, zin[0]-1e-6, rin[0]-1e-6, rin[-1]+1e-6
 };
@@ -121,38 +123,52 @@ PRT_HD double prt_np_maximum(double a, double b) { return (a != a) ? a : ((b != 
 // ---------------------------------------------------------------------------------------------
 // Elementary functions of the rounding contract
 
-// x^(-1/5): stands for error_norm ** (-1/5), scipy rk.py:155,163.
+// x^(-1/5): stands for error_norm ** (-1/5), scipy rk.py:155,163.  Hot path = normal finite x; NaN,
+// infinity and subnormals take the cold prologue.
+PRT_HD_NOINLINE double prt_pow_m02_special(double x, double& post)
+{
+    post = 1.0;
+    if (x != x) return x;
+    if (x == (double)INFINITY) return x;
+    if (x < 0x1p-1022) {
+        post = 0x1p20;
+        return x * 0x1p100;
+    }
+    return x;
+}
+
 PRT_HD double prt_pow_m02(double x)
 {
-    if (x != x) return x;
-    if (x == (double)INFINITY) return 0.0;
     double post = 1.0;
-    if (x < 0x1p-1022) {
-        x = x * 0x1p100;
-        post = 0x1p20;
+    if (!(x >= 0x1p-1022 && x < (double)INFINITY)) {
+        x = prt_pow_m02_special(x, post);
+        if (x != x) return x;
+        if (x == (double)INFINITY) return 0.0;
     }
-    uint64_t b = prt_double_to_bits(x);
-    int e = (int)((b >> 52) & 0x7ff) - 1023;
-    double m = prt_bits_to_double((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
-    int q = (e >= 0) ? (e / 5) : -((4 - e) / 5);
-    int r = e - 5 * q;
+    const uint64_t b = prt_double_to_bits(x);
+    const int e = (int)((b >> 52) & 0x7ff) - 1023;
+    const double m = prt_bits_to_double((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
+    // e = 5 q + r with r in 0..4 (floor division; e + 1025 > 0 keeps the integer division unsigned)
+    const unsigned eu = (unsigned)(e + 1025);
+    const int q = (int)(eu / 5u) - 205;
+    const int r = (int)(eu - 5u * (eu / 5u));
     double y = PRT_FMA(PRT_FMA(0.05264997, m, -0.28570902), m, 1.23209767);
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
-        double y2 = y * y;
-        double y4 = y2 * y2;
-        double y5 = y4 * y;
-        double res = PRT_FMA(-m, y5, 1.0);
+        const double y2 = y * y;
+        const double y4 = y2 * y2;
+        const double y5 = y4 * y;
+        const double res = PRT_FMA(-m, y5, 1.0);
         y = PRT_FMA(y * 0.2, res, y);
     }
     // 2^(-r/5)
-    double tr = (r == 0) ? 1.0
-              : (r == 1) ? 0x1.bdb8cdadbe120p-1
-              : (r == 2) ? 0x1.8406003b2ae5cp-1
-              : (r == 3) ? 0x1.51cb453b9536cp-1
-                         : 0x1.2611186bae674p-1;
+    const double tr = (r == 0) ? 1.0
+                    : (r == 1) ? 0x1.bdb8cdadbe120p-1
+                    : (r == 2) ? 0x1.8406003b2ae5cp-1
+                    : (r == 3) ? 0x1.51cb453b9536cp-1
+                               : 0x1.2611186bae674p-1;
     y = y * tr;
-    double p2 = prt_bits_to_double((uint64_t)(1023 - q) << 52);
+    const double p2 = prt_bits_to_double((uint64_t)(1023 - q) << 52);
     return (y * p2) * post;
 }
 
@@ -392,36 +408,115 @@ PRT_HD bool prt_event_one(const prt_env_view& E, int which, double x, double z, 
 
 // ---------------------------------------------------------------------------------------------
 // Dormand-Prince tableau (scipy rk.py:538-565), zeros omitted
-#define A21 (1.0 / 5)
-#define A31 (3.0 / 40)
-#define A32 (9.0 / 40)
-#define A41 (44.0 / 45)
-#define A42 (-56.0 / 15)
-#define A43 (32.0 / 9)
-#define A51 (19372.0 / 6561)
-#define A52 (-25360.0 / 2187)
-#define A53 (64448.0 / 6561)
-#define A54 (-212.0 / 729)
-#define A61 (9017.0 / 3168)
-#define A62 (-355.0 / 33)
-#define A63 (46732.0 / 5247)
-#define A64 (49.0 / 176)
-#define A65 (-5103.0 / 18656)
-#define B1 (35.0 / 384)
-#define B3 (500.0 / 1113)
-#define B4 (125.0 / 192)
-#define B5 (-2187.0 / 6784)
-#define B6 (11.0 / 84)
-#define E1 (-71.0 / 57600)
-#define E3 (71.0 / 16695)
-#define E4 (-71.0 / 1920)
-#define E5 (17253.0 / 339200)
-#define E6 (-22.0 / 525)
-#define E7 (1.0 / 40)
-#define C2 (1.0 / 5)
-#define C3 (3.0 / 10)
-#define C4 (4.0 / 5)
-#define C5 (8.0 / 9)
+// Dormand-Prince tableau (scipy rk.py:538-565, zeros omitted) and dense-output matrix P (rk.py:554-565).
+// On the device the coefficients live in __constant__ memory so that DFMA reads them as constant-bank
+// operands (a 64-bit immediate costs two UMOVs per use: 7 % of all executed instructions before).
+#define PRT_TABLEAU_INIT { \
+    /*  0 A21 */ 1.0 / 5, \
+    /*  1 A31 */ 3.0 / 40, \
+    /*  2 A32 */ 9.0 / 40, \
+    /*  3 A41 */ 44.0 / 45, \
+    /*  4 A42 */ -56.0 / 15, \
+    /*  5 A43 */ 32.0 / 9, \
+    /*  6 A51 */ 19372.0 / 6561, \
+    /*  7 A52 */ -25360.0 / 2187, \
+    /*  8 A53 */ 64448.0 / 6561, \
+    /*  9 A54 */ -212.0 / 729, \
+    /* 10 A61 */ 9017.0 / 3168, \
+    /* 11 A62 */ -355.0 / 33, \
+    /* 12 A63 */ 46732.0 / 5247, \
+    /* 13 A64 */ 49.0 / 176, \
+    /* 14 A65 */ -5103.0 / 18656, \
+    /* 15 B1  */ 35.0 / 384, \
+    /* 16 B3  */ 500.0 / 1113, \
+    /* 17 B4  */ 125.0 / 192, \
+    /* 18 B5  */ -2187.0 / 6784, \
+    /* 19 B6  */ 11.0 / 84, \
+    /* 20 E1  */ -71.0 / 57600, \
+    /* 21 E3  */ 71.0 / 16695, \
+    /* 22 E4  */ -71.0 / 1920, \
+    /* 23 E5  */ 17253.0 / 339200, \
+    /* 24 E6  */ -22.0 / 525, \
+    /* 25 E7  */ 1.0 / 40, \
+    /* 26 C2  */ 1.0 / 5, \
+    /* 27 C3  */ 3.0 / 10, \
+    /* 28 C4  */ 4.0 / 5, \
+    /* 29 C5  */ 8.0 / 9, \
+    /* 30 P11 */ -8048581381.0 / 2820520608.0, \
+    /* 31 P31 */ 131558114200.0 / 32700410799.0, \
+    /* 32 P41 */ -1754552775.0 / 470086768.0, \
+    /* 33 P51 */ 127303824393.0 / 49829197408.0, \
+    /* 34 P61 */ -282668133.0 / 205662961.0, \
+    /* 35 P71 */ 40617522.0 / 29380423.0, \
+    /* 36 P12 */ 8663915743.0 / 2820520608.0, \
+    /* 37 P32 */ -68118460800.0 / 10900136933.0, \
+    /* 38 P42 */ 14199869525.0 / 1410260304.0, \
+    /* 39 P52 */ -318862633887.0 / 49829197408.0, \
+    /* 40 P62 */ 2019193451.0 / 616988883.0, \
+    /* 41 P72 */ -110615467.0 / 29380423.0, \
+    /* 42 P13 */ -12715105075.0 / 11282082432.0, \
+    /* 43 P33 */ 87487479700.0 / 32700410799.0, \
+    /* 44 P43 */ -10690763975.0 / 1880347072.0, \
+    /* 45 P53 */ 701980252875.0 / 199316789632.0, \
+    /* 46 P63 */ -1453857185.0 / 822651844.0, \
+    /* 47 P73 */ 69997945.0 / 29380423.0 }
+#if defined(__CUDACC__)
+__constant__ double prt_tab_dev[48] = PRT_TABLEAU_INIT;
+#endif
+static const double prt_tab_host[48] = PRT_TABLEAU_INIT;
+#if defined(__CUDA_ARCH__)
+#define PRT_TAB(i) prt_tab_dev[i]
+#else
+#define PRT_TAB(i) prt_tab_host[i]
+#endif
+#define A21 PRT_TAB(0)
+#define A31 PRT_TAB(1)
+#define A32 PRT_TAB(2)
+#define A41 PRT_TAB(3)
+#define A42 PRT_TAB(4)
+#define A43 PRT_TAB(5)
+#define A51 PRT_TAB(6)
+#define A52 PRT_TAB(7)
+#define A53 PRT_TAB(8)
+#define A54 PRT_TAB(9)
+#define A61 PRT_TAB(10)
+#define A62 PRT_TAB(11)
+#define A63 PRT_TAB(12)
+#define A64 PRT_TAB(13)
+#define A65 PRT_TAB(14)
+#define B1 PRT_TAB(15)
+#define B3 PRT_TAB(16)
+#define B4 PRT_TAB(17)
+#define B5 PRT_TAB(18)
+#define B6 PRT_TAB(19)
+#define E1 PRT_TAB(20)
+#define E3 PRT_TAB(21)
+#define E4 PRT_TAB(22)
+#define E5 PRT_TAB(23)
+#define E6 PRT_TAB(24)
+#define E7 PRT_TAB(25)
+#define C2 PRT_TAB(26)
+#define C3 PRT_TAB(27)
+#define C4 PRT_TAB(28)
+#define C5 PRT_TAB(29)
+#define P11 PRT_TAB(30)
+#define P31 PRT_TAB(31)
+#define P41 PRT_TAB(32)
+#define P51 PRT_TAB(33)
+#define P61 PRT_TAB(34)
+#define P71 PRT_TAB(35)
+#define P12 PRT_TAB(36)
+#define P32 PRT_TAB(37)
+#define P42 PRT_TAB(38)
+#define P52 PRT_TAB(39)
+#define P62 PRT_TAB(40)
+#define P72 PRT_TAB(41)
+#define P13 PRT_TAB(42)
+#define P33 PRT_TAB(43)
+#define P43 PRT_TAB(44)
+#define P53 PRT_TAB(45)
+#define P63 PRT_TAB(46)
+#define P73 PRT_TAB(47)
 
 #define PRT_SQRT3 1.7320508075688772
 #define PRT_EPS 2.220446049250313e-16
@@ -441,26 +536,26 @@ struct prt_q3 {
 PRT_HD prt_q3 prt_dense_q(double k1, double k3, double k4, double k5, double k6, double k7)
 {
     prt_q3 q;
-    double a = (-8048581381.0 / 2820520608.0) * k1;
-    a = PRT_FMA(131558114200.0 / 32700410799.0, k3, a);
-    a = PRT_FMA(-1754552775.0 / 470086768.0, k4, a);
-    a = PRT_FMA(127303824393.0 / 49829197408.0, k5, a);
-    a = PRT_FMA(-282668133.0 / 205662961.0, k6, a);
-    a = PRT_FMA(40617522.0 / 29380423.0, k7, a);
+    double a = P11 * k1;
+    a = PRT_FMA(P31, k3, a);
+    a = PRT_FMA(P41, k4, a);
+    a = PRT_FMA(P51, k5, a);
+    a = PRT_FMA(P61, k6, a);
+    a = PRT_FMA(P71, k7, a);
     q.q1 = a;
-    a = (8663915743.0 / 2820520608.0) * k1;
-    a = PRT_FMA(-68118460800.0 / 10900136933.0, k3, a);
-    a = PRT_FMA(14199869525.0 / 1410260304.0, k4, a);
-    a = PRT_FMA(-318862633887.0 / 49829197408.0, k5, a);
-    a = PRT_FMA(2019193451.0 / 616988883.0, k6, a);
-    a = PRT_FMA(-110615467.0 / 29380423.0, k7, a);
+    a = P12 * k1;
+    a = PRT_FMA(P32, k3, a);
+    a = PRT_FMA(P42, k4, a);
+    a = PRT_FMA(P52, k5, a);
+    a = PRT_FMA(P62, k6, a);
+    a = PRT_FMA(P72, k7, a);
     q.q2 = a;
-    a = (-12715105075.0 / 11282082432.0) * k1;
-    a = PRT_FMA(87487479700.0 / 32700410799.0, k3, a);
-    a = PRT_FMA(-10690763975.0 / 1880347072.0, k4, a);
-    a = PRT_FMA(701980252875.0 / 199316789632.0, k5, a);
-    a = PRT_FMA(-1453857185.0 / 822651844.0, k6, a);
-    a = PRT_FMA(69997945.0 / 29380423.0, k7, a);
+    a = P13 * k1;
+    a = PRT_FMA(P33, k3, a);
+    a = PRT_FMA(P43, k4, a);
+    a = PRT_FMA(P53, k5, a);
+    a = PRT_FMA(P63, k6, a);
+    a = PRT_FMA(P73, k7, a);
     q.q3 = a;
     return q;
 }

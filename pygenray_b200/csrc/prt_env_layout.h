@@ -44,13 +44,15 @@ static inline double prt_inv_mean_step(const double* a, int n)
 }
 
 // returns 0 on success, nonzero on invalid sizes
+// n_env >= 1 realisations of the sound-speed field (cin/cpin: [n_env][n_r][n_z]) share one set of
+// coordinate, bathymetry and spline tables (tomography ensembles, BASELINE config 5)
 static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double* zin, const double* cin,
                                const double* cpin, int n_b, const double* depth_ranges, const double* depths,
-                               int n_ba, const double* ba_x, const double* ba_c, prt_env_blob& out)
+                               int n_ba, const double* ba_x, const double* ba_c, prt_env_blob& out, int n_env = 1)
 {
-    if (n_r < 2 || n_z < 2 || n_b < 2 || n_ba < 2) return 1;
+    if (n_r < 2 || n_z < 2 || n_b < 2 || n_ba < 2 || n_env < 1) return 1;
     size_t o_grid = 0;
-    size_t o_rpair = o_grid + prt_align256(sizeof(prt_d2) * (size_t)n_r * n_z);
+    size_t o_rpair = o_grid + prt_align256(sizeof(prt_d2) * (size_t)n_r * n_z * (size_t)n_env);
     size_t o_zpair = o_rpair + prt_align256(sizeof(prt_d2) * (size_t)(n_r - 1));
     size_t o_bx = o_zpair + prt_align256(sizeof(prt_d2) * (size_t)(n_z - 1));
     size_t o_bv = o_bx + prt_align256(sizeof(prt_d2) * (size_t)(n_b - 1));
@@ -63,7 +65,7 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
     out.bytes.assign(total, 0);
     unsigned char* base = out.bytes.data();
     prt_d2* grid = reinterpret_cast<prt_d2*>(base + o_grid);
-    const size_t n_nodes = (size_t)n_r * n_z;
+    const size_t n_nodes = (size_t)n_r * n_z * (size_t)n_env;
     for (size_t k = 0; k < n_nodes; ++k) {
         grid[k].x = cin[k];
         grid[k].y = cpin[k];
@@ -80,6 +82,8 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
 
     prt_env_view& v = out.view;
     v.n_r = n_r; v.n_z = n_z; v.n_b = n_b; v.n_ba = n_ba;
+    v.n_env = n_env;
+    v.grid_stride = (n_env > 1) ? (int64_t)n_r * n_z : 0;
     v.grid = reinterpret_cast<const prt_d2*>(o_grid);
     v.rpair = reinterpret_cast<const prt_d2*>(o_rpair);
     v.zpair = reinterpret_cast<const prt_d2*>(o_zpair);

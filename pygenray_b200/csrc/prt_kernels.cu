@@ -64,6 +64,7 @@ struct prt_fan_params {
     int32_t stored_convention;
     int32_t park_wait;
     int32_t lanes;  // rays per warp (32, 16, 8, 4, 2 or 1): small fans use partly filled warps, see pick_lanes()
+    int64_t rays_per_env;  // ensembles: ray r belongs to realisation r / rays_per_env and uses angles[r % rays_per_env]
 };
 
 // Lanes that hit a boundary wait (at most this many step attempts of the other lanes) so that the
@@ -126,7 +127,7 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_env_view& E, prt_ra
 #define PRT_MIN_BLOCKS 4
 #endif
 template <bool SAVE>
-__global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_fan_kernel(const __grid_constant__ prt_env_view E,
+__global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_fan_kernel(const __grid_constant__ prt_env_view E0,
                                                       const __grid_constant__ prt_fan_params P)
 {
     // P.lanes rays per warp (lanes >= P.lanes idle); whole warps stay in the kernel: the driver is warp-synchronous
@@ -134,6 +135,14 @@ __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_fan_kernel(const __gr
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t ray = warp * P.lanes + lane;
     const bool live = (lane < P.lanes) && (ray < P.n_rays);
+    // ensembles: same tables, this ray's realisation of the sound-speed grid
+    prt_env_view E = E0;
+    int64_t angle_index = ray;
+    if (P.rays_per_env > 0 && live) {
+        const int64_t env = ray / P.rays_per_env;
+        angle_index = ray - env * P.rays_per_env;
+        E.grid = E0.grid + env * E0.grid_stride;
+    }
     prt_shot S;
     S.x_end = P.receiver_range; S.rtol = P.rtol; S.atol = P.atol;
     S.terminate_backwards = P.terminate_backwards; S.n_save = P.n_save; S.max_bounces = P.max_bounces;
@@ -145,7 +154,7 @@ __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_fan_kernel(const __gr
             z = P.y0[3 * ray + 1];
             p = P.y0[3 * ray + 2];
         } else {
-            prt_initial_state(E, P.source_depth, P.source_range, P.angles[ray], T, z, p);
+            prt_initial_state(E, P.source_depth, P.source_range, P.angles[angle_index], T, z, p);
         }
     }
     prt_traj_sink sink;
@@ -472,6 +481,34 @@ int prt_env_create(int device, int32_t n_r, int32_t n_z, const double* rin, cons
     return PRT_SUCCESS;
 }
 
+int prt_ensemble_create(int device, int32_t n_env, int32_t n_r, int32_t n_z, const double* rin, const double* zin,
+                        const double* cin, const double* cpin, int32_t n_b, const double* depth_ranges,
+                        const double* depths, int32_t n_ba, const double* ba_x, const double* ba_c, prt_env_t** out)
+{
+    if (!out || !rin || !zin || !cin || !cpin || !depth_ranges || !depths || !ba_x || !ba_c)
+        return fail(PRT_ERR_ARG, "prt_ensemble_create: null pointer");
+    if (prt_device_count() <= device || device < 0)
+        return fail(PRT_ERR_NO_DEVICE, "prt_ensemble_create: no such CUDA device (this library has no CPU path)");
+    prt_env_blob blob;
+    if (prt_env_pack(n_r, n_z, rin, zin, cin, cpin, n_b, depth_ranges, depths, n_ba, ba_x, ba_c, blob, n_env))
+        return fail(PRT_ERR_ARG, "prt_ensemble_create: n_env >= 1 and every grid needs at least 2 points");
+    PRT_CUDA(cudaSetDevice(device));
+    void* dev = nullptr;
+    PRT_CUDA(cudaMalloc(&dev, blob.bytes.size()));
+    cudaError_t e = cudaMemcpy(dev, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(dev);
+        return fail(PRT_ERR_CUDA, std::string("cudaMemcpy(ensemble): ") + cudaGetErrorString(e));
+    }
+    prt_env* env = new prt_env;
+    env->device = device;
+    env->dev_blob = dev;
+    env->bytes = blob.bytes.size();
+    env->view = prt_env_rebase(blob.view, dev);
+    *out = env;
+    return PRT_SUCCESS;
+}
+
 int prt_env_destroy(prt_env_t* env)
 {
     if (!env) return PRT_SUCCESS;
@@ -483,17 +520,22 @@ int prt_env_destroy(prt_env_t* env)
 
 int64_t prt_env_device_bytes(const prt_env_t* env) { return env ? (int64_t)env->bytes : 0; }
 
-int prt_shoot_fan(const prt_env_t* env, int64_t n_rays, const double* angles_dev, const double* y0_dev,
-                  double source_depth, double source_range, double receiver_range, double rtol, double atol,
-                  int32_t terminate_backwards, int32_t n_save, const double* range_save_dev, double* out_traj_dev,
-                  double* out_final_dev, int32_t* out_n_bottom_dev, int32_t* out_n_surface_dev,
-                  int32_t* out_status_dev, uint32_t* out_counters_dev, int32_t stored_convention,
-                  int32_t* out_p_sign_changes_dev, int32_t max_bounces, void* stream)
+}  // extern "C"
+
+static int shoot_fan_impl(const prt_env_t* env, int64_t n_rays, int64_t rays_per_env, const double* angles_dev,
+                          const double* y0_dev, double source_depth, double source_range, double receiver_range,
+                          double rtol, double atol, int32_t terminate_backwards, int32_t n_save,
+                          const double* range_save_dev, double* out_traj_dev, double* out_final_dev,
+                          int32_t* out_n_bottom_dev, int32_t* out_n_surface_dev, int32_t* out_status_dev,
+                          uint32_t* out_counters_dev, int32_t stored_convention, int32_t* out_p_sign_changes_dev,
+                          int32_t max_bounces, void* stream)
 {
     if (!env) return fail(PRT_ERR_ARG, "prt_shoot_fan: null environment");
     if (n_rays < 0) return fail(PRT_ERR_ARG, "prt_shoot_fan: n_rays < 0");
     if (n_rays == 0) return PRT_SUCCESS;
     if (!angles_dev && !y0_dev) return fail(PRT_ERR_ARG, "prt_shoot_fan: need angles_dev or y0_dev");
+    if (rays_per_env == 0 && env->view.n_env > 1)
+        return fail(PRT_ERR_ARG, "prt_shoot_fan: this handle is an ensemble, use prt_shoot_ensemble");
     if (!out_final_dev || !out_n_bottom_dev || !out_n_surface_dev || !out_status_dev)
         return fail(PRT_ERR_ARG, "prt_shoot_fan: null output pointer");
     const bool save = (n_save > 0);
@@ -511,6 +553,7 @@ int prt_shoot_fan(const prt_env_t* env, int64_t n_rays, const double* angles_dev
     P.out_counters = out_counters_dev; P.max_bounces = max_bounces > 0 ? max_bounces : (1 << 20);
     P.stored_convention = stored_convention;
     P.park_wait = park_wait_setting();
+    P.rays_per_env = rays_per_env;
     if (P.rtol < 100.0 * PRT_EPS) P.rtol = 100.0 * PRT_EPS;  // validate_tol (scipy common.py:44-60)
     P.lanes = pick_lanes(n_rays, env->device);
     const int block = 128;
@@ -530,6 +573,37 @@ int prt_shoot_fan(const prt_env_t* env, int64_t n_rays, const double* angles_dev
         PRT_CUDA(cudaGetLastError());
     }
     return PRT_SUCCESS;
+}
+
+extern "C" {
+
+int prt_shoot_fan(const prt_env_t* env, int64_t n_rays, const double* angles_dev, const double* y0_dev,
+                  double source_depth, double source_range, double receiver_range, double rtol, double atol,
+                  int32_t terminate_backwards, int32_t n_save, const double* range_save_dev, double* out_traj_dev,
+                  double* out_final_dev, int32_t* out_n_bottom_dev, int32_t* out_n_surface_dev,
+                  int32_t* out_status_dev, uint32_t* out_counters_dev, int32_t stored_convention,
+                  int32_t* out_p_sign_changes_dev, int32_t max_bounces, void* stream)
+{
+    return shoot_fan_impl(env, n_rays, 0, angles_dev, y0_dev, source_depth, source_range, receiver_range, rtol, atol,
+                          terminate_backwards, n_save, range_save_dev, out_traj_dev, out_final_dev, out_n_bottom_dev,
+                          out_n_surface_dev, out_status_dev, out_counters_dev, stored_convention,
+                          out_p_sign_changes_dev, max_bounces, stream);
+}
+
+int prt_shoot_ensemble(const prt_env_t* env, int32_t n_env, int64_t rays_per_env, const double* angles_dev,
+                       double source_depth, double source_range, double receiver_range, double rtol, double atol,
+                       int32_t terminate_backwards, int32_t n_save, const double* range_save_dev,
+                       double* out_traj_dev, double* out_final_dev, int32_t* out_n_bottom_dev,
+                       int32_t* out_n_surface_dev, int32_t* out_status_dev, uint32_t* out_counters_dev,
+                       int32_t stored_convention, int32_t* out_p_sign_changes_dev, int32_t max_bounces, void* stream)
+{
+    if (!env) return fail(PRT_ERR_ARG, "prt_shoot_ensemble: null environment");
+    if (n_env < 1 || n_env > env->view.n_env) return fail(PRT_ERR_ARG, "prt_shoot_ensemble: n_env out of range");
+    if (rays_per_env < 1 || !angles_dev) return fail(PRT_ERR_ARG, "prt_shoot_ensemble: need rays_per_env >= 1 angles");
+    return shoot_fan_impl(env, (int64_t)n_env * rays_per_env, rays_per_env, angles_dev, nullptr, source_depth,
+                          source_range, receiver_range, rtol, atol, terminate_backwards, n_save, range_save_dev,
+                          out_traj_dev, out_final_dev, out_n_bottom_dev, out_n_surface_dev, out_status_dev,
+                          out_counters_dev, stored_convention, out_p_sign_changes_dev, max_bounces, stream);
 }
 
 int prt_shoot_fan_host(const prt_env_t* env, int64_t n_rays, const double* angles, const double* y0,

@@ -18,8 +18,8 @@ from scipy.interpolate import CubicSpline
 from . import _lib, _xr
 from .ray_objects import Ray, RayFan
 
-__all__ = ["shoot_rays", "shoot_ray", "shoot_fan_arrays", "DeviceEnvironment", "_unpack_envi",
-           "_mirror_envi_arrays", "bottom_angle_ppoly"]
+__all__ = ["shoot_rays", "shoot_ray", "shoot_fan_arrays", "shoot_ensemble_arrays", "DeviceEnvironment",
+           "DeviceEnsemble", "_unpack_envi", "_mirror_envi_arrays", "bottom_angle_ppoly"]
 
 ATOL = 1e-6  # scipy.integrate.solve_ivp default, never overridden by the reference (launch_rays.py:670-679)
 
@@ -136,6 +136,94 @@ class DeviceEnvironment:
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+
+class DeviceEnsemble(DeviceEnvironment):
+    """``n_env`` realisations of the sound-speed field on one grid geometry, staged together
+    (``prt_ensemble_create``): ``cin``/``cpin`` are ``[n_env][range][depth]``; coordinates, bathymetry and
+    bottom angles are shared.  Shot with :func:`shoot_ensemble_arrays` (tomography ensembles, config 5)."""
+
+    def __init__(self, cin, cpin, rin, zin, depths, depth_ranges, bottom_angles, device=None):
+        L = _lib.require_gpu()
+        import torch  # noqa: PLC0415
+
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = int(device)
+        cin, cpin, rin, zin = _as_f64(cin), _as_f64(cpin), _as_f64(rin), _as_f64(zin)
+        depths, depth_ranges = _as_f64(depths), _as_f64(depth_ranges)
+        if cin.ndim != 3 or cin.shape[1:] != (rin.shape[0], zin.shape[0]) or cpin.shape != cin.shape:
+            raise ValueError(f"ensemble sound speed must be [n_env][range][depth], got {cin.shape}")
+        ba_x, ba_c = bottom_angle_ppoly(depth_ranges, bottom_angles)
+        handle = C.c_void_p()
+        rc = L.prt_ensemble_create(
+            self.device, cin.shape[0], rin.shape[0], zin.shape[0], rin.ctypes.data, zin.ctypes.data, cin.ctypes.data,
+            cpin.ctypes.data, depths.shape[0], depth_ranges.ctypes.data, depths.ctypes.data, ba_x.shape[0],
+            ba_x.ctypes.data, ba_c.ctypes.data, C.byref(handle),
+        )
+        _lib.check(rc, "prt_ensemble_create")
+        self._h = handle
+        self.n_env, self.n_r, self.n_z = cin.shape[0], rin.shape[0], zin.shape[0]
+        self.device_bytes = int(L.prt_env_device_bytes(handle))
+
+
+def shoot_ensemble_arrays(dens, source_depth, source_range, receiver_range, angles, n_env=None, num_range_save=0,
+                          rtol=1e-9, terminate_backwards=True, counters=False, max_bounces=_lib.DEFAULT_MAX_BOUNCES,
+                          to_host=True):
+    """Shoot the same fan of INTERNAL ``angles`` through the first ``n_env`` realisations of ``dens`` in one
+    launch.  Returns the dict of :func:`shoot_fan_arrays` with a leading realisation axis:
+    ``final (3, n_env, n)``, ``status (n_env, n)``, ``traj (3, n_env, n, N)`` ..."""
+    L = _lib.require_gpu()
+    import torch  # noqa: PLC0415
+
+    if not (source_range < receiver_range):
+        raise ValueError("shoot_ensemble_arrays integrates forwards: mirror the environment for backwards shots")
+    n_env = dens.n_env if n_env is None else int(n_env)
+    dev = torch.device("cuda", dens.device)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream()
+        ang_d = torch.from_numpy(_as_f64(np.atleast_1d(angles)).reshape(-1)).to(dev)
+        k = ang_d.shape[0]
+        n = n_env * k
+        n_save = int(num_range_save) if num_range_save else 0
+        out = {}
+        rs_d = traj_d = None
+        if n_save:
+            rs_np = np.linspace(source_range, receiver_range, n_save)
+            rs_d = torch.from_numpy(rs_np).to(dev)
+            traj_d = torch.empty((3, n_env, k, n_save), dtype=torch.float64, device=dev)
+            out["range_save"] = rs_np
+        final_d = torch.empty((3, n_env, k), dtype=torch.float64, device=dev)
+        nb_d = torch.empty((n_env, k), dtype=torch.int32, device=dev)
+        ns_d = torch.empty((n_env, k), dtype=torch.int32, device=dev)
+        st_d = torch.empty((n_env, k), dtype=torch.int32, device=dev)
+        cnt_d = torch.empty((_lib.N_COUNTERS, n_env, k), dtype=torch.int32, device=dev) if counters else None
+
+        def ptr(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+
+        if n:
+            rc = L.prt_shoot_ensemble(
+                dens.handle, n_env, k, ptr(ang_d), float(source_depth), float(source_range), float(receiver_range),
+                float(rtol), ATOL, int(bool(terminate_backwards)), n_save, ptr(rs_d), ptr(traj_d), ptr(final_d),
+                ptr(nb_d), ptr(ns_d), ptr(st_d), ptr(cnt_d), 0, None, int(max_bounces),
+                C.c_void_p(stream.cuda_stream),
+            )
+            _lib.check(rc, "prt_shoot_ensemble")
+        dev_out = dict(final=final_d, n_bottom=nb_d, n_surface=ns_d, status=st_d)
+        if traj_d is not None:
+            dev_out["traj"] = traj_d
+        if cnt_d is not None:
+            dev_out["counters"] = cnt_d
+        if not to_host:
+            out.update(dev_out)
+            return out
+        host = {kk: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for kk, v in dev_out.items()}
+        for kk, v in dev_out.items():
+            host[kk].copy_(v, non_blocking=True)
+        stream.synchronize()
+        out.update({kk: v.numpy() for kk, v in host.items()})
+    return out
 
 
 def _fingerprint(*arrays):

@@ -223,3 +223,24 @@ def test_config2_full_size_properties(pr):
     o = _oracle_fan(env, False, 1000.0, 0.0, 500e3, ang[sub], 1001)
     assert np.array_equal(np.transpose(a["traj"][:, sub], (1, 0, 2)), o["traj"], equal_nan=True)
     assert np.array_equal(a["n_bottom"][sub], o["n_bottom"]) and np.array_equal(a["n_surface"][sub], o["n_surface"])
+
+
+def test_ensemble_launch_bit_identical_per_realisation(pr):
+    """BASELINE config 5 in miniature: 6 perturbed realisations x 96 rays in ONE launch == the oracle run
+    realisation by realisation."""
+    envs = [make_env(cases.config5_realisation(i)) for i in range(6)]
+    arrs = [pr._unpack_envi(e, flatearth=False) for e in envs]
+    cin = np.stack([a[0] for a in arrs]); cpin = np.stack([a[1] for a in arrs])
+    dens = pr.DeviceEnsemble(cin, cpin, *arrs[0][2:])
+    ang = np.linspace(-14, 14, 96)
+    g = pr.shoot_ensemble_arrays(dens, 1000.0, 0.0, 200e3, ang, num_range_save=41, counters=True)
+    assert g["final"].shape == (3, 6, 96) and g["traj"].shape == (3, 6, 96, 41)
+    for i, env in enumerate(envs):
+        o = _oracle_fan(env, False, 1000.0, 0.0, 200e3, ang, 41)
+        gi = dict(final=g["final"][:, i].T.copy(), n_bottom=g["n_bottom"][i], n_surface=g["n_surface"][i],
+                  status=g["status"][i], counters=g["counters"][:, i].T.astype(np.int64),
+                  traj=np.transpose(g["traj"][:, i], (1, 0, 2)))
+        assert_same_fan(o, gi, f"realisation {i}")
+    assert not np.array_equal(g["final"][:, 0], g["final"][:, 1])  # the realisations differ
+    with pytest.raises(pr._lib.PrtError):
+        pr.shoot_fan_arrays(dens, 1000.0, 0.0, 1e5, angles=ang)  # an ensemble handle needs the ensemble call
