@@ -662,17 +662,26 @@ struct prt_shot {
 // boundary wait for one another so that the event root searches also run together.
 enum { PRT_PH_INIT = 0, PRT_PH_STEP = 1, PRT_PH_ROOT = 2, PRT_PH_DONE = 3 };
 
+// The last accepted step of a ray: produced by attempt(), consumed in the same loop iteration by
+// advance() -- or, for a lane that fired an event, parked (in shared memory on the device) until the
+// warp's root searches run.  Keeping it out of the persistent ray state is what lets 4+ blocks of 128
+// threads be resident per SM: it is not live across the stage evaluations of the next attempts.
+struct prt_step {
+    double t_old, t_new, h, inv_h, yT, yz, yp, nf0, nf1, nf2;
+    prt_q3 qT, qz, qp;
+    double root;       // set by solve_roots
+    int32_t active;    // mask of events that fired on this step
+    int32_t event;     // earliest event (set by solve_roots)
+    bool finished;     // the step reached x_end
+};
+
 template <bool SAVE>
 struct prt_ray {
     // persistent ODE state (solver.t, solver.y, solver.f, solver.h_abs)
     double t, T, z, p, f0, f1, f2, h_abs;
-    // last accepted step, valid between attempt() == accepted and advance()/finish_terminal()
-    double t_old, t_new, h, inv_h, yT, yz, yp, nf0, nf1, nf2;
-    prt_q3 qT, qz, qp;
-    double root;
-    int32_t g, active, event, n_ts, cursor, n_surface, n_bottom, status, phase;
-    bool rejected, finished;
-    uint32_t c_nfev, c_att, c_acc, c_seg, c_bis, c_dense;
+    int32_t g, n_ts, cursor, n_surface, n_bottom, status, phase;
+    bool rejected;
+    uint32_t c_att, c_acc, c_seg, c_bis, c_dense;  // RHS evaluations = 2 c_seg + 6 c_att
 
     PRT_HD void start(double T0, double z0, double p0, double x0, const prt_shot& S)
     {
@@ -680,12 +689,12 @@ struct prt_ray {
         n_surface = n_bottom = 0;
         status = PRT_RAY_OK;
         cursor = 0;
-        c_nfev = c_att = c_acc = c_seg = c_bis = c_dense = 0;
-        event = -1; active = 0; finished = false; rejected = false;
+        c_att = c_acc = c_seg = c_bis = c_dense = 0;
+        rejected = false;
         phase = (x0 < S.x_end) ? PRT_PH_INIT : PRT_PH_DONE;  // launch_rays.py:404
     }
 
-    // RK45.__init__ (rk.py:85-103) + select_initial_step (common.py:68-134) + g = [event(t0, y0)]
+    // RK45.__init__ (rk.py:85-103) + select_initial_step (common.py:68-134) + g = [st.event(t0, y0)]
     PRT_HD void seg_init(const prt_env_view& E, const prt_shot& S)
     {
         ++c_seg;
@@ -701,21 +710,19 @@ struct prt_ray {
         h0 = prt_py_min(h0, interval);
         double g0, g1, g2, cc;
         prt_rhs(E, t + h0, PRT_FMA(h0, f1, z), PRT_FMA(h0, f2, p), g0, g1, g2, cc);
-        c_nfev += 2;
         double d2 = prt_rms3((g0 - f0) / s0, (g1 - f1) / s1, (g2 - f2) / s2) / h0;
         double h1;
         if (d1 <= 1e-15 && d2 <= 1e-15) h1 = prt_py_max(1e-6, h0 * 1e-3);
         else h1 = 1.0 / prt_pow_m02(0.01 / prt_py_max(d1, d2));
         h_abs = prt_py_min(prt_py_min(100.0 * h0, h1), interval);
         n_ts = 1;
-        event = -1;
         rejected = false;
         phase = PRT_PH_STEP;
     }
 
     // One attempt of _step_impl (rk.py:111-176).  Returns true when the step was accepted; then the
-    // step record (t_old .. nf2, events, dense output if needed) is filled in.
-    PRT_HD bool attempt(const prt_env_view& E, const prt_shot& S)
+    // step record (st.t_old .. st.nf2, events, dense output if needed) is filled in.
+    PRT_HD bool attempt(const prt_env_view& E, const prt_shot& S, prt_step& st)
     {
         const double min_step = 10.0 * fabs(prt_next_up(t) - t);
         if (rejected) {
@@ -813,7 +820,6 @@ struct prt_ray {
         prt_rhs(E, t + hh, nz, np_, k7T, k7z, k7p, c_new);  // f_new (FSAL)
         (void)k2T;
 #endif
-        c_nfev += 6;
         double eT = E1 * f0; eT = PRT_FMA(E3, k3T, eT); eT = PRT_FMA(E4, k4T, eT); eT = PRT_FMA(E5, k5T, eT); eT = PRT_FMA(E6, k6T, eT); eT = PRT_FMA(E7, k7T, eT);
         double ez = E1 * f1; ez = PRT_FMA(E3, k3z, ez); ez = PRT_FMA(E4, k4z, ez); ez = PRT_FMA(E5, k5z, ez); ez = PRT_FMA(E6, k6z, ez); ez = PRT_FMA(E7, k7z, ez);
         double ep = E1 * f2; ep = PRT_FMA(E3, k3p, ep); ep = PRT_FMA(E4, k4p, ep); ep = PRT_FMA(E5, k5p, ep); ep = PRT_FMA(E6, k6p, ep); ep = PRT_FMA(E7, k7p, ep);
@@ -831,12 +837,12 @@ struct prt_ray {
         h_abs *= factor;
         rejected = false;
         ++c_acc;
-        t_old = t; t_new = tn; h = hh;
-        yT = nT; yz = nz; yp = np_;
-        nf0 = k7T; nf1 = k7z; nf2 = k7p;
-        finished = (tn - S.x_end >= 0.0);  // base.py:205-206
-        // events at the step end (ivp.py:678-699); c(t_new, y_new) comes from the FSAL stage, which was
-        // evaluated at t + h: identical unless the clipped step made t + h != t_new
+        st.t_old = t; st.t_new = tn; st.h = hh;
+        st.yT = nT; st.yz = nz; st.yp = np_;
+        st.nf0 = k7T; st.nf1 = k7z; st.nf2 = k7p;
+        st.finished = (tn - S.x_end >= 0.0);  // base.py:205-206
+        // events at the step end (ivp.py:678-699); c(st.t_new, y_new) comes from the FSAL stage, which was
+        // evaluated at t + st.h: identical unless the clipped step made t + st.h != st.t_new
         if (t + hh != tn) {
             double cz_unused;
             prt_field(E, tn, nz, c_new, cz_unused);
@@ -844,66 +850,66 @@ struct prt_ray {
         const int g_new = prt_events(E, tn, nz, np_, c_new);
         // find_active_events (ivp.py:134-157): up for direction +1, up|down for direction 0
         const int up = (~g) & g_new, down = g & (~g_new);
-        active = (up & (PRT_EV_SURFACE | PRT_EV_BOTTOM)) | ((up | down) & (PRT_EV_VERTICAL | PRT_EV_BBOX));
+        st.active = (up & (PRT_EV_SURFACE | PRT_EV_BOTTOM)) | ((up | down) & (PRT_EV_VERTICAL | PRT_EV_BBOX));
         g = g_new;
-        bool need_dense = (active != 0);
+        bool need_dense = (st.active != 0);
         if (SAVE && !need_dense) need_dense = (cursor < S.n_save - 1) && (prt_ld(S.range_save + cursor) <= tn);
         if (need_dense) {
             ++c_dense;
-            qT = prt_dense_q(f0, k3T, k4T, k5T, k6T, k7T);
-            qz = prt_dense_q(f1, k3z, k4z, k5z, k6z, k7z);
-            qp = prt_dense_q(f2, k3p, k4p, k5p, k6p, k7p);
-            inv_h = 1.0 / hh;
+            st.qT = prt_dense_q(f0, k3T, k4T, k5T, k6T, k7T);
+            st.qz = prt_dense_q(f1, k3z, k4z, k5z, k6z, k7z);
+            st.qp = prt_dense_q(f2, k3p, k4p, k5p, k6p, k7p);
+            st.inv_h = 1.0 / hh;
         }
         return true;
     }
 
-    PRT_HD void emit(const prt_traj_sink& sink, int i, double rsv) const
+    PRT_HD void emit(const prt_traj_sink& sink, const prt_step& st, int i, double rsv) const
     {
-        const double xx = (rsv - t_old) * inv_h;
+        const double xx = (rsv - st.t_old) * st.inv_h;
         const double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
-        sink.put(i, prt_dense_eval(f0, qT, h, T, p1, p2, p3, p4), prt_dense_eval(f1, qz, h, z, p1, p2, p3, p4),
-                 prt_dense_eval(f2, qp, h, p, p1, p2, p3, p4));
+        sink.put(i, prt_dense_eval(f0, st.qT, st.h, T, p1, p2, p3, p4), prt_dense_eval(f1, st.qz, st.h, z, p1, p2, p3, p4),
+                 prt_dense_eval(f2, st.qp, st.h, p, p1, p2, p3, p4));
     }
 
-    // accepted step without an event: stream the save points it owns, then move on
-    PRT_HD void advance(const prt_shot& S, const prt_traj_sink& sink)
+    // accepted step without an st.event: stream the save points it owns, then move on
+    PRT_HD void advance(const prt_shot& S, const prt_traj_sink& sink, const prt_step& st)
     {
         if (SAVE) {
             const int ub = S.n_save - 1;
             while (cursor < ub) {
                 const double rsv = prt_ld(S.range_save + cursor);
-                if (!(rsv <= t_new)) break;
-                emit(sink, cursor, rsv);
+                if (!(rsv <= st.t_new)) break;
+                emit(sink, st, cursor, rsv);
                 ++cursor;
             }
         }
-        T = yT; z = yz; p = yp;
-        f0 = nf0; f1 = nf1; f2 = nf2;
-        t = t_new;
+        T = st.yT; z = st.yz; p = st.yp;
+        f0 = st.nf0; f1 = st.nf1; f2 = st.nf2;
+        t = st.t_new;
         ++n_ts;
-        if (finished) phase = PRT_PH_DONE;  // sol.status == 0, launch_rays.py:425-426
+        if (st.finished) phase = PRT_PH_DONE;  // sol.status == 0, launch_rays.py:425-426
     }
 
-    PRT_HD bool event_at(const prt_env_view& E, int e, double x) const
+    PRT_HD bool event_at(const prt_env_view& E, const prt_step& st, int e, double x) const
     {
-        const double xx = (x - t_old) * inv_h;
+        const double xx = (x - st.t_old) * st.inv_h;
         const double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
-        return prt_event_one(E, e, x, prt_dense_eval(f1, qz, h, z, p1, p2, p3, p4),
-                             prt_dense_eval(f2, qp, h, p, p1, p2, p3, p4));
+        return prt_event_one(E, e, x, prt_dense_eval(f1, st.qz, st.h, z, p1, p2, p3, p4),
+                             prt_dense_eval(f2, st.qp, st.h, p, p1, p2, p3, p4));
     }
 
-    // handle_events (ivp.py:80-131): every event is terminal -> earliest root, ties to the lower
-    // event index.  solve_event_equation = brentq(xtol = rtol = 4 eps, maxiter 100) on a +-1
+    // handle_events (ivp.py:80-131): every st.event is terminal -> earliest st.root, ties to the lower
+    // st.event index.  solve_event_equation = brentq(xtol = rtol = 4 eps, maxiter 100) on a +-1
     // function, which degenerates to bisection (|f| is always 1).
-    PRT_HD void solve_roots(const prt_env_view& E)
+    PRT_HD void solve_roots(const prt_env_view& E, prt_step& st)
     {
         double best_root = 0.0;
         int best = -1;
         for (int e = 0; e < 4; ++e) {
-            if (!(active & (1 << e))) continue;
-            double xpre = t_old, xcur = t_new, xblk = 0.0;
-            bool fpre = event_at(E, e, t_old), fcur = event_at(E, e, t_new);
+            if (!(st.active & (1 << e))) continue;
+            double xpre = st.t_old, xcur = st.t_new, xblk = 0.0;
+            bool fpre = event_at(E, st, e, st.t_old), fcur = event_at(E, st, e, st.t_new);
             c_bis += 2;
             if (fpre == fcur) {
                 status = PRT_RAY_BRENTQ_SIGN;
@@ -922,7 +928,7 @@ struct prt_ray {
                 fpre = fcur;
                 if (fabs(sbis) > delta) xcur += sbis;
                 else xcur += (sbis > 0 ? delta : -delta);
-                fcur = event_at(E, e, xcur);
+                fcur = event_at(E, st, e, xcur);
                 ++c_bis;
             }
             if (!converged) {
@@ -934,47 +940,47 @@ struct prt_ray {
                 best_root = xcur;
             }
         }
-        event = best;
-        root = best_root;
+        st.event = best;
+        st.root = best_root;
     }
 
-    // terminal step: _interpolate_ray bookkeeping for the finished segment (launch_rays.py:745-784),
-    // state at the event, then the reflection (launch_rays.py:432-480)
-    PRT_HD void finish_terminal(const prt_env_view& E, const prt_shot& S, const prt_traj_sink& sink)
+    // terminal step: _interpolate_ray bookkeeping for the st.finished segment (launch_rays.py:745-784),
+    // state at the st.event, then the reflection (launch_rays.py:432-480)
+    PRT_HD void finish_terminal(const prt_env_view& E, const prt_shot& S, const prt_traj_sink& sink, const prt_step& st)
     {
         if (status != PRT_RAY_OK) {
             phase = PRT_PH_DONE;
             return;
         }
-        const bool popped = (n_ts > 1) && (root == t_old);  // donot_append, ivp.py:701-710
+        const bool popped = (n_ts > 1) && (st.root == st.t_old);  // donot_append, ivp.py:701-710
         if (SAVE) {
             const int start = cursor > 0 ? cursor - 1 : 0;
-            const int ub = prt_argmin_from(S.range_save, S.n_save, start, root);  // idx2
+            const int ub = prt_argmin_from(S.range_save, S.n_save, start, st.root);  // idx2
             if (!popped) {
                 while (cursor < ub) {
-                    emit(sink, cursor, prt_ld(S.range_save + cursor));
+                    emit(sink, st, cursor, prt_ld(S.range_save + cursor));
                     ++cursor;
                 }
             }
             cursor = ub;  // the next segment owns indices >= idx2
         }
         if (!popped) {
-            const double xx = (root - t_old) * inv_h;
+            const double xx = (st.root - st.t_old) * st.inv_h;
             const double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
-            const double nT = prt_dense_eval(f0, qT, h, T, p1, p2, p3, p4);
-            const double nz = prt_dense_eval(f1, qz, h, z, p1, p2, p3, p4);
-            const double np_ = prt_dense_eval(f2, qp, h, p, p1, p2, p3, p4);
+            const double nT = prt_dense_eval(f0, st.qT, st.h, T, p1, p2, p3, p4);
+            const double nz = prt_dense_eval(f1, st.qz, st.h, z, p1, p2, p3, p4);
+            const double np_ = prt_dense_eval(f2, st.qp, st.h, p, p1, p2, p3, p4);
             T = nT; z = nz; p = np_;
-        }  // else: sol.y[:, -1] stays the state at t_old
-        t = root;
+        }  // else: sol.y[:, -1] stays the state at st.t_old
+        t = st.root;
         phase = PRT_PH_DONE;
-        if (event == 2) { status = PRT_RAY_VERTICAL; return; }
-        if (event == 3) { status = PRT_RAY_BBOX; return; }
+        if (st.event == 2) { status = PRT_RAY_VERTICAL; return; }
+        if (st.event == 3) { status = PRT_RAY_BBOX; return; }
         double c, cz;
         prt_field(E, t, z, c, cz);
         const double theta = prt_asin(p * c) * PRT_RAD2DEG;  // ray_angle
         double theta_bounce;
-        if (event == 0) {
+        if (st.event == 0) {
             theta_bounce = -theta;
             ++n_surface;
         } else {
@@ -1002,7 +1008,7 @@ struct prt_ray {
         res.n_surface = n_surface;
         res.status = status;
         if (cnt) {
-            cnt[PRT_CNT_NFEV] = c_nfev; cnt[PRT_CNT_ATTEMPTS] = c_att; cnt[PRT_CNT_ACCEPTED] = c_acc;
+            cnt[PRT_CNT_NFEV] = 2u * c_seg + 6u * c_att; cnt[PRT_CNT_ATTEMPTS] = c_att; cnt[PRT_CNT_ACCEPTED] = c_acc;
             cnt[PRT_CNT_SEGMENTS] = c_seg; cnt[PRT_CNT_BISECT] = c_bis; cnt[PRT_CNT_DENSE] = c_dense;
         }
     }
@@ -1018,12 +1024,13 @@ PRT_HD void prt_integrate_ray(const prt_env_view& E, double T, double z, double 
     r.start(T, z, p, x0, S);
     while (r.phase != PRT_PH_DONE) {
         if (r.phase == PRT_PH_INIT) r.seg_init(E, S);
-        if (!r.attempt(E, S)) continue;
-        if (r.active) {
-            r.solve_roots(E);
-            r.finish_terminal(E, S, sink);
+        prt_step st;
+        if (!r.attempt(E, S, st)) continue;
+        if (st.active) {
+            r.solve_roots(E, st);
+            r.finish_terminal(E, S, sink, st);
         } else {
-            r.advance(S, sink);
+            r.advance(S, sink, st);
         }
     }
     r.result(S, sink, res, cnt);

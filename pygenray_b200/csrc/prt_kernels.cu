@@ -80,17 +80,52 @@ static int park_wait_setting()
     return g_park_wait;
 }
 
+// Parked step records: [field][thread] doubles in shared memory (structure of arrays: conflict-free)
+#define PRT_PARK_FIELDS 20
+struct prt_park_slot {
+    double* base;  // &park[0][threadIdx.x]
+    __device__ __forceinline__ void store(const prt_step& st) const
+    {
+        double* q = base;
+        const int n = blockDim.x;
+        q[0 * n] = st.t_old; q[1 * n] = st.t_new; q[2 * n] = st.h; q[3 * n] = st.inv_h;
+        q[4 * n] = st.yT; q[5 * n] = st.yz; q[6 * n] = st.yp;
+        q[7 * n] = st.nf0; q[8 * n] = st.nf1; q[9 * n] = st.nf2;
+        q[10 * n] = st.qT.q1; q[11 * n] = st.qT.q2; q[12 * n] = st.qT.q3;
+        q[13 * n] = st.qz.q1; q[14 * n] = st.qz.q2; q[15 * n] = st.qz.q3;
+        q[16 * n] = st.qp.q1; q[17 * n] = st.qp.q2; q[18 * n] = st.qp.q3;
+        q[19 * n] = __longlong_as_double(((long long)st.active << 1) | (st.finished ? 1 : 0));
+    }
+    __device__ __forceinline__ void load(prt_step& st) const
+    {
+        const double* q = base;
+        const int n = blockDim.x;
+        st.t_old = q[0 * n]; st.t_new = q[1 * n]; st.h = q[2 * n]; st.inv_h = q[3 * n];
+        st.yT = q[4 * n]; st.yz = q[5 * n]; st.yp = q[6 * n];
+        st.nf0 = q[7 * n]; st.nf1 = q[8 * n]; st.nf2 = q[9 * n];
+        st.qT.q1 = q[10 * n]; st.qT.q2 = q[11 * n]; st.qT.q3 = q[12 * n];
+        st.qz.q1 = q[13 * n]; st.qz.q2 = q[14 * n]; st.qz.q3 = q[15 * n];
+        st.qp.q1 = q[16 * n]; st.qp.q2 = q[17 * n]; st.qp.q3 = q[18 * n];
+        const long long f = __double_as_longlong(q[19 * n]);
+        st.active = (int32_t)(f >> 1);
+        st.finished = (f & 1) != 0;
+        st.root = 0.0;
+        st.event = -1;
+    }
+};
+
 // Warp-synchronous driver of 32 rays (semantics = prt_integrate_ray for each lane; only the
 // interleaving differs, so results are bit-identical):
 //   * every iteration all stepping lanes make exactly ONE RK45 attempt together, accepted or not
 //     (no lane re-runs the stage code alone after a rejection);
-//   * a lane whose accepted step fired an event parks; the bisection root search, the reflection
-//     and the next segment's start-up run once for all parked lanes, when no lane is left stepping
-//     or the oldest parked lane has waited `park_wait` iterations (neighbouring launch angles
-//     reach a boundary within a few steps of each other).
+//   * a lane whose accepted step fired an event parks its step record in shared memory; the bisection
+//     root search, the reflection and the next segment's start-up run once for all parked lanes, when
+//     no lane is left stepping or the oldest parked lane has waited `park_wait` iterations
+//     (neighbouring launch angles reach a boundary within a few steps of each other).
 template <bool SAVE>
 __device__ __forceinline__ void prt_integrate_warp(const prt_env_view& E, prt_ray<SAVE>& r, const prt_shot& S,
-                                                   const prt_traj_sink& sink, int park_wait)
+                                                   const prt_traj_sink& sink, int park_wait,
+                                                   const prt_park_slot& park)
 {
     const unsigned full = 0xffffffffu;
     int waited = 0;
@@ -99,9 +134,14 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_env_view& E, prt_ra
         if (r.phase == PRT_PH_INIT) r.seg_init(E, S);
         __syncwarp(full);
         if (r.phase == PRT_PH_STEP) {
-            if (r.attempt(E, S)) {
-                if (r.active) r.phase = PRT_PH_ROOT;
-                else r.advance(S, sink);
+            prt_step st;
+            if (r.attempt(E, S, st)) {
+                if (st.active) {
+                    park.store(st);
+                    r.phase = PRT_PH_ROOT;
+                } else {
+                    r.advance(S, sink, st);
+                }
             }
         }
         __syncwarp(full);
@@ -111,8 +151,10 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_env_view& E, prt_ra
             ++waited;
             if (!stepping || waited > park_wait) {
                 if (r.phase == PRT_PH_ROOT) {
-                    r.solve_roots(E);
-                    r.finish_terminal(E, S, sink);
+                    prt_step st;
+                    park.load(st);
+                    r.solve_roots(E, st);
+                    r.finish_terminal(E, S, sink, st);
                 }
                 waited = 0;
             }
@@ -167,10 +209,13 @@ __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_fan_kernel(const __gr
         sink.z = sink.T + plane;
         sink.p = sink.z + plane;
     }
+    __shared__ double park_mem[PRT_PARK_FIELDS * 128];
+    prt_park_slot park;
+    park.base = park_mem + threadIdx.x;
     prt_ray<SAVE> r;
     r.start(T, z, p, P.source_range, S);
     if (!live) r.phase = PRT_PH_DONE;
-    prt_integrate_warp<SAVE>(E, r, S, sink, P.park_wait);
+    prt_integrate_warp<SAVE>(E, r, S, sink, P.park_wait, park);
     if (!live) return;
     prt_ray_result res;
     uint32_t cnt[PRT_CNT_N];
@@ -371,10 +416,13 @@ __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_refine_round_kernel(c
     sink.T = sink.z = sink.p = nullptr;
     sink.stride = 1;
     sink.sgn = 1.0;
+    __shared__ double park_mem[PRT_PARK_FIELDS * 128];
+    prt_park_slot park;
+    park.base = park_mem + threadIdx.x;
     prt_ray<false> r;
     r.start(T, z, p, P.source_range, shot);
     if (!live) r.phase = PRT_PH_DONE;
-    prt_integrate_warp<false>(E, r, shot, sink, P.park_wait);
+    prt_integrate_warp<false>(E, r, shot, sink, P.park_wait, park);
     if (!live) return;
     prt_ray_result res;
     r.result(shot, sink, res, nullptr);
