@@ -166,6 +166,15 @@ PRT_API int prt_shoot_fan_host(const prt_env_t *env, int64_t n_rays, const doubl
                        int32_t *out_p_sign_changes, int32_t max_bounces);
 
 /*
+ * Pack the arrival table of a fan into records [n_rays][6] = T, z, p, n_bottom, n_surface, status
+ * (doubles): the unit exchanged between GPUs (one all-gather; the reference gathers pickled Ray
+ * objects from its pool workers, launch_rays.py:157-186).
+ */
+PRT_API int prt_pack_arrivals(int64_t n_rays, const double *final_dev, const int32_t *n_bottom_dev,
+                              const int32_t *n_surface_dev, const int32_t *status_dev, double *records_dev,
+                              void *stream);
+
+/*
  * Eigenray bracketing (eigenrays.py:62-79): for every receiver depth, find adjacent surviving fan
  * rays whose final depths straddle it (sign change of zs[:, -1] + receiver_depth, zs negative-z).
  *   z_end_dev [n_rays]   final depths of the surviving fan rays in STORED convention (= -z)

@@ -23,7 +23,7 @@ DEFAULT_MAX_BOUNCES = 1 << 20
 EXPORTS = (
     "prt_abi_version", "prt_last_error", "prt_device_count", "prt_env_create", "prt_ensemble_create",
     "prt_shoot_ensemble", "prt_env_destroy",
-    "prt_env_device_bytes", "prt_shoot_fan", "prt_shoot_fan_host", "prt_count_brackets", "prt_fill_brackets",
+    "prt_env_device_bytes", "prt_shoot_fan", "prt_shoot_fan_host", "prt_pack_arrivals", "prt_count_brackets", "prt_fill_brackets",
     "prt_refine_workspace_bytes", "prt_refine_brackets", "prt_launch_count", "prt_measure_fp64_peak",
 )
 
@@ -65,6 +65,8 @@ def load():
     L.prt_shoot_ensemble.argtypes = [vp, i32, i64, vp] + fan_tail + [vp]
     L.prt_shoot_fan_host.restype = C.c_int
     L.prt_shoot_fan_host.argtypes = [vp, i64, vp, vp] + fan_tail
+    L.prt_pack_arrivals.restype = C.c_int
+    L.prt_pack_arrivals.argtypes = [i64, vp, vp, vp, vp, vp, vp]
     L.prt_count_brackets.restype = C.c_int
     L.prt_count_brackets.argtypes = [i64, vp, i32, vp, vp, vp]
     L.prt_fill_brackets.restype = C.c_int

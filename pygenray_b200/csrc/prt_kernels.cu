@@ -466,6 +466,22 @@ __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_refine_round_kernel(c
     list_out[atomicAdd(n_out, 1)] = b;
 }
 
+// arrival records [n][6] = T, z, p, n_bottom, n_surface, status (the unit of the multi-GPU all-gather)
+__global__ void prt_pack_arrivals_kernel(int64_t n, const double* __restrict__ fin, const int32_t* __restrict__ nb,
+                                         const int32_t* __restrict__ ns, const int32_t* __restrict__ st,
+                                         double* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* o = out + 6 * i;
+    o[0] = fin[i];
+    o[1] = fin[n + i];
+    o[2] = fin[2 * n + i];
+    o[3] = (double)nb[i];
+    o[4] = (double)ns[i];
+    o[5] = (double)st[i];
+}
+
 // ---------------------------------------------------------------------------------------------
 // FP64 FMA-pipe peak: 8 independent DFMA chains per thread
 __global__ void prt_fp64_peak_kernel(double* out, int iters, double a, double b)
@@ -738,6 +754,19 @@ int prt_fill_brackets(int64_t n_rays, const double* z_end_dev, const double* the
     prt_fill_brackets_kernel<<<(unsigned)n_rcv, 256, 0, s>>>(n_rays, z_end_dev, thetas_dev, n_rcv, receiver_depths_dev,
                                                              offsets_dev, br_z1_dev, br_z2_dev, br_th1_dev, br_th2_dev,
                                                              br_rd_dev, br_rcv_dev, br_k_dev);
+    g_launches.fetch_add(1);
+    PRT_CUDA(cudaGetLastError());
+    return PRT_SUCCESS;
+}
+
+int prt_pack_arrivals(int64_t n_rays, const double* final_dev, const int32_t* n_bottom_dev,
+                      const int32_t* n_surface_dev, const int32_t* status_dev, double* records_dev, void* stream)
+{
+    if (n_rays <= 0) return PRT_SUCCESS;
+    if (!final_dev || !n_bottom_dev || !n_surface_dev || !status_dev || !records_dev)
+        return fail(PRT_ERR_ARG, "prt_pack_arrivals: null pointer");
+    prt_pack_arrivals_kernel<<<(unsigned)((n_rays + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        n_rays, final_dev, n_bottom_dev, n_surface_dev, status_dev, records_dev);
     g_launches.fetch_add(1);
     PRT_CUDA(cudaGetLastError());
     return PRT_SUCCESS;

@@ -27,29 +27,50 @@ def shard_sizes(n_rays, world, block=BLOCK):
     return [int(shard_indices(n_rays, r, world, block).shape[0]) for r in range(world)]
 
 
+_GATHER_INDEX_CACHE = {}
+
+
+def _gather_index(n_rays, world, block, device):
+    """Row of the padded all-gather output that holds global ray i (cached per fan shape and device)."""
+    key = (n_rays, world, block, str(device))
+    idx = _GATHER_INDEX_CACHE.get(key)
+    if idx is None:
+        import torch  # noqa: PLC0415
+
+        sizes = shard_sizes(n_rays, world, block)
+        pad = max(sizes)
+        src = np.empty(n_rays, dtype=np.int64)
+        for r in range(world):
+            mine = shard_indices(n_rays, r, world, block)
+            src[mine] = r * pad + np.arange(mine.shape[0])
+        idx = (torch.from_numpy(src).to(device), sizes, pad)
+        _GATHER_INDEX_CACHE[key] = idx
+    return idx
+
+
 def all_gather_arrivals(local_records, n_rays, rank, world, block=BLOCK, group=None):
     """All-gather the per-rank arrival records and put them back in launch-angle order.
 
     ``local_records``: float64 tensor [n_local, RECORD_WIDTH] on the rank's device (CUDA with NCCL, CPU
     with gloo).  Returns a [n_rays, RECORD_WIDTH] tensor on the same device, identical on every rank.
+    One collective + one gather by a cached index (no per-rank Python work in the step).
     """
     import torch  # noqa: PLC0415
     import torch.distributed as dist  # noqa: PLC0415
 
-    sizes = shard_sizes(n_rays, world, block)
-    assert local_records.shape[0] == sizes[rank], "local shard has the wrong number of rays"
     if world == 1:
+        assert local_records.shape[0] == n_rays
         return local_records
-    pad = max(sizes)
-    buf = torch.zeros((pad, RECORD_WIDTH), dtype=torch.float64, device=local_records.device)
-    buf[: sizes[rank]] = local_records
+    src, sizes, pad = _gather_index(n_rays, world, block, local_records.device)
+    assert local_records.shape[0] == sizes[rank], "local shard has the wrong number of rays"
+    if sizes[rank] == pad:
+        buf = local_records.contiguous()
+    else:
+        buf = torch.zeros((pad, RECORD_WIDTH), dtype=torch.float64, device=local_records.device)
+        buf[: sizes[rank]] = local_records
     gathered = torch.empty((world * pad, RECORD_WIDTH), dtype=torch.float64, device=local_records.device)
     dist.all_gather_into_tensor(gathered, buf, group=group)
-    out = torch.empty((n_rays, RECORD_WIDTH), dtype=torch.float64, device=local_records.device)
-    for r in range(world):
-        idx = torch.from_numpy(shard_indices(n_rays, r, world, block)).to(local_records.device)
-        out[idx] = gathered[r * pad: r * pad + sizes[r]]
-    return out
+    return gathered.index_select(0, src)
 
 
 def records_from_result(res):
@@ -57,7 +78,20 @@ def records_from_result(res):
     import torch  # noqa: PLC0415
 
     final = res["final"]
-    rec = torch.empty((final.shape[1], RECORD_WIDTH), dtype=torch.float64, device=final.device)
+    n = final.shape[1]
+    rec = torch.empty((n, RECORD_WIDTH), dtype=torch.float64, device=final.device)
+    if final.is_cuda:
+        import ctypes as C  # noqa: PLC0415
+
+        from . import _lib  # noqa: PLC0415
+
+        with torch.cuda.device(final.device):
+            rc = _lib.load().prt_pack_arrivals(
+                n, C.c_void_p(final.data_ptr()), C.c_void_p(res["n_bottom"].data_ptr()),
+                C.c_void_p(res["n_surface"].data_ptr()), C.c_void_p(res["status"].data_ptr()),
+                C.c_void_p(rec.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "prt_pack_arrivals")
+        return rec
     rec[:, :3] = final.t()
     rec[:, 3] = res["n_bottom"]
     rec[:, 4] = res["n_surface"]

@@ -1,0 +1,44 @@
+"""Seeded random environments / shots for parity fuzzing (used by CPU and GPU parity tests)."""
+import numpy as np
+
+from oracle import cases
+
+
+def random_case(seed):
+    rng = np.random.default_rng(seed)
+    n_r = int(rng.integers(4, 60))
+    n_z = int(rng.integers(8, 200))
+    R = float(rng.uniform(2e4, 3e5))
+    zmax = float(rng.uniform(2000, 6500))
+    if rng.random() < 0.5:
+        r = np.linspace(0, R, n_r)
+    else:
+        r = np.sort(np.concatenate(([0.0, R], rng.uniform(0, R, n_r - 2))))
+    if rng.random() < 0.5:
+        z = np.linspace(0, zmax, n_z)
+    else:
+        z = np.sort(np.concatenate(([0.0, zmax], rng.uniform(0, zmax, n_z - 2))))
+    # keep grid points distinct (duplicate coordinates make the reference divide by zero)
+    r = np.unique(np.round(r, 3)); z = np.unique(np.round(z, 3))
+    n_r, n_z = len(r), len(z)
+    axis = rng.uniform(600, 1600)
+    c = np.array([cases.munk_ssp(z, axis + rng.uniform(-200, 200) * ri / R) for ri in r])
+    c += rng.normal(0, rng.choice([0.0, 0.05, 0.5]), size=c.shape)
+    n_b = int(rng.integers(4, 40))
+    b_end = R * float(rng.choice([1.0, 1.0, 1.0, 0.6, 1.3]))
+    bathy_r = np.linspace(0, b_end, n_b)
+    depth0 = rng.uniform(0.4, 1.1) * zmax
+    bathy = depth0 + rng.uniform(-0.2, 0.2) * zmax * np.sin(np.linspace(0, rng.uniform(1, 9), n_b)) \
+        + rng.normal(0, 10, n_b)
+    arrays = dict(c=c, r=r, z=z, bathy=bathy, bathy_r=bathy_r)
+    n_rays = int(rng.integers(1, 48))
+    lim = float(rng.choice([8.0, 15.0, 30.0, 60.0, 89.0]))
+    angles = np.sort(rng.uniform(-lim, lim, n_rays))
+    zs = float(rng.uniform(5, min(depth0, zmax) * 0.9))
+    r0 = float(rng.choice([0.0, rng.uniform(0, 0.3 * R)]))
+    r1 = float(rng.uniform(r0 + 0.2 * (R - r0), R * float(rng.choice([1.0, 1.0, 0.9]))))
+    n_save = int(rng.choice([0, 2, 3, 17, 120, 400]))
+    rtol = float(rng.choice([1e-9, 1e-9, 1e-6, 1e-11]))
+    tb = bool(rng.random() < 0.8)
+    return dict(arrays=arrays, flat=bool(rng.random() < 0.3), zs=zs, r0=r0, r1=r1, angles=angles, n_save=n_save,
+                rtol=rtol, terminate_backwards=tb, lat=float(rng.uniform(-60, 60)))

@@ -94,3 +94,17 @@ def test_backwards_mirrored_environment(harness):
     o, h = _both(harness, oenv, 300.0, -4e5, -1e5, np.linspace(-15, 15, 31), 120)
     assert (o["status"] == 0).any()
     assert_same_fan(o, h, "mirrored environment, negative ranges")
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_fuzz_random_environments(harness, seed):
+    """Random grids (uniform and irregular, noisy sound speed), bathymetry shorter or longer than the
+    track, random sources, angle ranges up to +-89 deg, save grids from 2 points up, tolerances."""
+    from fuzz_cases import random_case
+
+    k = random_case(seed)
+    env = make_env(k["arrays"], flat=k["flat"], lat=k["lat"])
+    oenv = oracle_env_from(env, k["flat"])
+    o, h = _both(harness, oenv, k["zs"], k["r0"], k["r1"], k["angles"], k["n_save"], rtol=k["rtol"],
+                 terminate_backwards=k["terminate_backwards"])
+    assert_same_fan(o, h, f"fuzz seed {seed}")

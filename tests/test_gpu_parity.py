@@ -244,3 +244,32 @@ def test_ensemble_launch_bit_identical_per_realisation(pr):
     assert not np.array_equal(g["final"][:, 0], g["final"][:, 1])  # the realisations differ
     with pytest.raises(pr._lib.PrtError):
         pr.shoot_fan_arrays(dens, 1000.0, 0.0, 1e5, angles=ang)  # an ensemble handle needs the ensemble call
+
+
+@pytest.mark.parametrize("seed", range(100, 130))
+def test_fuzz_random_environments_gpu(pr, seed):
+    """Seeded random environments / shots (tests/fuzz_cases.py): libprt.so == oracle, bit for bit."""
+    from fuzz_cases import random_case
+
+    k = random_case(seed)
+    env = make_env(k["arrays"], flat=k["flat"], lat=k["lat"])
+    g = _gpu_fan(pr, env, k["flat"], k["zs"], k["r0"], k["r1"], k["angles"], k["n_save"], rtol=k["rtol"],
+                 terminate_backwards=k["terminate_backwards"])
+    o = _oracle_fan(env, k["flat"], k["zs"], k["r0"], k["r1"], k["angles"], k["n_save"], rtol=k["rtol"],
+                    terminate_backwards=k["terminate_backwards"])
+    assert_same_fan(o, g, f"fuzz seed {seed}")
+
+
+def test_sharded_fan_single_rank_and_records(pr):
+    """dist.shoot_fan_sharded at world 1 == plain fan; prt_pack_arrivals lays out [n][6] records."""
+    from pygenray_b200 import dist as pdist
+
+    env = make_env(cases.config2_arrays())
+    denv = pr.DeviceEnvironment(*pr._unpack_envi(env, flatearth=False))
+    ang = np.linspace(-15, 15, 130)
+    table, local = pdist.shoot_fan_sharded(denv, 1000.0, 0.0, 1e5, ang, 0, 1)
+    ref = pr.shoot_fan_arrays(denv, 1000.0, 0.0, 1e5, angles=ang)
+    t = table.cpu().numpy()
+    assert np.array_equal(t[:, :3], ref["final"].T, equal_nan=True)
+    assert np.array_equal(t[:, 3], ref["n_bottom"]) and np.array_equal(t[:, 4], ref["n_surface"])
+    assert np.array_equal(t[:, 5], ref["status"])
