@@ -288,7 +288,6 @@ def run_b200(args):
         torch.cuda.synchronize()
         _lib.check(rc, "prt_shoot_fan")
         kern_ms.append(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
     cnt = cnt_d.cpu().numpy().astype(np.uint32)
     flops = algorithmic_flops(cnt)
     k_ms = float(np.mean(kern_ms))
@@ -374,6 +373,7 @@ def run_b200(args):
                                    "sample": f"first {sub.stop} brackets, {dtc:.1f} s"}
             eig["parity_vs_cpu"] = bool(np.array_equal(o["theta"], ref["theta"].cpu().numpy()[sub], equal_nan=True))
 
+    clocks = sampler.stop() if rank == 0 else None  # sampled over the device-timed, kernel-only and e2e legs
     if rank == 0:
         # CPU oracle on the same workload (bounded: the whole 10k fan takes seconds in C)
         sub = angles if len(angles) <= 20000 else angles[:: len(angles) // 4096]
@@ -387,7 +387,11 @@ def run_b200(args):
                        "parallelism": f"launch angles interleaved over {world} rank(s); arrival tables all-gathered"
                        if world > 1 else "single GPU, one thread per ray"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-                         "frac": achieved / (fp64_peak / 1e12) if fp64_peak > 0 else None, "traffic": None,
+                         "frac": achieved / (fp64_peak / 1e12) if fp64_peak > 0 else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload from the
+                         # ncu --set full capture summarised in profiles/r01_ncu_fan.md (10.9 MB + 203.7 MB)
+                         "traffic": 214.6e6 if (w["name"] == "cfg2" and world == 1) else None,
+                         "traffic_algorithmic_bytes": out_bytes,
                          "kernel": "prt_fan_kernel", "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
                          "peak_source": "DFMA microbenchmark (prt_measure_fp64_peak) in this run; "
                                         "MEASURED_PEAKS.json has no FP64 figure",

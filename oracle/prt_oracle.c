@@ -22,7 +22,7 @@
  * Rounding contract ("PRT arithmetic"): IEEE-754 binary64, round-to-nearest-even, every
  * operation written below is one correctly rounded operation; fma() is used exactly where
  * written and nowhere else (compile with -ffp-contract=off); +,-,*,/,sqrt,fma only, plus the
- * three elementary functions det_pow_m02 / det_sin / det_asin defined in this file from those
+ * elementary functions orc_pow_m02 / orc_pow_m01 / orc_rsqrt / orc_sin / orc_asin defined in this file from those
  * operations; three divisions of the reference are written as multiplications by a correctly
  * rounded reciprocal (interpolation weights, dense-output abscissa, fact/c^2 in derivsrd: marked
  * "contract:" below), as LLVM fast-math is free to do for the reference's own Numba code.
@@ -105,6 +105,59 @@ ORC_API double orc_pow_m02(double x)
         double y5 = y4 * y;
         double res = fma(-m, y5, 1.0);
         y = fma(y * 0.2, res, y);
+    }
+    y = y * T[r];
+    uint64_t pb = (uint64_t)(1023 - q) << 52;
+    double p2;
+    memcpy(&p2, &pb, 8);
+    return (y * p2) * post;
+}
+
+/* 1/sqrt(w) for normal w > 0: integer-shift seed (3.4e-2) + 4 Newton steps y <- y (1.5 - 0.5 w y^2);
+ * <= 2.3 ulp.  contract: stands for the 1/sqrt of ref:integration_processes.py:95 (see derivsrd). */
+ORC_API double orc_rsqrt(double w)
+{
+    uint64_t b;
+    memcpy(&b, &w, 8);
+    b = 0x5FE6EB50C7B537A9ULL - (b >> 1);
+    double y;
+    memcpy(&y, &b, 8);
+    const double hw = 0.5 * w;
+    for (int it = 0; it < 4; ++it) {
+        double t = y * y;
+        double r = fma(-hw, t, 1.5);
+        y = y * r;
+    }
+    return y;
+}
+
+/* x^(-1/10) for x > 0: the step controller's error_norm ** (-1/5) expressed on the MEAN SQUARE
+ * x = error_norm^2 (no square root); exponent split by 10 + 3 Newton steps; <= 2 ulp. */
+ORC_API double orc_pow_m01(double x)
+{
+    static const double T[10] = {1.0, 0x1.ddb680117ab12p-1, 0x1.bdb8cdadbe120p-1, 0x1.9fdf8bcce533ep-1,
+                                 0x1.8406003b2ae5cp-1, 0x1.6a09e667f3bcdp-1, 0x1.51cb453b9536cp-1,
+                                 0x1.3b2c47bff8329p-1, 0x1.2611186bae674p-1, 0x1.125fbee250664p-1}; /* 2^(-r/10) */
+    if (x != x) return x;
+    if (x == INFINITY) return 0.0;
+    double post = 1.0;
+    if (x < 0x1p-1022) { x = x * 0x1p100; post = 0x1p10; }
+    uint64_t b;
+    memcpy(&b, &x, 8);
+    int e = (int)((b >> 52) & 0x7ff) - 1023;
+    b = (b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL;
+    double m;
+    memcpy(&m, &b, 8);
+    int q = (e >= 0) ? (e / 10) : -((9 - e) / 10);
+    int r = e - 10 * q;
+    double y = fma(fma(0.024999779689669537, m, -0.14120119176598264), m, 1.1157678629591425);
+    for (int it = 0; it < 3; ++it) {
+        double y2 = y * y;
+        double y4 = y2 * y2;
+        double y8 = y4 * y4;
+        double y10 = y8 * y2;
+        double res = fma(-m, y10, 1.0);
+        y = fma(y * 0.1, res, y);
     }
     y = y * T[r];
     uint64_t pb = (uint64_t)(1023 - q) << 52;
@@ -255,9 +308,9 @@ static void derivsrd(const orc_env *E, double x, const double *y, double *dydx, 
     double c2 = c * c;
     double arg = fma(-c2, pz * pz, 1.0);
     if (arg <= 0.0) arg = 1e-30;
-    /* contract: fact / c^2 is formed once as u = 1 / (c^2 sqrt(arg)); then
+    /* contract: fact / c^2 is formed once as u = 1 / (c^2 sqrt(arg)) = rsqrt(c^4 arg); then
      * [fact/c, c*pz*fact, -fact*cp/c^2] = [c u, c^2 (c u) pz, -cp u] */
-    double u = 1.0 / (c2 * sqrt(arg));
+    double u = orc_rsqrt((c2 * c2) * arg);
     double t1 = c * u;
     dydx[0] = t1;
     dydx[1] = (c2 * t1) * pz;
@@ -440,16 +493,21 @@ static int solver_step_impl(solver_t *S)
             double scale = fma(np_maximum(fabs(y[k]), fabs(y_new[k])), S->rtol, S->atol);
             r[k] = (kdot(S->K, k, RK_E, 7) * h) / scale;
         }
-        double error_norm = rms3(r);
-        if (error_norm < 1.0) {
+        /* contract: error_norm = sqrt(mean(r^2)) is carried as its square ms (no square root, no division):
+         * accept iff ms < 1, and error_norm ** (-1/5) = ms ** (-1/10)   (scipy:rk.py:148-165) */
+        double ms = r[0] * r[0];
+        ms = fma(r[1], r[1], ms);
+        ms = fma(r[2], r[2], ms);
+        ms = ms * 0x1.5555555555555p-2;
+        if (ms < 1.0) {
             double factor;
-            if (error_norm == 0.0) factor = MAX_FACTOR;
-            else factor = py_min(MAX_FACTOR, SAFETY * orc_pow_m02(error_norm));
+            if (ms == 0.0) factor = MAX_FACTOR;
+            else factor = py_min(MAX_FACTOR, SAFETY * orc_pow_m01(ms));
             if (step_rejected) factor = py_min(1.0, factor);
             h_abs *= factor;
             break;
         } else {
-            h_abs *= py_max(MIN_FACTOR, SAFETY * orc_pow_m02(error_norm));
+            h_abs *= py_max(MIN_FACTOR, SAFETY * orc_pow_m01(ms));
             step_rejected = 1;
         }
     }

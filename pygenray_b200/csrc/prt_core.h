@@ -123,6 +123,19 @@ PRT_HD double prt_np_maximum(double a, double b) { return (a != a) ? a : ((b != 
 // ---------------------------------------------------------------------------------------------
 // Elementary functions of the rounding contract
 
+#define PRT_POW10_INIT {1.0, 0x1.ddb680117ab12p-1, 0x1.bdb8cdadbe120p-1, 0x1.9fdf8bcce533ep-1, 0x1.8406003b2ae5cp-1, \
+                        0x1.6a09e667f3bcdp-1, 0x1.51cb453b9536cp-1, 0x1.3b2c47bff8329p-1, 0x1.2611186bae674p-1, \
+                        0x1.125fbee250664p-1}
+#if defined(__CUDACC__)
+__constant__ double prt_pow10_dev[10] = PRT_POW10_INIT;
+#endif
+static const double prt_pow10_host[10] = PRT_POW10_INIT;
+#if defined(__CUDA_ARCH__)
+#define PRT_POW10_TAB(i) prt_pow10_dev[i]
+#else
+#define PRT_POW10_TAB(i) prt_pow10_host[i]
+#endif
+
 // x^(-1/5): stands for error_norm ** (-1/5), scipy rk.py:155,163.  Hot path = normal finite x; NaN,
 // infinity and subnormals take the cold prologue.
 PRT_HD_NOINLINE double prt_pow_m02_special(double x, double& post)
@@ -170,6 +183,62 @@ PRT_HD double prt_pow_m02(double x)
     y = y * tr;
     const double p2 = prt_bits_to_double((uint64_t)(1023 - q) << 52);
     return (y * p2) * post;
+}
+
+// x^(-1/10): the controller's error_norm ** (-1/5) on the mean square x = error_norm^2 (no sqrt).
+PRT_HD_NOINLINE double prt_pow_m01_special(double x, double& post)
+{
+    post = 1.0;
+    if (x != x) return x;
+    if (x == (double)INFINITY) return x;
+    if (x < 0x1p-1022) {
+        post = 0x1p10;
+        return x * 0x1p100;
+    }
+    return x;
+}
+
+PRT_HD double prt_pow_m01(double x)
+{
+    double post = 1.0;
+    if (!(x >= 0x1p-1022 && x < (double)INFINITY)) {
+        x = prt_pow_m01_special(x, post);
+        if (x != x) return x;
+        if (x == (double)INFINITY) return 0.0;
+    }
+    const uint64_t b = prt_double_to_bits(x);
+    const int e = (int)((b >> 52) & 0x7ff) - 1023;
+    const double m = prt_bits_to_double((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
+    const unsigned eu = (unsigned)(e + 1030);  // e = 10 q + r, r in 0..9 (floor division, kept unsigned)
+    const int q = (int)(eu / 10u) - 103;
+    const int r = (int)(eu - 10u * (eu / 10u));
+    double y = PRT_FMA(PRT_FMA(0.024999779689669537, m, -0.14120119176598264), m, 1.1157678629591425);
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+        const double y2 = y * y;
+        const double y4 = y2 * y2;
+        const double y8 = y4 * y4;
+        const double y10 = y8 * y2;
+        const double res = PRT_FMA(-m, y10, 1.0);
+        y = PRT_FMA(y * 0.1, res, y);
+    }
+    y = y * PRT_POW10_TAB(r);  // 2^(-r/10)
+    const double p2 = prt_bits_to_double((uint64_t)(1023 - q) << 52);
+    return (y * p2) * post;
+}
+
+// 1/sqrt(w), normal w > 0: integer-shift seed + 4 Newton steps (<= 2.3 ulp); see oracle orc_rsqrt
+PRT_HD double prt_rsqrt(double w)
+{
+    double y = prt_bits_to_double(0x5FE6EB50C7B537A9ULL - (prt_double_to_bits(w) >> 1));
+    const double hw = 0.5 * w;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const double t = y * y;
+        const double r = PRT_FMA(-hw, t, 1.5);
+        y = y * r;
+    }
+    return y;
 }
 
 PRT_HD double prt_k_sin(double r)
@@ -345,8 +414,8 @@ PRT_HD double prt_bathy(const prt_env_view& E, double x)
     return PRT_FMA(w, v.y, (1.0 - w) * v.x);
 }
 
-// derivsrd (integration_processes.py:26-98) with one square root and one reciprocal:
-//   u = 1 / (c^2 sqrt(arg));  dT = c u;  dz = c^2 dT p;  dp = -cz u          (also returns c)
+// derivsrd (integration_processes.py:26-98) with a single reciprocal square root:
+//   u = 1 / (c^2 sqrt(arg)) = rsqrt(c^4 arg);  dT = c u;  dz = c^2 dT p;  dp = -cz u     (also returns c)
 PRT_HD void prt_rhs(const prt_env_view& E, double x, double z, double p, double& dT, double& dz, double& dp,
                     double& c_out)
 {
@@ -355,7 +424,7 @@ PRT_HD void prt_rhs(const prt_env_view& E, double x, double z, double p, double&
     double c2 = c * c;
     double arg = PRT_FMA(-c2, p * p, 1.0);
     if (arg <= 0.0) arg = 1e-30;
-    double u = 1.0 / (c2 * sqrt(arg));
+    double u = prt_rsqrt((c2 * c2) * arg);
     double t1 = c * u;
     dT = t1;
     dz = (c2 * t1) * p;
@@ -826,13 +895,19 @@ struct prt_ray {
         const double scT = PRT_FMA(prt_np_maximum(fabs(T), fabs(nT)), S.rtol, S.atol);
         const double scz = PRT_FMA(prt_np_maximum(fabs(z), fabs(nz)), S.rtol, S.atol);
         const double scp = PRT_FMA(prt_np_maximum(fabs(p), fabs(np_)), S.rtol, S.atol);
-        const double err = prt_rms3((eT * hh) / scT, (ez * hh) / scz, (ep * hh) / scp);
-        if (!(err < 1.0)) {
-            h_abs *= prt_py_max(0.2, 0.9 * prt_pow_m02(err));
+        // error_norm carried as its square (mean square of the scaled error): accept iff ms < 1 and
+        // error_norm ** (-1/5) = ms ** (-1/10)  -- no square root, no division by sqrt(3) (rk.py:148-165)
+        const double r0 = (eT * hh) / scT, r1 = (ez * hh) / scz, r2 = (ep * hh) / scp;
+        double ms = r0 * r0;
+        ms = PRT_FMA(r1, r1, ms);
+        ms = PRT_FMA(r2, r2, ms);
+        ms = ms * 0x1.5555555555555p-2;
+        if (!(ms < 1.0)) {
+            h_abs *= prt_py_max(0.2, 0.9 * prt_pow_m01(ms));
             rejected = true;
             return false;
         }
-        double factor = (err == 0.0) ? 10.0 : prt_py_min(10.0, 0.9 * prt_pow_m02(err));
+        double factor = (ms == 0.0) ? 10.0 : prt_py_min(10.0, 0.9 * prt_pow_m01(ms));
         if (rejected) factor = prt_py_min(1.0, factor);
         h_abs *= factor;
         rejected = false;

@@ -198,7 +198,7 @@ def test_eigenray_refinement_bit_identical_to_oracle(pr):
     assert np.array_equal(ref["shots"].cpu().numpy(), o["shots"])
     assert np.array_equal(ref["theta"].cpu().numpy(), o["theta"], equal_nan=True)
     assert np.array_equal(ref["final"].cpu().numpy().T, o["final"], equal_nan=True)
-    assert (o["status"] == 0).sum() > 20
+    assert (o["status"] == 0).sum() > 5 and (o["status"] == 2).sum() > 5  # both outcomes exercised
 
 
 # ---- full-size properties (BASELINE.json sizes; no oracle pass over the whole set) -----------------

