@@ -379,15 +379,33 @@ PRT_HD
 #endif
 void prt_field(const prt_env_view& E, double x, double z, double& c, double& cz)
 {
-    prt_d2 re, ze;
-    int i = prt_locate(E.rpair, E.n_r, E.r0, E.r_inv, x, re);
-    int j = prt_locate(E.zpair, E.n_z, E.z0, E.z_inv, z, ze);
+    // Speculate on the guessed cell: every load (cell edges, reciprocals, the four corner nodes) is issued
+    // from the guessed indices at once, so the lookup costs ONE cache round trip; the guesses are verified
+    // afterwards and the rare miss (cell boundary rounding, non-uniform grids) takes the general lookup.
+    const int mr = E.n_r - 2, mz = E.n_z - 2;
+    int i = PRT_D2I((x - E.r0) * E.r_inv);
+    int j = PRT_D2I((z - E.z0) * E.z_inv);
+    i = i < 0 ? 0 : i; i = i > mr ? mr : i;
+    j = j < 0 ? 0 : j; j = j > mz ? mz : j;
+    prt_d2 re = prt_ld2(E.rpair + i), ze = prt_ld2(E.zpair + j);
     const prt_d2* g = E.grid + ((size_t)i * (size_t)E.n_z + (size_t)j);
     double ir = prt_ld(E.rrecip + i), iz = prt_ld(E.zrecip + j);
     prt_d2 v00 = prt_ld2(g);
     prt_d2 v01 = prt_ld2(g + 1);
     prt_d2 v10 = prt_ld2(g + E.n_z);
     prt_d2 v11 = prt_ld2(g + E.n_z + 1);
+    const bool ok = (i == 0 || re.x < x) && (i == mr || x <= re.y) && (j == 0 || ze.x < z) && (j == mz || z <= ze.y);
+    if (!ok) {
+        i = prt_locate(E.rpair, E.n_r, E.r0, E.r_inv, x, re);
+        j = prt_locate(E.zpair, E.n_z, E.z0, E.z_inv, z, ze);
+        g = E.grid + ((size_t)i * (size_t)E.n_z + (size_t)j);
+        ir = prt_ld(E.rrecip + i);
+        iz = prt_ld(E.zrecip + j);
+        v00 = prt_ld2(g);
+        v01 = prt_ld2(g + 1);
+        v10 = prt_ld2(g + E.n_z);
+        v11 = prt_ld2(g + E.n_z + 1);
+    }
     double wx = (x - re.x) * ir;
     double wy = (z - ze.x) * iz;
     double ax = 1.0 - wx, ay = 1.0 - wy;
