@@ -273,12 +273,11 @@ static double bilinear_interp(double x, double y, const double *xg, int nx, cons
     double v10 = values[(size_t)(i + 1) * ny + j];
     double v01 = values[(size_t)i * ny + j + 1];
     double v11 = values[(size_t)(i + 1) * ny + j + 1];
-    double ax = 1.0 - wx, ay = 1.0 - wy;
-    double v = (ax * ay) * v00;
-    v = fma(wx * ay, v10, v);
-    v = fma(ax * wy, v01, v);
-    v = fma(wx * wy, v11, v);
-    return v;
+    /* contract: the four-weight sum (1-wx)(1-wy) v00 + wx (1-wy) v10 + (1-wx) wy v01 + wx wy v11
+     * regrouped as two depth lerps and one range lerp */
+    double l0 = fma(wy, v01 - v00, v00);
+    double l1 = fma(wy, v11 - v10, v10);
+    return fma(wx, l1 - l0, l0);
 }
 
 /* ref:integration_processes.py:177-235 linear_interp */

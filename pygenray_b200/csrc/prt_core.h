@@ -371,7 +371,8 @@ PRT_HD int prt_locate(const prt_d2* pair, int n, double x0, double inv, double v
 
 // c(x, z) and dc/dz(x, z): bilinear_interp (integration_processes.py:101-174) evaluated ONCE for
 // both fields (the reference evaluates it twice with identical weights, :86-87).  The weight
-// divisions use the per-cell reciprocals 1/(x[i+1]-x[i]) tabulated at staging time.
+// divisions use the per-cell reciprocals 1/(x[i+1]-x[i]) tabulated at staging time; the four-weight
+// sum is regrouped as lerps (contract, mirrored in the oracle).
 #if defined(PRT_FIELD_NOINLINE)
 PRT_HD_NOINLINE
 #else
@@ -408,18 +409,13 @@ void prt_field(const prt_env_view& E, double x, double z, double& c, double& cz)
     }
     double wx = (x - re.x) * ir;
     double wy = (z - ze.x) * iz;
-    double ax = 1.0 - wx, ay = 1.0 - wy;
-    double w00 = ax * ay, w10 = wx * ay, w01 = ax * wy, w11 = wx * wy;
-    double a = w00 * v00.x;
-    a = PRT_FMA(w10, v10.x, a);
-    a = PRT_FMA(w01, v01.x, a);
-    a = PRT_FMA(w11, v11.x, a);
-    double b = w00 * v00.y;
-    b = PRT_FMA(w10, v10.y, b);
-    b = PRT_FMA(w01, v01.y, b);
-    b = PRT_FMA(w11, v11.y, b);
-    c = a;
-    cz = b;
+    // bilinear interpolation as two depth lerps and one range lerp (dependent depth 3 after the weights):
+    //   l0 = v00 + wy (v01 - v00),  l1 = v10 + wy (v11 - v10),  v = l0 + wx (l1 - l0)
+    // == the reference's (1-wx)(1-wy) v00 + wx (1-wy) v10 + (1-wx) wy v01 + wx wy v11, regrouped
+    const double c0 = PRT_FMA(wy, v01.x - v00.x, v00.x), c1 = PRT_FMA(wy, v11.x - v10.x, v10.x);
+    const double d0 = PRT_FMA(wy, v01.y - v00.y, v00.y), d1 = PRT_FMA(wy, v11.y - v10.y, v10.y);
+    c = PRT_FMA(wx, c1 - c0, c0);
+    cz = PRT_FMA(wx, d1 - d0, d0);
 }
 
 // bottom depth at x: linear_interp (integration_processes.py:177-235)
