@@ -93,6 +93,8 @@ struct prt_env_view {
     const prt_d2* zpair;    // [n_z-1] {zin[j], zin[j+1]}
     const prt_d2* bxpair;   // [n_b-1] {depth_ranges[i], depth_ranges[i+1]}
     const prt_d2* bvpair;   // [n_b-1] {depths[i], depths[i+1]}
+    const prt_d2* rcell;    // [n_r-1] x 2 prt_d2: {lo, hi}, {rin[i], 1/(rin[i+1]-rin[i])}; lo/hi = cell edges with
+    const prt_d2* zcell;    // [n_z-1]   -inf / +inf at the two ends of the grid: "cell i holds v" <=> lo < v <= hi
     const double* rrecip;   // [n_r-1] 1 / (rin[i+1] - rin[i])
     const double* zrecip;   // [n_z-1] 1 / (zin[j+1] - zin[j])
     const double* brecip;   // [n_b-1] 1 / (depth_ranges[i+1] - depth_ranges[i])
@@ -380,35 +382,40 @@ PRT_HD
 #endif
 void prt_field(const prt_env_view& E, double x, double z, double& c, double& cz)
 {
-    // Speculate on the guessed cell: every load (cell edges, reciprocals, the four corner nodes) is issued
-    // from the guessed indices at once, so the lookup costs ONE cache round trip; the guesses are verified
-    // afterwards and the rare miss (cell boundary rounding, non-uniform grids) takes the general lookup.
+    // Speculate on the guessed cell: every load (cell records and the four corner nodes) is issued from the
+    // guessed indices at once, so the lookup costs ONE cache round trip; the guesses are verified afterwards
+    // (two compares per axis against edges padded with -inf / +inf at the grid ends, false for NaN) and the
+    // rare miss (cell-boundary rounding, non-uniform grids) takes the general lookup.
     const int mr = E.n_r - 2, mz = E.n_z - 2;
     int i = PRT_D2I((x - E.r0) * E.r_inv);
     int j = PRT_D2I((z - E.z0) * E.z_inv);
     i = i < 0 ? 0 : i; i = i > mr ? mr : i;
     j = j < 0 ? 0 : j; j = j > mz ? mz : j;
-    prt_d2 re = prt_ld2(E.rpair + i), ze = prt_ld2(E.zpair + j);
-    const prt_d2* g = E.grid + ((size_t)i * (size_t)E.n_z + (size_t)j);
-    double ir = prt_ld(E.rrecip + i), iz = prt_ld(E.zrecip + j);
+    const prt_d2* rc = E.rcell + 2 * (unsigned)i;
+    const prt_d2* zc = E.zcell + 2 * (unsigned)j;
+    const prt_d2 rv = prt_ld2(rc), ra = prt_ld2(rc + 1);
+    const prt_d2 zv = prt_ld2(zc), za = prt_ld2(zc + 1);
+    const prt_d2* g = E.grid + ((unsigned)i * (unsigned)E.n_z + (unsigned)j);
     prt_d2 v00 = prt_ld2(g);
     prt_d2 v01 = prt_ld2(g + 1);
     prt_d2 v10 = prt_ld2(g + E.n_z);
     prt_d2 v11 = prt_ld2(g + E.n_z + 1);
-    const bool ok = (i == 0 || re.x < x) && (i == mr || x <= re.y) && (j == 0 || ze.x < z) && (j == mz || z <= ze.y);
-    if (!ok) {
+    double wx, wy;
+    if ((rv.x < x) & (x <= rv.y) & (zv.x < z) & (z <= zv.y)) {
+        wx = (x - ra.x) * ra.y;
+        wy = (z - za.x) * za.y;
+    } else {
+        prt_d2 re, ze;
         i = prt_locate(E.rpair, E.n_r, E.r0, E.r_inv, x, re);
         j = prt_locate(E.zpair, E.n_z, E.z0, E.z_inv, z, ze);
-        g = E.grid + ((size_t)i * (size_t)E.n_z + (size_t)j);
-        ir = prt_ld(E.rrecip + i);
-        iz = prt_ld(E.zrecip + j);
+        g = E.grid + ((unsigned)i * (unsigned)E.n_z + (unsigned)j);
         v00 = prt_ld2(g);
         v01 = prt_ld2(g + 1);
         v10 = prt_ld2(g + E.n_z);
         v11 = prt_ld2(g + E.n_z + 1);
+        wx = (x - re.x) * prt_ld(E.rrecip + i);
+        wy = (z - ze.x) * prt_ld(E.zrecip + j);
     }
-    double wx = (x - re.x) * ir;
-    double wy = (z - ze.x) * iz;
     // bilinear interpolation as two depth lerps and one range lerp (dependent depth 3 after the weights):
     //   l0 = v00 + wy (v01 - v00),  l1 = v10 + wy (v11 - v10),  v = l0 + wx (l1 - l0)
     // == the reference's (1-wx)(1-wy) v00 + wx (1-wy) v10 + (1-wx) wy v01 + wx wy v11, regrouped

@@ -8,6 +8,7 @@
 //   rrecip [n_r-1] 1/(r[i+1]-r[i]) -- interpolation weights without a division (same for z, bathymetry)
 // and a prt_env_view whose pointers are offsets into the blob until prt_env_rebase() is applied.
 #pragma once
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -36,6 +37,17 @@ static inline void prt_pack_recip(double* dst, const double* a, int n)
     for (int i = 0; i < n - 1; ++i) dst[i] = 1.0 / (a[i + 1] - a[i]);
 }
 
+// {lo, hi}, {a[i], 1/(a[i+1]-a[i])} per cell; lo = -inf for the first cell, hi = +inf for the last
+static inline void prt_pack_cells(prt_d2* dst, const double* a, int n)
+{
+    for (int i = 0; i < n - 1; ++i) {
+        dst[2 * i].x = (i == 0) ? -INFINITY : a[i];
+        dst[2 * i].y = (i == n - 2) ? INFINITY : a[i + 1];
+        dst[2 * i + 1].x = a[i];
+        dst[2 * i + 1].y = 1.0 / (a[i + 1] - a[i]);
+    }
+}
+
 static inline double prt_inv_mean_step(const double* a, int n)
 {
     double span = a[n - 1] - a[0];
@@ -59,7 +71,9 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
     size_t o_rrec = o_bv + prt_align256(sizeof(prt_d2) * (size_t)(n_b - 1));
     size_t o_zrec = o_rrec + prt_align256(sizeof(double) * (size_t)(n_r - 1));
     size_t o_brec = o_zrec + prt_align256(sizeof(double) * (size_t)(n_z - 1));
-    size_t o_bax = o_brec + prt_align256(sizeof(double) * (size_t)(n_b - 1));
+    size_t o_rcell = o_brec + prt_align256(sizeof(double) * (size_t)(n_b - 1));
+    size_t o_zcell = o_rcell + prt_align256(sizeof(prt_d2) * 2 * (size_t)(n_r - 1));
+    size_t o_bax = o_zcell + prt_align256(sizeof(prt_d2) * 2 * (size_t)(n_z - 1));
     size_t o_bac = o_bax + prt_align256(sizeof(double) * (size_t)n_ba);
     size_t total = o_bac + prt_align256(sizeof(double) * 4 * (size_t)(n_ba - 1));
     out.bytes.assign(total, 0);
@@ -74,6 +88,8 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
     prt_pack_pairs(reinterpret_cast<prt_d2*>(base + o_zpair), zin, n_z);
     prt_pack_pairs(reinterpret_cast<prt_d2*>(base + o_bx), depth_ranges, n_b);
     prt_pack_pairs(reinterpret_cast<prt_d2*>(base + o_bv), depths, n_b);
+    prt_pack_cells(reinterpret_cast<prt_d2*>(base + o_rcell), rin, n_r);
+    prt_pack_cells(reinterpret_cast<prt_d2*>(base + o_zcell), zin, n_z);
     prt_pack_recip(reinterpret_cast<double*>(base + o_rrec), rin, n_r);
     prt_pack_recip(reinterpret_cast<double*>(base + o_zrec), zin, n_z);
     prt_pack_recip(reinterpret_cast<double*>(base + o_brec), depth_ranges, n_b);
@@ -89,6 +105,8 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
     v.zpair = reinterpret_cast<const prt_d2*>(o_zpair);
     v.bxpair = reinterpret_cast<const prt_d2*>(o_bx);
     v.bvpair = reinterpret_cast<const prt_d2*>(o_bv);
+    v.rcell = reinterpret_cast<const prt_d2*>(o_rcell);
+    v.zcell = reinterpret_cast<const prt_d2*>(o_zcell);
     v.rrecip = reinterpret_cast<const double*>(o_rrec);
     v.zrecip = reinterpret_cast<const double*>(o_zrec);
     v.brecip = reinterpret_cast<const double*>(o_brec);
@@ -116,6 +134,8 @@ static inline prt_env_view prt_env_rebase(const prt_env_view& view, const void* 
     v.zpair = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.zpair));
     v.bxpair = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.bxpair));
     v.bvpair = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.bvpair));
+    v.rcell = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.rcell));
+    v.zcell = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.zcell));
     v.rrecip = reinterpret_cast<const double*>(b + reinterpret_cast<size_t>(view.rrecip));
     v.zrecip = reinterpret_cast<const double*>(b + reinterpret_cast<size_t>(view.zrecip));
     v.brecip = reinterpret_cast<const double*>(b + reinterpret_cast<size_t>(view.brecip));
