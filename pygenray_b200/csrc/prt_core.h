@@ -109,7 +109,7 @@ struct prt_env_view {
 // np.nextafter(t, +inf) (scipy rk.py:119) by integer increment of the bit pattern
 PRT_HD double prt_next_up(double t)
 {
-    if (t != t || t == (double)INFINITY) return t;
+    if (!(fabs(t) < (double)INFINITY)) return t;  // NaN, +-inf: unchanged (never reached: t is a finite range)
     if (t == 0.0) return 4.9406564584124654e-324;
     uint64_t b = prt_double_to_bits(t);
     b = (t > 0.0) ? b + 1 : b - 1;
@@ -923,12 +923,15 @@ struct prt_ray {
         ms = PRT_FMA(r1, r1, ms);
         ms = PRT_FMA(r2, r2, ms);
         ms = ms * 0x1.5555555555555p-2;
+        // one evaluation of the controller power for accepting and rejecting lanes alike (lanes of a warp
+        // split between the two outcomes on most attempts)
+        const double pw = (ms == 0.0) ? 0.0 : prt_pow_m01(ms);
         if (!(ms < 1.0)) {
-            h_abs *= prt_py_max(0.2, 0.9 * prt_pow_m01(ms));
+            h_abs *= prt_py_max(0.2, 0.9 * pw);
             rejected = true;
             return false;
         }
-        double factor = (ms == 0.0) ? 10.0 : prt_py_min(10.0, 0.9 * prt_pow_m01(ms));
+        double factor = (ms == 0.0) ? 10.0 : prt_py_min(10.0, 0.9 * pw);
         if (rejected) factor = prt_py_min(1.0, factor);
         h_abs *= factor;
         rejected = false;
