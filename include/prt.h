@@ -82,6 +82,11 @@ typedef struct prt_env prt_env_t;
 PRT_API int prt_abi_version(void);
 PRT_API const char *prt_last_error(void);
 
+/* Launch hint: the caller is about to run `n_fans` similar fans concurrently on different streams (e.g. a
+ * fan split into chunks whose device-to-host copies overlap the remaining chunks); affects only how small
+ * fans are spread over warps, never results.  Default 1. */
+PRT_API int prt_set_concurrency(int n_fans);
+
 /* number of visible CUDA devices (0 if none / no driver) */
 PRT_API int prt_device_count(void);
 

@@ -21,7 +21,7 @@ N_COUNTERS = 6
 DEFAULT_MAX_BOUNCES = 1 << 20
 
 EXPORTS = (
-    "prt_abi_version", "prt_last_error", "prt_device_count", "prt_env_create", "prt_ensemble_create",
+    "prt_abi_version", "prt_set_concurrency", "prt_last_error", "prt_device_count", "prt_env_create", "prt_ensemble_create",
     "prt_shoot_ensemble", "prt_env_destroy",
     "prt_env_device_bytes", "prt_shoot_fan", "prt_shoot_fan_host", "prt_pack_arrivals", "prt_count_brackets", "prt_fill_brackets",
     "prt_refine_workspace_bytes", "prt_refine_brackets", "prt_launch_count", "prt_measure_fp64_peak",
@@ -49,6 +49,8 @@ def load():
     d, i32, i64, vp = C.c_double, C.c_int32, C.c_int64, C.c_void_p
     L.prt_abi_version.restype = C.c_int
     L.prt_last_error.restype = C.c_char_p
+    L.prt_set_concurrency.restype = C.c_int
+    L.prt_set_concurrency.argtypes = [C.c_int]
     L.prt_device_count.restype = C.c_int
     L.prt_env_create.restype = C.c_int
     L.prt_env_create.argtypes = [C.c_int, i32, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, C.POINTER(vp)]

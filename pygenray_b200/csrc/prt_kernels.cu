@@ -259,8 +259,11 @@ __global__ void prt_sign_changes_kernel(int64_t n_rays, int32_t n_save, const do
 // to give every scheduler several full warps is therefore spread over MORE, partly filled warps
 // (fewer rays per warp) until the resident-warp capacity of the chip is used: latency hiding by
 // thread-level parallelism instead of idle schedulers.  Large fans use full warps.
+static std::atomic<int> g_concurrency{1};
+
 static int pick_lanes(int64_t n_units, int device)
 {
+    n_units *= g_concurrency.load();  // several fans in flight on different streams share the chip
     static int forced = -1;
     if (forced < 0) {
         const char* e = getenv("PRT_LANES");
@@ -504,6 +507,11 @@ __global__ void prt_fp64_peak_kernel(double* out, int iters, double a, double b)
 extern "C" {
 
 int prt_abi_version(void) { return PRT_ABI_VERSION; }
+int prt_set_concurrency(int n_fans)
+{
+    g_concurrency.store(n_fans > 0 ? n_fans : 1);
+    return PRT_SUCCESS;
+}
 const char* prt_last_error(void) { return g_last_error.c_str(); }
 int64_t prt_launch_count(void) { return g_launches.load(); }
 

@@ -343,6 +343,111 @@ def shoot_fan_arrays(denv, source_depth, source_range, receiver_range, angles=No
     return out
 
 
+_PIPELINE_MIN_RAYS = 4096
+_PIPELINE_CHUNKS = 8
+
+
+def _shoot_fan_pipelined(denv, source_depth, source_range, receiver_range, angles, num_range_save, rtol,
+                         terminate_backwards, max_bounces=_lib.DEFAULT_MAX_BOUNCES):
+    """Large fan with trajectories, host arrays out: the fan is cut into contiguous chunks shot concurrently on
+    separate streams, and each chunk's surviving rays are copied to the host while the slower chunks (steep,
+    reflecting rays at the ends of the fan) are still integrating.  Survivors are compacted per chunk on the
+    device and placed from the middle of the fan outwards, so the host arrays are contiguous without a
+    host-side pass.  Same result dict as ``shoot_fan_arrays(..., stored_convention=True, ray_id_counts=True,
+    compact=True)``."""
+    L = _lib.require_gpu()
+    import torch  # noqa: PLC0415
+
+    ang = _as_f64(np.atleast_1d(angles)).reshape(-1)
+    n, n_save = ang.shape[0], int(num_range_save)
+    n_chunks = max(1, min(_PIPELINE_CHUNKS, n // 1024))
+    per = -(-n // n_chunks)
+    per = -(-per // 32) * 32
+    bounds = [(a, min(a + per, n)) for a in range(0, n, per)]
+    n_chunks = len(bounds)
+    dev = torch.device("cuda", denv.device)
+    rs_np = np.linspace(source_range, receiver_range, n_save)
+
+    def ptr(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream()
+        ang_d = torch.from_numpy(ang).pin_memory().to(dev, non_blocking=True)
+        rs_d = torch.from_numpy(rs_np).to(dev)
+        traj_h = torch.empty((3, n, n_save), dtype=torch.float64, pin_memory=True)
+        final_h = torch.empty((3, n), dtype=torch.float64, pin_memory=True)
+        nb_h = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        ns_h = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        fl_h = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        chunks = []
+        L.prt_set_concurrency(n_chunks)
+        try:
+            for (a, b) in bounds:
+                m = b - a
+                st = torch.cuda.Stream(device=dev)
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    c = dict(a=a, b=b, stream=st,
+                             traj=torch.empty((3, m, n_save), dtype=torch.float64, device=dev),
+                             final=torch.empty((3, m), dtype=torch.float64, device=dev),
+                             nb=torch.empty(m, dtype=torch.int32, device=dev),
+                             ns=torch.empty(m, dtype=torch.int32, device=dev),
+                             status=torch.empty(m, dtype=torch.int32, device=dev),
+                             flips=torch.empty(m, dtype=torch.int32, device=dev))
+                    rc = L.prt_shoot_fan(
+                        denv.handle, m, C.c_void_p(ang_d.data_ptr() + 8 * a), None, float(source_depth),
+                        float(source_range), float(receiver_range), float(rtol), ATOL,
+                        int(bool(terminate_backwards)), n_save, ptr(rs_d), ptr(c["traj"]), ptr(c["final"]),
+                        ptr(c["nb"]), ptr(c["ns"]), ptr(c["status"]), None, 1, ptr(c["flips"]), int(max_bounces),
+                        C.c_void_p(st.cuda_stream))
+                    _lib.check(rc, "prt_shoot_fan")
+                chunks.append(c)
+        finally:
+            L.prt_set_concurrency(1)
+
+        # middle chunks first (they finish first), growing a contiguous block of host rows outwards
+        centre = (n_chunks - 1) / 2.0
+        order = sorted(range(n_chunks), key=lambda k: (abs(k - centre), k))
+        left = right = None
+        kept_parts = {}
+        for k in order:
+            c = chunks[k]
+            with torch.cuda.stream(c["stream"]):
+                ok = c["status"] == 0
+                idx = torch.nonzero(ok).squeeze(1)  # synchronises this chunk's stream only
+                kc = int(idx.shape[0])
+                m = c["b"] - c["a"]
+                src = {key: c[key] for key in ("traj", "final", "nb", "ns", "flips")}
+                if kc < m:
+                    src = {key: (v.index_select(1, idx) if key in ("traj", "final") else v[idx]) for key, v in src.items()}
+                if left is None:
+                    lo = c["a"]
+                    left, right = lo, lo + kc
+                elif k < centre:
+                    lo = left - kc
+                    left = lo
+                else:
+                    lo = right
+                    right = lo + kc
+                if kc:
+                    for q in range(3):  # plane by plane: each destination slice is contiguous (a strided
+                        traj_h[q, lo:lo + kc].copy_(src["traj"][q], non_blocking=True)  # D2H would be staged)
+                        final_h[q, lo:lo + kc].copy_(src["final"][q], non_blocking=True)
+                    nb_h[lo:lo + kc].copy_(src["nb"], non_blocking=True)
+                    ns_h[lo:lo + kc].copy_(src["ns"], non_blocking=True)
+                    fl_h[lo:lo + kc].copy_(src["flips"], non_blocking=True)
+                kept_parts[k] = idx.cpu().numpy() + c["a"]
+                c["keep_alive"] = src
+        for c in chunks:
+            c["stream"].synchronize()
+            main.wait_stream(c["stream"])
+    kept = np.concatenate([kept_parts[k] for k in range(n_chunks)]) if n_chunks else np.zeros(0, np.int64)
+    return dict(range_save=rs_np, traj=traj_h[:, left:right].numpy(), final=final_h[:, left:right].numpy(),
+                n_bottom=nb_h[left:right].numpy(), n_surface=ns_h[left:right].numpy(),
+                status=np.zeros(right - left, dtype=np.int32), p_sign_changes=fl_h[left:right].numpy(), kept=kept)
+
+
 _RAISING = {
     5: (ValueError, "A value in x_new is outside the interpolation range of the bottom-angle spline."),
     6: (ValueError, "f(a) and f(b) must have different signs"),
@@ -402,6 +507,10 @@ def shoot_rays(source_depth, source_range, launch_angles, receiver_range, num_ra
         internal = launch_angles
         stored = -launch_angles    # ray.launch_angle = -launch_angles[k] (launch_rays.py:180-182)
 
+    if launch_angles.shape[0] >= _PIPELINE_MIN_RAYS and num_range_save:
+        res = _shoot_fan_pipelined(denv, source_depth, src_i, rcv_i, internal, num_range_save, rtol,
+                                   terminate_backwards)
+        return _fan_from_device(res, stored, source_depth, backwards)
     res = shoot_fan_arrays(denv, source_depth, src_i, rcv_i, angles=internal, num_range_save=num_range_save,
                            rtol=rtol, terminate_backwards=terminate_backwards, stored_convention=True,
                            ray_id_counts=True, compact=not small)

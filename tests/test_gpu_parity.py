@@ -273,3 +273,22 @@ def test_sharded_fan_single_rank_and_records(pr):
     assert np.array_equal(t[:, :3], ref["final"].T, equal_nan=True)
     assert np.array_equal(t[:, 3], ref["n_bottom"]) and np.array_equal(t[:, 4], ref["n_surface"])
     assert np.array_equal(t[:, 5], ref["status"])
+
+
+def test_pipelined_large_fan_equals_single_launch(pr):
+    """shoot_rays on >= 4096 rays (chunked launches, copies overlapped, survivors placed centre-out) returns
+    exactly what one launch + device compaction returns, including dropped rays at both ends of the fan."""
+    env = make_env(cases.config2_arrays())
+    user = np.linspace(-16, 16, 5000)
+    fan = pr.shoot_rays(1000.0, 0.0, user, 300e3, 37, env, rtol=1e-9, debug=False, flatearth=False)
+    denv = pr.DeviceEnvironment(*pr._unpack_envi(env, flatearth=False))
+    ref = pr.shoot_fan_arrays(denv, 1000.0, 0.0, 300e3, angles=-user, num_range_save=37, stored_convention=True,
+                              ray_id_counts=True, compact=True)
+    assert len(fan) == ref["traj"].shape[1] < 5000  # some steep rays are dropped
+    assert np.array_equal(fan.thetas, user[ref["kept"]])
+    assert np.array_equal(fan.ts, ref["traj"][0]) and np.array_equal(fan.zs, ref["traj"][1])
+    assert np.array_equal(fan.ps, ref["traj"][2])
+    assert np.array_equal(fan.n_botts, ref["n_bottom"]) and np.array_equal(fan.n_surfs, ref["n_surface"])
+    ids = ref["p_sign_changes"] * np.sign(fan.thetas)
+    free = (fan.n_botts == 0) & (fan.n_surfs == 0)
+    assert list(fan.ray_ids[:50]) == [str(v) if f else f"{v}b" for v, f in zip(ids[:50], free[:50])]
