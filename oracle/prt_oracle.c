@@ -113,13 +113,14 @@ ORC_API double orc_pow_m02(double x)
     return (y * p2) * post;
 }
 
-/* 1/sqrt(w) for normal w > 0: integer-shift seed (3.4e-2) + 4 Newton steps y <- y (1.5 - 0.5 w y^2);
- * <= 2.3 ulp.  contract: stands for the 1/sqrt of ref:integration_processes.py:95 (see derivsrd). */
+/* 1/sqrt(w) for normal w > 0: integer-shift seed on the high word (3.4e-2) + 4 Newton steps
+ * y <- y (1.5 - 0.5 w y^2); <= 2.3 ulp.  contract: stands for the 1/sqrt of
+ * ref:integration_processes.py:95 (see derivsrd). */
 ORC_API double orc_rsqrt(double w)
 {
     uint64_t b;
     memcpy(&b, &w, 8);
-    b = 0x5FE6EB50C7B537A9ULL - (b >> 1);
+    b = (uint64_t)(uint32_t)(0x5FE6EB50u - ((uint32_t)(b >> 32) >> 1)) << 32;
     double y;
     memcpy(&y, &b, 8);
     const double hw = 0.5 * w;
@@ -131,25 +132,44 @@ ORC_API double orc_rsqrt(double w)
     return y;
 }
 
-/* x^(-1/10) for x > 0: the step controller's error_norm ** (-1/5) expressed on the MEAN SQUARE
- * x = error_norm^2 (no square root); exponent split by 10 + 3 Newton steps; <= 2 ulp. */
+/* 1/x for normal x > 0: integer seed on the high word (5e-2) + 4 Newton steps y <- y + y (1 - x y);
+ * <= 1 ulp.  contract: stands for the divisions by the error scale (scipy:rk.py:151) and by the step
+ * length (scipy:rk.py:722), whose divisors are known before their dividends. */
+ORC_API double orc_rcp(double x)
+{
+    uint64_t b;
+    memcpy(&b, &x, 8);
+    b = (uint64_t)(uint32_t)(0x7FDE6238u - (uint32_t)(b >> 32)) << 32;
+    double y;
+    memcpy(&y, &b, 8);
+    for (int it = 0; it < 4; ++it) {
+        double e = fma(-x, y, 1.0);
+        y = fma(y, e, y);
+    }
+    return y;
+}
+
+/* x^(-1/10): the step controller's error_norm ** (-1/5) expressed on the MEAN SQUARE
+ * x = error_norm^2 (no square root); exponent split by 10 + 3 Newton steps; <= 2 ulp for
+ * 2^-70 <= x < 2^70.  contract: the biased exponent is clamped to [953, 1092]; outside that range the
+ * controller's factor 0.9 x^(-1/10) is pinned at MAX_FACTOR (x -> 0) or MIN_FACTOR (x -> inf, NaN)
+ * whatever the exact power, so 0, subnormals, inf and NaN need no special case. */
 ORC_API double orc_pow_m01(double x)
 {
     static const double T[10] = {1.0, 0x1.ddb680117ab12p-1, 0x1.bdb8cdadbe120p-1, 0x1.9fdf8bcce533ep-1,
                                  0x1.8406003b2ae5cp-1, 0x1.6a09e667f3bcdp-1, 0x1.51cb453b9536cp-1,
                                  0x1.3b2c47bff8329p-1, 0x1.2611186bae674p-1, 0x1.125fbee250664p-1}; /* 2^(-r/10) */
-    if (x != x) return x;
-    if (x == INFINITY) return 0.0;
-    double post = 1.0;
-    if (x < 0x1p-1022) { x = x * 0x1p100; post = 0x1p10; }
     uint64_t b;
     memcpy(&b, &x, 8);
-    int e = (int)((b >> 52) & 0x7ff) - 1023;
+    int ef = (int)((b >> 52) & 0x7ff);
+    if (ef < 953) ef = 953;
+    if (ef > 1092) ef = 1092;
     b = (b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL;
     double m;
     memcpy(&m, &b, 8);
-    int q = (e >= 0) ? (e / 10) : -((9 - e) / 10);
-    int r = e - 10 * q;
+    unsigned eu = (unsigned)(ef + 7); /* e + 1030, e = ef - 1023 = 10 q + r */
+    unsigned q10 = eu / 10u;          /* q + 103 */
+    int r = (int)(eu - 10u * q10);
     double y = fma(fma(0.024999779689669537, m, -0.14120119176598264), m, 1.1157678629591425);
     for (int it = 0; it < 3; ++it) {
         double y2 = y * y;
@@ -160,10 +180,10 @@ ORC_API double orc_pow_m01(double x)
         y = fma(y * 0.1, res, y);
     }
     y = y * T[r];
-    uint64_t pb = (uint64_t)(1023 - q) << 52;
+    uint64_t pb = (uint64_t)(1126u - q10) << 52;
     double p2;
     memcpy(&p2, &pb, 8);
-    return (y * p2) * post;
+    return y * p2;
 }
 
 static double k_sin(double r)
@@ -308,11 +328,10 @@ static void derivsrd(const orc_env *E, double x, const double *y, double *dydx, 
     double arg = fma(-c2, pz * pz, 1.0);
     if (arg <= 0.0) arg = 1e-30;
     /* contract: fact / c^2 is formed once as u = 1 / (c^2 sqrt(arg)) = rsqrt(c^4 arg); then
-     * [fact/c, c*pz*fact, -fact*cp/c^2] = [c u, c^2 (c u) pz, -cp u] */
+     * [fact/c, c*pz*fact, -fact*cp/c^2] = [c u, (c^3 pz) u, -cp u] */
     double u = orc_rsqrt((c2 * c2) * arg);
-    double t1 = c * u;
-    dydx[0] = t1;
-    dydx[1] = (c2 * t1) * pz;
+    dydx[0] = c * u;
+    dydx[1] = ((c2 * c) * pz) * u;
     dydx[2] = (-cp) * u;
     cnt[CNT_NFEV]++;
 }
@@ -402,7 +421,7 @@ typedef struct {
 
 static void dense_eval(const dense_t *d, double t, double *y)
 {
-    double x = (t - d->t_old) * (1.0 / d->h); /* contract: division by h as a multiplication by 1/h */
+    double x = (t - d->t_old) * orc_rcp(d->h); /* contract: division by h as a multiplication by rcp(h) */
     double p1 = x, p2 = p1 * x, p3 = p2 * x, p4 = p3 * x; /* np.cumprod */
     for (int k = 0; k < 3; ++k) {
         double acc = d->Q[k][0] * p1;
@@ -487,11 +506,14 @@ static int solver_step_impl(solver_t *S)
         derivsrd(S->E, t + h, y_new, f_new, S->cnt);
         memcpy(S->K[6], f_new, sizeof f_new);
         /* error estimate */
-        double r[3];
-        for (int k = 0; k < 3; ++k) {
-            double scale = fma(np_maximum(fabs(y[k]), fabs(y_new[k])), S->rtol, S->atol);
-            r[k] = (kdot(S->K, k, RK_E, 7) * h) / scale;
-        }
+        /* contract: error / scale as a multiplication by 1/scale, the three reciprocals formed from ONE
+         * reciprocal of the product of the scales (they are known before the last stage value is) */
+        double r[3], scale[3];
+        for (int k = 0; k < 3; ++k) scale[k] = fma(np_maximum(fabs(y[k]), fabs(y_new[k])), S->rtol, S->atol);
+        double s01 = scale[0] * scale[1], s12 = scale[1] * scale[2], s02 = scale[0] * scale[2];
+        double inv3 = orc_rcp(s01 * scale[2]);
+        double inv[3] = {inv3 * s12, inv3 * s02, inv3 * s01};
+        for (int k = 0; k < 3; ++k) r[k] = (kdot(S->K, k, RK_E, 7) * h) * inv[k];
         /* contract: error_norm = sqrt(mean(r^2)) is carried as its square ms (no square root, no division):
          * accept iff ms < 1, and error_norm ** (-1/5) = ms ** (-1/10)   (scipy:rk.py:148-165) */
         double ms = r[0] * r[0];

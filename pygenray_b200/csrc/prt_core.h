@@ -30,6 +30,13 @@
 #define PRT_HD_NOINLINE
 #endif
 
+// explicit re-convergence of the lanes in `mask` (all of them must arrive); nothing to do on the host
+#if defined(__CUDA_ARCH__)
+#define PRT_CONVERGE(mask) __syncwarp(mask)
+#else
+#define PRT_CONVERGE(mask) ((void)(mask))
+#endif
+
 struct alignas(16) prt_d2 {
     double x, y;
 };
@@ -47,6 +54,9 @@ PRT_HD double prt_ld(const double* p) { return __ldg(p); }
 #define PRT_FMA(a, b, c) __fma_rn((a), (b), (c))
 PRT_HD double prt_bits_to_double(uint64_t b) { return __longlong_as_double((long long)b); }
 PRT_HD uint64_t prt_double_to_bits(double d) { return (uint64_t)__double_as_longlong(d); }
+PRT_HD uint32_t prt_hi32(double d) { return (uint32_t)__double2hiint(d); }
+PRT_HD uint32_t prt_lo32(double d) { return (uint32_t)__double2loint(d); }
+PRT_HD double prt_from_hilo(uint32_t hi, uint32_t lo) { return __hiloint2double((int)hi, (int)lo); }
 #else
 #include <string.h>
 PRT_HD prt_d2 prt_ld2(const prt_d2* p) { return *p; }
@@ -64,6 +74,9 @@ PRT_HD uint64_t prt_double_to_bits(double d)
     memcpy(&b, &d, 8);
     return b;
 }
+PRT_HD uint32_t prt_hi32(double d) { return (uint32_t)(prt_double_to_bits(d) >> 32); }
+PRT_HD uint32_t prt_lo32(double d) { return (uint32_t)prt_double_to_bits(d); }
+PRT_HD double prt_from_hilo(uint32_t hi, uint32_t lo) { return prt_bits_to_double(((uint64_t)hi << 32) | lo); }
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -103,7 +116,19 @@ struct prt_env_view {
     int64_t grid_stride;    // ensembles: nodes between consecutive realisations' grids (0 for one environment)
     int32_t n_env;          // number of realisations sharing the coordinate tables (1 for one environment)
     double r0, r_inv, z0, z_inv, b0, b_inv;  // cell-index guesses: (v - x0) * inv (any value is correct)
+    double r_off, z_off, b_off;              // -x0 * inv: the same guesses as one fma, v * inv + off
+    const prt_d2* rxr;      // [n_r-1] {rin[i], 1/(rin[i+1]-rin[i])}: all the speculative stage lookup needs per axis
+    const prt_d2* zxr;      // [n_z-1] {zin[j], 1/(zin[j+1]-zin[j])}
+    const prt_d2* bcell;    // [n_b-1] x 3 prt_d2: {lo, hi} (padded like rcell), {x[i], 1/(x[i+1]-x[i])}, {depth[i], depth[i+1]}
     double bb_zmax, bb_zmin, bb_rmin, bb_rmax;  // zin[-1]+1e-6, zin[0]-1e-6, rin[0]-1e-6, rin[-1]+1e-6
+};
+
+// One ray's environment: the shared tables plus this ray's sound-speed grid (ensembles: one grid per
+// realisation behind one set of tables).  The tables are referenced, never copied, so that on the device
+// every field is read straight from the kernel's __grid_constant__ parameter.
+struct prt_envp {
+    const prt_env_view& v;
+    const prt_d2* grid;
 };
 
 // np.nextafter(t, +inf) (scipy rk.py:119) by integer increment of the bit pattern
@@ -188,32 +213,19 @@ PRT_HD double prt_pow_m02(double x)
 }
 
 // x^(-1/10): the controller's error_norm ** (-1/5) on the mean square x = error_norm^2 (no sqrt).
-PRT_HD_NOINLINE double prt_pow_m01_special(double x, double& post)
-{
-    post = 1.0;
-    if (x != x) return x;
-    if (x == (double)INFINITY) return x;
-    if (x < 0x1p-1022) {
-        post = 0x1p10;
-        return x * 0x1p100;
-    }
-    return x;
-}
-
+// Branch-free: the biased exponent is clamped to [953, 1092] (2^-70 <= x < 2^70), outside of which the
+// step-size factor 0.9 x^(-1/10) is pinned at its limits anyway (0 and subnormals -> >= 119 -> MAX_FACTOR;
+// huge, inf and NaN bit patterns -> <= 2^-7 -> MIN_FACTOR), so no value of x needs a special case.
 PRT_HD double prt_pow_m01(double x)
 {
-    double post = 1.0;
-    if (!(x >= 0x1p-1022 && x < (double)INFINITY)) {
-        x = prt_pow_m01_special(x, post);
-        if (x != x) return x;
-        if (x == (double)INFINITY) return 0.0;
-    }
-    const uint64_t b = prt_double_to_bits(x);
-    const int e = (int)((b >> 52) & 0x7ff) - 1023;
-    const double m = prt_bits_to_double((b & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
-    const unsigned eu = (unsigned)(e + 1030);  // e = 10 q + r, r in 0..9 (floor division, kept unsigned)
-    const int q = (int)(eu / 10u) - 103;
-    const int r = (int)(eu - 10u * (eu / 10u));
+    const uint32_t hi = prt_hi32(x);
+    int ef = (int)((hi >> 20) & 0x7ffu);
+    ef = ef < 953 ? 953 : ef;
+    ef = ef > 1092 ? 1092 : ef;
+    const double m = prt_from_hilo((hi & 0x000fffffu) | 0x3ff00000u, prt_lo32(x));
+    const unsigned eu = (unsigned)(ef + 7);  // e + 1030 with e = ef - 1023 = 10 q + r, r in 0..9
+    const unsigned q10 = eu / 10u;           // q + 103
+    const int r = (int)(eu - 10u * q10);
     double y = PRT_FMA(PRT_FMA(0.024999779689669537, m, -0.14120119176598264), m, 1.1157678629591425);
 #pragma unroll
     for (int it = 0; it < 3; ++it) {
@@ -225,20 +237,33 @@ PRT_HD double prt_pow_m01(double x)
         y = PRT_FMA(y * 0.1, res, y);
     }
     y = y * PRT_POW10_TAB(r);  // 2^(-r/10)
-    const double p2 = prt_bits_to_double((uint64_t)(1023 - q) << 52);
-    return (y * p2) * post;
+    return y * prt_from_hilo((uint32_t)(1126u - q10) << 20, 0u);  // 2^(-q)
 }
 
-// 1/sqrt(w), normal w > 0: integer-shift seed + 4 Newton steps (<= 2.3 ulp); see oracle orc_rsqrt
+// 1/sqrt(w), normal w > 0: integer-shift seed on the high word + 4 Newton steps (<= 2.3 ulp); see oracle orc_rsqrt
 PRT_HD double prt_rsqrt(double w)
 {
-    double y = prt_bits_to_double(0x5FE6EB50C7B537A9ULL - (prt_double_to_bits(w) >> 1));
+    double y = prt_from_hilo(0x5FE6EB50u - (prt_hi32(w) >> 1), 0u);
     const double hw = 0.5 * w;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const double t = y * y;
         const double r = PRT_FMA(-hw, t, 1.5);
         y = y * r;
+    }
+    return y;
+}
+
+// 1/x, normal x > 0: integer seed on the high word (5 %) + 4 Newton steps (<= 1 ulp); see oracle orc_rcp.
+// Used where the reference divides by a quantity that is known before the dividend is (error scales, step
+// length): the reciprocal is formed off the critical path and the division becomes a multiplication.
+PRT_HD double prt_rcp(double x)
+{
+    double y = prt_from_hilo(0x7FDE6238u - prt_hi32(x), 0u);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const double e = PRT_FMA(-x, y, 1.0);
+        y = PRT_FMA(y, e, y);
     }
     return y;
 }
@@ -374,82 +399,151 @@ PRT_HD int prt_locate(const prt_d2* pair, int n, double x0, double inv, double v
 // c(x, z) and dc/dz(x, z): bilinear_interp (integration_processes.py:101-174) evaluated ONCE for
 // both fields (the reference evaluates it twice with identical weights, :86-87).  The weight
 // divisions use the per-cell reciprocals 1/(x[i+1]-x[i]) tabulated at staging time; the four-weight
-// sum is regrouped as lerps (contract, mirrored in the oracle).
-#if defined(PRT_FIELD_NOINLINE)
-PRT_HD_NOINLINE
-#else
-PRT_HD
-#endif
-void prt_field(const prt_env_view& E, double x, double z, double& c, double& cz)
+// sum is regrouped as lerps (contract, mirrored in the oracle):
+//   l0 = v00 + wy (v01 - v00),  l1 = v10 + wy (v11 - v10),  v = l0 + wx (l1 - l0)
+PRT_HD void prt_bilerp(const prt_d2& v00, const prt_d2& v01, const prt_d2& v10, const prt_d2& v11, double wx,
+                       double wy, double& c, double& cz)
 {
-    // Speculate on the guessed cell: every load (cell records and the four corner nodes) is issued from the
-    // guessed indices at once, so the lookup costs ONE cache round trip; the guesses are verified afterwards
-    // (two compares per axis against edges padded with -inf / +inf at the grid ends, false for NaN) and the
-    // rare miss (cell-boundary rounding, non-uniform grids) takes the general lookup.
-    const int mr = E.n_r - 2, mz = E.n_z - 2;
-    int i = PRT_D2I((x - E.r0) * E.r_inv);
-    int j = PRT_D2I((z - E.z0) * E.z_inv);
-    i = i < 0 ? 0 : i; i = i > mr ? mr : i;
-    j = j < 0 ? 0 : j; j = j > mz ? mz : j;
-    const prt_d2* rc = E.rcell + 2 * (unsigned)i;
-    const prt_d2* zc = E.zcell + 2 * (unsigned)j;
-    const prt_d2 rv = prt_ld2(rc), ra = prt_ld2(rc + 1);
-    const prt_d2 zv = prt_ld2(zc), za = prt_ld2(zc + 1);
-    const prt_d2* g = E.grid + ((unsigned)i * (unsigned)E.n_z + (unsigned)j);
-    prt_d2 v00 = prt_ld2(g);
-    prt_d2 v01 = prt_ld2(g + 1);
-    prt_d2 v10 = prt_ld2(g + E.n_z);
-    prt_d2 v11 = prt_ld2(g + E.n_z + 1);
-    double wx, wy;
-    if ((rv.x < x) & (x <= rv.y) & (zv.x < z) & (z <= zv.y)) {
-        wx = (x - ra.x) * ra.y;
-        wy = (z - za.x) * za.y;
-    } else {
-        prt_d2 re, ze;
-        i = prt_locate(E.rpair, E.n_r, E.r0, E.r_inv, x, re);
-        j = prt_locate(E.zpair, E.n_z, E.z0, E.z_inv, z, ze);
-        g = E.grid + ((unsigned)i * (unsigned)E.n_z + (unsigned)j);
-        v00 = prt_ld2(g);
-        v01 = prt_ld2(g + 1);
-        v10 = prt_ld2(g + E.n_z);
-        v11 = prt_ld2(g + E.n_z + 1);
-        wx = (x - re.x) * prt_ld(E.rrecip + i);
-        wy = (z - ze.x) * prt_ld(E.zrecip + j);
-    }
-    // bilinear interpolation as two depth lerps and one range lerp (dependent depth 3 after the weights):
-    //   l0 = v00 + wy (v01 - v00),  l1 = v10 + wy (v11 - v10),  v = l0 + wx (l1 - l0)
-    // == the reference's (1-wx)(1-wy) v00 + wx (1-wy) v10 + (1-wx) wy v01 + wx wy v11, regrouped
     const double c0 = PRT_FMA(wy, v01.x - v00.x, v00.x), c1 = PRT_FMA(wy, v11.x - v10.x, v10.x);
     const double d0 = PRT_FMA(wy, v01.y - v00.y, v00.y), d1 = PRT_FMA(wy, v11.y - v10.y, v10.y);
     c = PRT_FMA(wx, c1 - c0, c0);
     cz = PRT_FMA(wx, d1 - d0, d0);
 }
 
-// bottom depth at x: linear_interp (integration_processes.py:177-235)
-PRT_HD double prt_bathy(const prt_env_view& E, double x)
+// guessed cell of v: trunc(v * inv + off) folded into [0, m] (negative and NaN guesses land on a valid cell;
+// any cell is a correct GUESS)
+PRT_HD unsigned prt_guess(double v, double inv, double off, int m)
 {
-    prt_d2 xe;
-    int i = prt_locate(E.bxpair, E.n_b, E.b0, E.b_inv, x, xe);
-    prt_d2 v = prt_ld2(E.bvpair + i);
-    double w = (x - xe.x) * prt_ld(E.brecip + i);
+    const unsigned g = (unsigned)PRT_D2I(PRT_FMA(v, inv, off));
+    return g > (unsigned)m ? (unsigned)m : g;
+}
+
+// Exact lookup, one cache round trip in the common case: every load (cell records and the four corner
+// nodes) is issued from the guessed indices at once; the guesses are verified afterwards (two compares per
+// axis against edges padded with -inf / +inf at the grid ends, false for NaN) and the rare miss
+// (cell-boundary rounding, non-uniform grids) takes the general lookup.
+PRT_HD void prt_field(const prt_envp& E, double x, double z, double& c, double& cz)
+{
+    const prt_env_view& V = E.v;
+    unsigned i = prt_guess(x, V.r_inv, V.r_off, V.n_r - 2);
+    unsigned j = prt_guess(z, V.z_inv, V.z_off, V.n_z - 2);
+    const prt_d2* rc = V.rcell + 2 * i;
+    const prt_d2* zc = V.zcell + 2 * j;
+    const prt_d2 rv = prt_ld2(rc), ra = prt_ld2(rc + 1);
+    const prt_d2 zv = prt_ld2(zc), za = prt_ld2(zc + 1);
+    const prt_d2* g = E.grid + (i * (unsigned)V.n_z + j);
+    prt_d2 v00 = prt_ld2(g);
+    prt_d2 v01 = prt_ld2(g + 1);
+    prt_d2 v10 = prt_ld2(g + V.n_z);
+    prt_d2 v11 = prt_ld2(g + V.n_z + 1);
+    double wx, wy;
+    if ((rv.x < x) & (x <= rv.y) & (zv.x < z) & (z <= zv.y)) {
+        wx = (x - ra.x) * ra.y;
+        wy = (z - za.x) * za.y;
+    } else {
+        prt_d2 re, ze;
+        i = (unsigned)prt_locate(V.rpair, V.n_r, V.r0, V.r_inv, x, re);
+        j = (unsigned)prt_locate(V.zpair, V.n_z, V.z0, V.z_inv, z, ze);
+        g = E.grid + (i * (unsigned)V.n_z + j);
+        v00 = prt_ld2(g);
+        v01 = prt_ld2(g + 1);
+        v10 = prt_ld2(g + V.n_z);
+        v11 = prt_ld2(g + V.n_z + 1);
+        wx = (x - re.x) * prt_ld(V.rrecip + i);
+        wy = (z - ze.x) * prt_ld(V.zrecip + j);
+    }
+    prt_bilerp(v00, v01, v10, v11, wx, wy, c, cz);
+}
+
+// Speculative lookup for the Runge-Kutta stages: the same arithmetic from the guessed cell, but NO branch
+// and no extra load -- the guess is checked on the interpolation weight itself: w = (v - x[i]) / (x[i+1] - x[i])
+// is computed from the true edge and width of cell i, so PRT_W_LO < w < PRT_W_HI proves x[i] < v < x[i+1]
+// (the 1e-6 margins dwarf the 4e-16 rounding of w), i.e. that i IS searchsorted(v) - 1.  `ok` collects the
+// proofs and the caller re-runs the whole step attempt through the exact lookup when any of them failed
+// (prt_ray::attempt): abscissae within 1e-6 of a node or outside the grid, and wrong guesses on non-uniform
+// grids.  The stage code of an attempt is thus one branch-free block that the scheduler is free to
+// interleave across stages.
+#define PRT_W_LO 0x1p-20
+#define PRT_W_HI (1.0 - 0x1p-20)
+struct prt_xcell {
+    const prt_d2* row;  // &grid[i][0]
+    double wx;
+};
+
+PRT_HD prt_xcell prt_xlook(const prt_envp& E, double x, bool& ok)
+{
+    const prt_env_view& V = E.v;
+    const unsigned i = prt_guess(x, V.r_inv, V.r_off, V.n_r - 2);
+    const prt_d2 ra = prt_ld2(V.rxr + i);
+    prt_xcell xc;
+    xc.row = E.grid + i * (unsigned)V.n_z;
+    xc.wx = (x - ra.x) * ra.y;
+    ok = ok & (xc.wx > PRT_W_LO) & (xc.wx < PRT_W_HI);
+    return xc;
+}
+
+PRT_HD void prt_field_spec(const prt_envp& E, const prt_xcell& xc, double z, double& c, double& cz, bool& ok)
+{
+    const prt_env_view& V = E.v;
+    const unsigned j = prt_guess(z, V.z_inv, V.z_off, V.n_z - 2);
+    const prt_d2* g = xc.row + j;
+    const prt_d2 za = prt_ld2(V.zxr + j);
+    const prt_d2 v00 = prt_ld2(g), v01 = prt_ld2(g + 1), v10 = prt_ld2(g + V.n_z), v11 = prt_ld2(g + V.n_z + 1);
+    const double wy = (z - za.x) * za.y;
+    ok = ok & (wy > PRT_W_LO) & (wy < PRT_W_HI);
+    prt_bilerp(v00, v01, v10, v11, xc.wx, wy, c, cz);
+}
+
+// bottom depth at x: linear_interp (integration_processes.py:177-235); same guess / verify scheme, one
+// record {padded edges, x[i] and reciprocal, depth[i] and depth[i+1]} per bathymetry cell
+PRT_HD double prt_bathy(const prt_envp& E, double x)
+{
+    const prt_env_view& V = E.v;
+    const unsigned g = prt_guess(x, V.b_inv, V.b_off, V.n_b - 2);
+    const prt_d2* bc = V.bcell + 3 * g;
+    const prt_d2 e = prt_ld2(bc), a = prt_ld2(bc + 1);
+    prt_d2 v = prt_ld2(bc + 2);
+    double w = (x - a.x) * a.y;
+    if (!((e.x < x) & (x <= e.y))) {
+        prt_d2 xe;
+        const int i = prt_locate(V.bxpair, V.n_b, V.b0, V.b_inv, x, xe);
+        v = prt_ld2(V.bvpair + i);
+        w = (x - xe.x) * prt_ld(V.brecip + i);
+    }
     return PRT_FMA(w, v.y, (1.0 - w) * v.x);
 }
 
-// derivsrd (integration_processes.py:26-98) with a single reciprocal square root:
-//   u = 1 / (c^2 sqrt(arg)) = rsqrt(c^4 arg);  dT = c u;  dz = c^2 dT p;  dp = -cz u     (also returns c)
-PRT_HD void prt_rhs(const prt_env_view& E, double x, double z, double p, double& dT, double& dz, double& dp,
+// derivsrd (integration_processes.py:26-98) from c and dc/dz, with a single reciprocal square root:
+//   u = 1 / (c^2 sqrt(arg)) = rsqrt(c^4 arg);  [dT, dz, dp] = [c u, (c^3 p) u, -cz u]
+// (every output is ONE multiplication after u; c^3 p is formed while the Newton iteration runs)
+PRT_HD void prt_rhs_tail(double c, double cz, double p, double& dT, double& dz, double& dp)
+{
+    const double c2 = c * c;
+    const double arg = PRT_FMA(-c2, p * p, 1.0);
+    const double c4 = c2 * c2;
+    const double w = (arg <= 0.0) ? c4 * 1e-30 : c4 * arg;  // "if arg <= 0: arg = 1e-30"
+    const double c3p = (c2 * c) * p;
+    const double u = prt_rsqrt(w);
+    dT = c * u;
+    dz = c3p * u;
+    dp = (-cz) * u;
+}
+
+PRT_HD void prt_rhs(const prt_envp& E, double x, double z, double p, double& dT, double& dz, double& dp,
                     double& c_out)
 {
     double c, cz;
     prt_field(E, x, z, c, cz);
-    double c2 = c * c;
-    double arg = PRT_FMA(-c2, p * p, 1.0);
-    if (arg <= 0.0) arg = 1e-30;
-    double u = prt_rsqrt((c2 * c2) * arg);
-    double t1 = c * u;
-    dT = t1;
-    dz = (c2 * t1) * p;
-    dp = (-cz) * u;
+    prt_rhs_tail(c, cz, p, dT, dz, dp);
+    c_out = c;
+}
+
+PRT_HD void prt_rhs_spec(const prt_envp& E, const prt_xcell& xc, double z, double p, double& dT, double& dz,
+                         double& dp, double& c_out, bool& ok)
+{
+    double c, cz;
+    prt_field_spec(E, xc, z, c, cz, ok);
+    prt_rhs_tail(c, cz, p, dT, dz, dp);
     c_out = c;
 }
 
@@ -470,23 +564,21 @@ PRT_HD bool prt_ev_vertical(double pc)
     return fabs(prt_asin(pc) * PRT_RAD2DEG) > (90.0 - 1e-3);
 }
 
-PRT_HD int prt_events(const prt_env_view& E, double x, double z, double p, double c)
+PRT_HD int prt_events(const prt_envp& E, double x, double z, double p, double c)
 {
     double pc = p * c;
     int m = 0;
     if ((z < 0.0) && (pc < 0.0) && (pc >= -1.0)) m |= PRT_EV_SURFACE;
-    if ((pc > 0.0) && (pc <= 1.0)) {
-        if (z > prt_bathy(E, x)) m |= PRT_EV_BOTTOM;
-    }
+    if ((pc > 0.0) & (pc <= 1.0) & (z > prt_bathy(E, x))) m |= PRT_EV_BOTTOM;  // bathymetry looked up unconditionally
     if (prt_ev_vertical(pc)) m |= PRT_EV_VERTICAL;
-    if ((z > E.bb_zmax) | (z < E.bb_zmin) | (x < E.bb_rmin) | (x > E.bb_rmax)) m |= PRT_EV_BBOX;
+    if ((z > E.v.bb_zmax) | (z < E.v.bb_zmin) | (x < E.v.bb_rmin) | (x > E.v.bb_rmax)) m |= PRT_EV_BBOX;
     return m;
 }
 
 // single event evaluated on demand (inside the root search)
-PRT_HD bool prt_event_one(const prt_env_view& E, int which, double x, double z, double p)
+PRT_HD bool prt_event_one(const prt_envp& E, int which, double x, double z, double p)
 {
-    if (which == 3) return (z > E.bb_zmax) | (z < E.bb_zmin) | (x < E.bb_rmin) | (x > E.bb_rmax);
+    if (which == 3) return (z > E.v.bb_zmax) | (z < E.v.bb_zmin) | (x < E.v.bb_rmin) | (x > E.v.bb_rmax);
     if (which == 0 && !(z < 0.0)) return false;
     double c, cz;
     prt_field(E, x, z, c, cz);
@@ -690,7 +782,7 @@ PRT_HD double prt_bottom_angle(const prt_env_view& E, double x, bool& oob)
 }
 
 // y0 = [0, z_src, sin(radians(angle)) / c(src)]  (launch_rays.py:140-144, 284-285)
-PRT_HD void prt_initial_state(const prt_env_view& E, double source_depth, double source_range, double angle_deg,
+PRT_HD void prt_initial_state(const prt_envp& E, double source_depth, double source_range, double angle_deg,
                               double& T, double& z, double& p)
 {
     double c, cz;
@@ -746,6 +838,102 @@ struct prt_shot {
 };
 
 // ---------------------------------------------------------------------------------------------
+// One trial step of RK45: rk_step (scipy rk.py:14-71) + the error estimate and the controller power of
+// _step_impl (rk.py:148-165).  Everything the accept / reject decision and an accepted step need.
+struct prt_try {
+    double k3T, k3z, k3p, k4T, k4z, k4p, k5T, k5z, k5p, k6T, k6z, k6p, k7T, k7z, k7p;  // stage values (k7 = f_new)
+    double nT, nz, np_;  // y_new
+    double c_new;        // sound speed at (t + h, y_new), by-product of the FSAL stage
+    double ms;           // mean square of the scaled error = error_norm^2
+    double pw;           // ms^(-1/10) = error_norm^(-1/5)
+};
+
+// EXACT = false: speculative cell lookups, no branch anywhere; `ok` tells whether every guess was right.
+// EXACT = true : the general lookup (prt_field) in every stage; same arithmetic, hence the same bits
+//                whenever the speculative version reports ok.
+template <bool EXACT>
+PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, double hh, double T, double z,
+                       double p, double f0, double f1, double f2, prt_try& v, bool& ok)
+{
+    double k2T, k2z, k2p, cc, a, b;
+    (void)k2T;
+#define PRT_STAGE(xs, zs, ps, kT, kz, kp, cout)                                  \
+    do {                                                                         \
+        if (EXACT) {                                                             \
+            prt_rhs(E, (xs), (zs), (ps), kT, kz, kp, cout);                      \
+        } else {                                                                 \
+            const prt_xcell xc_ = prt_xlook(E, (xs), ok);                        \
+            prt_rhs_spec(E, xc_, (zs), (ps), kT, kz, kp, cout, ok);              \
+        }                                                                        \
+    } while (0)
+    PRT_STAGE(PRT_FMA(C2, hh, t), PRT_FMA(hh, A21 * f1, z), PRT_FMA(hh, A21 * f2, p), k2T, k2z, k2p, cc);
+    a = A31 * f1; a = PRT_FMA(A32, k2z, a);
+    b = A31 * f2; b = PRT_FMA(A32, k2p, b);
+    PRT_STAGE(PRT_FMA(C3, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), v.k3T, v.k3z, v.k3p, cc);
+    a = A41 * f1; a = PRT_FMA(A42, k2z, a); a = PRT_FMA(A43, v.k3z, a);
+    b = A41 * f2; b = PRT_FMA(A42, k2p, b); b = PRT_FMA(A43, v.k3p, b);
+    PRT_STAGE(PRT_FMA(C4, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), v.k4T, v.k4z, v.k4p, cc);
+    a = A51 * f1; a = PRT_FMA(A52, k2z, a); a = PRT_FMA(A53, v.k3z, a); a = PRT_FMA(A54, v.k4z, a);
+    b = A51 * f2; b = PRT_FMA(A52, k2p, b); b = PRT_FMA(A53, v.k3p, b); b = PRT_FMA(A54, v.k4p, b);
+    PRT_STAGE(PRT_FMA(C5, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), v.k5T, v.k5z, v.k5p, cc);
+    a = A61 * f1; a = PRT_FMA(A62, k2z, a); a = PRT_FMA(A63, v.k3z, a); a = PRT_FMA(A64, v.k4z, a); a = PRT_FMA(A65, v.k5z, a);
+    b = A61 * f2; b = PRT_FMA(A62, k2p, b); b = PRT_FMA(A63, v.k3p, b); b = PRT_FMA(A64, v.k4p, b); b = PRT_FMA(A65, v.k5p, b);
+    // stages 6 and 7 (FSAL) share the abscissa t + h, hence the range cell and its weight
+    const double x6 = t + hh;
+    prt_xcell xc6;
+    if (!EXACT) xc6 = prt_xlook(E, x6, ok);
+    if (EXACT) prt_rhs(E, x6, PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), v.k6T, v.k6z, v.k6p, cc);
+    else prt_rhs_spec(E, xc6, PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), v.k6T, v.k6z, v.k6p, cc, ok);
+    double sT = B1 * f0; sT = PRT_FMA(B3, v.k3T, sT); sT = PRT_FMA(B4, v.k4T, sT); sT = PRT_FMA(B5, v.k5T, sT); sT = PRT_FMA(B6, v.k6T, sT);
+    double sz = B1 * f1; sz = PRT_FMA(B3, v.k3z, sz); sz = PRT_FMA(B4, v.k4z, sz); sz = PRT_FMA(B5, v.k5z, sz); sz = PRT_FMA(B6, v.k6z, sz);
+    double sp = B1 * f2; sp = PRT_FMA(B3, v.k3p, sp); sp = PRT_FMA(B4, v.k4p, sp); sp = PRT_FMA(B5, v.k5p, sp); sp = PRT_FMA(B6, v.k6p, sp);
+    v.nT = PRT_FMA(hh, sT, T); v.nz = PRT_FMA(hh, sz, z); v.np_ = PRT_FMA(hh, sp, p);
+    // error scales and their reciprocals (rk.py:148-152): known before the last stage, so the three
+    // divisions of the reference become one reciprocal (of the product) formed in the shadow of that stage
+    const double scT = PRT_FMA(prt_np_maximum(fabs(T), fabs(v.nT)), rtol, atol);
+    const double scz = PRT_FMA(prt_np_maximum(fabs(z), fabs(v.nz)), rtol, atol);
+    const double scp = PRT_FMA(prt_np_maximum(fabs(p), fabs(v.np_)), rtol, atol);
+    const double sTz = scT * scz, szp = scz * scp, sTp = scT * scp;
+    const double inv3 = prt_rcp(sTz * scp);
+    const double iT = inv3 * szp, iz = inv3 * sTp, ip = inv3 * sTz;
+    double eT = E1 * f0; eT = PRT_FMA(E3, v.k3T, eT); eT = PRT_FMA(E4, v.k4T, eT); eT = PRT_FMA(E5, v.k5T, eT); eT = PRT_FMA(E6, v.k6T, eT);
+    double ez = E1 * f1; ez = PRT_FMA(E3, v.k3z, ez); ez = PRT_FMA(E4, v.k4z, ez); ez = PRT_FMA(E5, v.k5z, ez); ez = PRT_FMA(E6, v.k6z, ez);
+    double ep = E1 * f2; ep = PRT_FMA(E3, v.k3p, ep); ep = PRT_FMA(E4, v.k4p, ep); ep = PRT_FMA(E5, v.k5p, ep); ep = PRT_FMA(E6, v.k6p, ep);
+    if (EXACT) prt_rhs(E, x6, v.nz, v.np_, v.k7T, v.k7z, v.k7p, v.c_new);  // f_new (FSAL)
+    else prt_rhs_spec(E, xc6, v.nz, v.np_, v.k7T, v.k7z, v.k7p, v.c_new, ok);
+#undef PRT_STAGE
+    eT = PRT_FMA(E7, v.k7T, eT); ez = PRT_FMA(E7, v.k7z, ez); ep = PRT_FMA(E7, v.k7p, ep);
+    // error_norm carried as its square (mean square of the scaled error): accept iff ms < 1 and
+    // error_norm ** (-1/5) = ms ** (-1/10)  -- no square root, no division by sqrt(3) (rk.py:148-165)
+    const double r0 = (eT * hh) * iT, r1 = (ez * hh) * iz, r2 = (ep * hh) * ip;
+    double ms = r0 * r0;
+    ms = PRT_FMA(r1, r1, ms);
+    ms = PRT_FMA(r2, r2, ms);
+    ms = ms * 0x1.5555555555555p-2;
+    v.ms = ms;
+    v.pw = prt_pow_m01(ms);
+}
+
+#if defined(PRT_COUNT_COLD) && defined(__CUDACC__)
+__device__ unsigned long long prt_dbg_cold;
+#endif
+// cold path of prt_ray::attempt: the same trial step through the general cell lookup
+PRT_HD_NOINLINE void prt_rk_try_exact(const prt_env_view* V, const prt_d2* grid, double rtol, double atol, double t,
+                                      double hh, double T, double z, double p, double f0, double f1, double f2,
+                                      prt_try* out)
+{
+    const prt_envp E{*V, grid};
+    bool ok = true;
+#if defined(PRT_COUNT_COLD) && !defined(__CUDACC__)
+    extern long long prt_cold_count;
+    ++prt_cold_count;
+#elif defined(PRT_COUNT_COLD) && defined(__CUDA_ARCH__)
+    atomicAdd(&prt_dbg_cold, 1ULL);
+#endif
+    prt_rk_try<true>(E, rtol, atol, t, hh, T, z, p, f0, f1, f2, *out, ok);
+}
+
+// ---------------------------------------------------------------------------------------------
 // One ray as a small state machine.  The same per-ray arithmetic is driven either ray by ray
 // (prt_integrate_ray, used for host-side parity tests) or warp-synchronously (prt_integrate_warp
 // in prt_kernels.cu), where lanes always execute step attempts together and lanes that hit a
@@ -785,7 +973,7 @@ struct prt_ray {
     }
 
     // RK45.__init__ (rk.py:85-103) + select_initial_step (common.py:68-134) + g = [st.event(t0, y0)]
-    PRT_HD void seg_init(const prt_env_view& E, const prt_shot& S)
+    PRT_HD void seg_init(const prt_envp& E, const prt_shot& S)
     {
         ++c_seg;
         double c_here;
@@ -811,131 +999,58 @@ struct prt_ray {
     }
 
     // One attempt of _step_impl (rk.py:111-176).  Returns true when the step was accepted; then the
-    // step record (st.t_old .. st.nf2, events, dense output if needed) is filled in.
-    PRT_HD bool attempt(const prt_env_view& E, const prt_shot& S, prt_step& st)
+    // step record (st.t_old .. st.nf2, events, dense output if needed) is filled in.  `lanes` = the lanes
+    // of the warp that make this attempt together (device only): the prologue is select-only and the lanes
+    // are re-converged explicitly before the trial step, so that its ~700 instructions are never executed
+    // once per divergent sub-group.
+    PRT_HD bool attempt(const prt_envp& E, const prt_shot& S, prt_step& st, unsigned lanes = 0xffffffffu)
     {
         const double min_step = 10.0 * fabs(prt_next_up(t) - t);
-        if (rejected) {
-            if (h_abs < min_step) {  // TOO_SMALL_STEP -> solve_ivp status -1
-                status = PRT_RAY_STEP_TOO_SMALL;
-                phase = PRT_PH_DONE;
-                return false;
-            }
-        } else if (h_abs < min_step) {
-            h_abs = min_step;
+        // TOO_SMALL_STEP -> solve_ivp status -1 (only after a rejection; before the first trial of a step
+        // h_abs is raised to min_step instead, rk.py:118-124)
+        const bool too_small = rejected & (h_abs < min_step);
+        const double h_try = (h_abs < min_step) ? min_step : h_abs;
+        double tn = t + h_try;
+        tn = (tn - S.x_end > 0.0) ? S.x_end : tn;
+        const double hh = tn - t;
+        PRT_CONVERGE(lanes);
+        if (too_small) {
+            status = PRT_RAY_STEP_TOO_SMALL;
+            phase = PRT_PH_DONE;
+            return false;
         }
         ++c_att;
-        double tn = t + h_abs;
-        if (tn - S.x_end > 0.0) tn = S.x_end;
-        const double hh = tn - t;
         h_abs = fabs(hh);
-#if defined(PRT_ROLL_STAGES)
-        // rk_step (rk.py:14-71).  The six stage evaluations share ONE copy of the right-hand side: a
-        // rolled loop whose body switches on the stage number (warp-uniform, so no divergence) keeps
-        // the hot loop inside the instruction cache; the stage values stay in named registers.
-        double k2z = 0, k2p = 0, k3T = 0, k3z = 0, k3p = 0, k4T = 0, k4z = 0, k4p = 0, k5T = 0, k5z = 0, k5p = 0;
-        double k6T = 0, k6z = 0, k6p = 0, k7T = 0, k7z = 0, k7p = 0, c_new = 0;
-        double nT = 0, nz = 0, np_ = 0;
-#pragma unroll 1
-        for (int s = 2; s <= 7; ++s) {
-            double xs, a, b;
-            switch (s) {
-            case 2:
-                xs = PRT_FMA(C2, hh, t);
-                a = A21 * f1;
-                b = A21 * f2;
-                break;
-            case 3:
-                xs = PRT_FMA(C3, hh, t);
-                a = A31 * f1; a = PRT_FMA(A32, k2z, a);
-                b = A31 * f2; b = PRT_FMA(A32, k2p, b);
-                break;
-            case 4:
-                xs = PRT_FMA(C4, hh, t);
-                a = A41 * f1; a = PRT_FMA(A42, k2z, a); a = PRT_FMA(A43, k3z, a);
-                b = A41 * f2; b = PRT_FMA(A42, k2p, b); b = PRT_FMA(A43, k3p, b);
-                break;
-            case 5:
-                xs = PRT_FMA(C5, hh, t);
-                a = A51 * f1; a = PRT_FMA(A52, k2z, a); a = PRT_FMA(A53, k3z, a); a = PRT_FMA(A54, k4z, a);
-                b = A51 * f2; b = PRT_FMA(A52, k2p, b); b = PRT_FMA(A53, k3p, b); b = PRT_FMA(A54, k4p, b);
-                break;
-            case 6:
-                xs = t + hh;
-                a = A61 * f1; a = PRT_FMA(A62, k2z, a); a = PRT_FMA(A63, k3z, a); a = PRT_FMA(A64, k4z, a); a = PRT_FMA(A65, k5z, a);
-                b = A61 * f2; b = PRT_FMA(A62, k2p, b); b = PRT_FMA(A63, k3p, b); b = PRT_FMA(A64, k4p, b); b = PRT_FMA(A65, k5p, b);
-                break;
-            default: {  // 7: y_new, then f_new (FSAL)
-                xs = t + hh;
-                double sT = B1 * f0; sT = PRT_FMA(B3, k3T, sT); sT = PRT_FMA(B4, k4T, sT); sT = PRT_FMA(B5, k5T, sT); sT = PRT_FMA(B6, k6T, sT);
-                a = B1 * f1; a = PRT_FMA(B3, k3z, a); a = PRT_FMA(B4, k4z, a); a = PRT_FMA(B5, k5z, a); a = PRT_FMA(B6, k6z, a);
-                b = B1 * f2; b = PRT_FMA(B3, k3p, b); b = PRT_FMA(B4, k4p, b); b = PRT_FMA(B5, k5p, b); b = PRT_FMA(B6, k6p, b);
-                nT = PRT_FMA(hh, sT, T);
-                break;
-            }
-            }
-            const double zs = PRT_FMA(hh, a, z), ps = PRT_FMA(hh, b, p);
-            double dT, dz, dp, cc;
-            prt_rhs(E, xs, zs, ps, dT, dz, dp, cc);
-            switch (s) {
-            case 2: k2z = dz; k2p = dp; break;
-            case 3: k3T = dT; k3z = dz; k3p = dp; break;
-            case 4: k4T = dT; k4z = dz; k4p = dp; break;
-            case 5: k5T = dT; k5z = dz; k5p = dp; break;
-            case 6: k6T = dT; k6z = dz; k6p = dp; break;
-            default: k7T = dT; k7z = dz; k7p = dp; c_new = cc; nz = zs; np_ = ps; break;
-            }
-        }
-#else
-        // rk_step (rk.py:14-71), fully unrolled: six inlined right-hand sides
-        double k2T, k2z, k2p, k3T, k3z, k3p, k4T, k4z, k4p, k5T, k5z, k5p, k6T, k6z, k6p, k7T, k7z, k7p, cc, c_new;
-        double a, b;
-        prt_rhs(E, PRT_FMA(C2, hh, t), PRT_FMA(hh, A21 * f1, z), PRT_FMA(hh, A21 * f2, p), k2T, k2z, k2p, cc);
-        a = A31 * f1; a = PRT_FMA(A32, k2z, a);
-        b = A31 * f2; b = PRT_FMA(A32, k2p, b);
-        prt_rhs(E, PRT_FMA(C3, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), k3T, k3z, k3p, cc);
-        a = A41 * f1; a = PRT_FMA(A42, k2z, a); a = PRT_FMA(A43, k3z, a);
-        b = A41 * f2; b = PRT_FMA(A42, k2p, b); b = PRT_FMA(A43, k3p, b);
-        prt_rhs(E, PRT_FMA(C4, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), k4T, k4z, k4p, cc);
-        a = A51 * f1; a = PRT_FMA(A52, k2z, a); a = PRT_FMA(A53, k3z, a); a = PRT_FMA(A54, k4z, a);
-        b = A51 * f2; b = PRT_FMA(A52, k2p, b); b = PRT_FMA(A53, k3p, b); b = PRT_FMA(A54, k4p, b);
-        prt_rhs(E, PRT_FMA(C5, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), k5T, k5z, k5p, cc);
-        a = A61 * f1; a = PRT_FMA(A62, k2z, a); a = PRT_FMA(A63, k3z, a); a = PRT_FMA(A64, k4z, a); a = PRT_FMA(A65, k5z, a);
-        b = A61 * f2; b = PRT_FMA(A62, k2p, b); b = PRT_FMA(A63, k3p, b); b = PRT_FMA(A64, k4p, b); b = PRT_FMA(A65, k5p, b);
-        prt_rhs(E, t + hh, PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), k6T, k6z, k6p, cc);
-        double sT = B1 * f0; sT = PRT_FMA(B3, k3T, sT); sT = PRT_FMA(B4, k4T, sT); sT = PRT_FMA(B5, k5T, sT); sT = PRT_FMA(B6, k6T, sT);
-        double sz = B1 * f1; sz = PRT_FMA(B3, k3z, sz); sz = PRT_FMA(B4, k4z, sz); sz = PRT_FMA(B5, k5z, sz); sz = PRT_FMA(B6, k6z, sz);
-        double sp = B1 * f2; sp = PRT_FMA(B3, k3p, sp); sp = PRT_FMA(B4, k4p, sp); sp = PRT_FMA(B5, k5p, sp); sp = PRT_FMA(B6, k6p, sp);
-        const double nT = PRT_FMA(hh, sT, T), nz = PRT_FMA(hh, sz, z), np_ = PRT_FMA(hh, sp, p);
-        prt_rhs(E, t + hh, nz, np_, k7T, k7z, k7p, c_new);  // f_new (FSAL)
-        (void)k2T;
+        // the trial step: speculative cell lookups, one branch-free block; re-run through the general lookup
+        // if any of its seven guesses missed (same arithmetic, so the same bits either way)
+        prt_try v;
+        bool ok = true;
+        prt_rk_try<false>(E, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, v, ok);
+#if defined(PRT_ASSUME_OK)
+        ok = true;
 #endif
-        double eT = E1 * f0; eT = PRT_FMA(E3, k3T, eT); eT = PRT_FMA(E4, k4T, eT); eT = PRT_FMA(E5, k5T, eT); eT = PRT_FMA(E6, k6T, eT); eT = PRT_FMA(E7, k7T, eT);
-        double ez = E1 * f1; ez = PRT_FMA(E3, k3z, ez); ez = PRT_FMA(E4, k4z, ez); ez = PRT_FMA(E5, k5z, ez); ez = PRT_FMA(E6, k6z, ez); ez = PRT_FMA(E7, k7z, ez);
-        double ep = E1 * f2; ep = PRT_FMA(E3, k3p, ep); ep = PRT_FMA(E4, k4p, ep); ep = PRT_FMA(E5, k5p, ep); ep = PRT_FMA(E6, k6p, ep); ep = PRT_FMA(E7, k7p, ep);
-        const double scT = PRT_FMA(prt_np_maximum(fabs(T), fabs(nT)), S.rtol, S.atol);
-        const double scz = PRT_FMA(prt_np_maximum(fabs(z), fabs(nz)), S.rtol, S.atol);
-        const double scp = PRT_FMA(prt_np_maximum(fabs(p), fabs(np_)), S.rtol, S.atol);
-        // error_norm carried as its square (mean square of the scaled error): accept iff ms < 1 and
-        // error_norm ** (-1/5) = ms ** (-1/10)  -- no square root, no division by sqrt(3) (rk.py:148-165)
-        const double r0 = (eT * hh) / scT, r1 = (ez * hh) / scz, r2 = (ep * hh) / scp;
-        double ms = r0 * r0;
-        ms = PRT_FMA(r1, r1, ms);
-        ms = PRT_FMA(r2, r2, ms);
-        ms = ms * 0x1.5555555555555p-2;
-        // one evaluation of the controller power for accepting and rejecting lanes alike (lanes of a warp
-        // split between the two outcomes on most attempts)
-        const double pw = (ms == 0.0) ? 0.0 : prt_pow_m01(ms);
-        if (!(ms < 1.0)) {
-            h_abs *= prt_py_max(0.2, 0.9 * pw);
+        if (!ok) {
+            prt_try cold;
+            prt_rk_try_exact(&E.v, E.grid, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, &cold);
+            v = cold;
+        }
+        // controller (rk.py:153-165); one power serves accepting and rejecting lanes.  ms == 0 needs no special
+        // case: prt_pow_m01(0) >= 119, so the factor is MAX_FACTOR as in the reference
+        if (!(v.ms < 1.0)) {
+            h_abs *= prt_py_max(0.2, 0.9 * v.pw);
             rejected = true;
             return false;
         }
-        double factor = (ms == 0.0) ? 10.0 : prt_py_min(10.0, 0.9 * pw);
+        double factor = prt_py_min(10.0, 0.9 * v.pw);
         if (rejected) factor = prt_py_min(1.0, factor);
         h_abs *= factor;
         rejected = false;
         ++c_acc;
+        const double nT = v.nT, nz = v.nz, np_ = v.np_;
+        const double k3T = v.k3T, k3z = v.k3z, k3p = v.k3p, k4T = v.k4T, k4z = v.k4z, k4p = v.k4p;
+        const double k5T = v.k5T, k5z = v.k5z, k5p = v.k5p, k6T = v.k6T, k6z = v.k6z, k6p = v.k6p;
+        const double k7T = v.k7T, k7z = v.k7z, k7p = v.k7p;
+        double c_new = v.c_new;
         st.t_old = t; st.t_new = tn; st.h = hh;
         st.yT = nT; st.yz = nz; st.yp = np_;
         st.nf0 = k7T; st.nf1 = k7z; st.nf2 = k7p;
@@ -958,7 +1073,7 @@ struct prt_ray {
             st.qT = prt_dense_q(f0, k3T, k4T, k5T, k6T, k7T);
             st.qz = prt_dense_q(f1, k3z, k4z, k5z, k6z, k7z);
             st.qp = prt_dense_q(f2, k3p, k4p, k5p, k6p, k7p);
-            st.inv_h = 1.0 / hh;
+            st.inv_h = prt_rcp(hh);  // contract: dense-output abscissa (t - t_old) * rcp(h), rk.py:722
         }
         return true;
     }
@@ -990,7 +1105,7 @@ struct prt_ray {
         if (st.finished) phase = PRT_PH_DONE;  // sol.status == 0, launch_rays.py:425-426
     }
 
-    PRT_HD bool event_at(const prt_env_view& E, const prt_step& st, int e, double x) const
+    PRT_HD bool event_at(const prt_envp& E, const prt_step& st, int e, double x) const
     {
         const double xx = (x - st.t_old) * st.inv_h;
         const double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
@@ -1001,7 +1116,7 @@ struct prt_ray {
     // handle_events (ivp.py:80-131): every st.event is terminal -> earliest st.root, ties to the lower
     // st.event index.  solve_event_equation = brentq(xtol = rtol = 4 eps, maxiter 100) on a +-1
     // function, which degenerates to bisection (|f| is always 1).
-    PRT_HD void solve_roots(const prt_env_view& E, prt_step& st)
+    PRT_HD void solve_roots(const prt_envp& E, prt_step& st)
     {
         double best_root = 0.0;
         int best = -1;
@@ -1045,7 +1160,7 @@ struct prt_ray {
 
     // terminal step: _interpolate_ray bookkeeping for the st.finished segment (launch_rays.py:745-784),
     // state at the st.event, then the reflection (launch_rays.py:432-480)
-    PRT_HD void finish_terminal(const prt_env_view& E, const prt_shot& S, const prt_traj_sink& sink, const prt_step& st)
+    PRT_HD void finish_terminal(const prt_envp& E, const prt_shot& S, const prt_traj_sink& sink, const prt_step& st)
     {
         if (status != PRT_RAY_OK) {
             phase = PRT_PH_DONE;
@@ -1084,7 +1199,7 @@ struct prt_ray {
             ++n_surface;
         } else {
             bool oob;
-            const double beta = prt_bottom_angle(E, t, oob);
+            const double beta = prt_bottom_angle(E.v, t, oob);
             if (oob) { status = PRT_RAY_BOTTOM_OOB; return; }
             theta_bounce = 2.0 * beta - theta;
             ++n_bottom;
@@ -1115,7 +1230,7 @@ struct prt_ray {
 
 // ray-by-ray driver (host parity harness; also the semantic definition of the warp driver)
 template <bool SAVE>
-PRT_HD void prt_integrate_ray(const prt_env_view& E, double T, double z, double p, double x0, prt_shot S,
+PRT_HD void prt_integrate_ray(const prt_envp& E, double T, double z, double p, double x0, prt_shot S,
                               const prt_traj_sink& sink, prt_ray_result& res, uint32_t* cnt)
 {
     if (S.rtol < 100.0 * PRT_EPS) S.rtol = 100.0 * PRT_EPS;  // validate_tol, common.py:44-60

@@ -48,6 +48,28 @@ static inline void prt_pack_cells(prt_d2* dst, const double* a, int n)
     }
 }
 
+// {a[i], 1/(a[i+1]-a[i])} per cell
+static inline void prt_pack_xr(prt_d2* dst, const double* a, int n)
+{
+    for (int i = 0; i < n - 1; ++i) {
+        dst[i].x = a[i];
+        dst[i].y = 1.0 / (a[i + 1] - a[i]);
+    }
+}
+
+// bathymetry cells: {lo, hi} padded like prt_pack_cells, {x[i], 1/(x[i+1]-x[i])}, {depth[i], depth[i+1]}
+static inline void prt_pack_bcells(prt_d2* dst, const double* x, const double* d, int n)
+{
+    for (int i = 0; i < n - 1; ++i) {
+        dst[3 * i].x = (i == 0) ? -INFINITY : x[i];
+        dst[3 * i].y = (i == n - 2) ? INFINITY : x[i + 1];
+        dst[3 * i + 1].x = x[i];
+        dst[3 * i + 1].y = 1.0 / (x[i + 1] - x[i]);
+        dst[3 * i + 2].x = d[i];
+        dst[3 * i + 2].y = d[i + 1];
+    }
+}
+
 static inline double prt_inv_mean_step(const double* a, int n)
 {
     double span = a[n - 1] - a[0];
@@ -73,7 +95,10 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
     size_t o_brec = o_zrec + prt_align256(sizeof(double) * (size_t)(n_z - 1));
     size_t o_rcell = o_brec + prt_align256(sizeof(double) * (size_t)(n_b - 1));
     size_t o_zcell = o_rcell + prt_align256(sizeof(prt_d2) * 2 * (size_t)(n_r - 1));
-    size_t o_bax = o_zcell + prt_align256(sizeof(prt_d2) * 2 * (size_t)(n_z - 1));
+    size_t o_bcell = o_zcell + prt_align256(sizeof(prt_d2) * 2 * (size_t)(n_z - 1));
+    size_t o_rxr = o_bcell + prt_align256(sizeof(prt_d2) * 3 * (size_t)(n_b - 1));
+    size_t o_zxr = o_rxr + prt_align256(sizeof(prt_d2) * (size_t)(n_r - 1));
+    size_t o_bax = o_zxr + prt_align256(sizeof(prt_d2) * (size_t)(n_z - 1));
     size_t o_bac = o_bax + prt_align256(sizeof(double) * (size_t)n_ba);
     size_t total = o_bac + prt_align256(sizeof(double) * 4 * (size_t)(n_ba - 1));
     out.bytes.assign(total, 0);
@@ -90,6 +115,9 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
     prt_pack_pairs(reinterpret_cast<prt_d2*>(base + o_bv), depths, n_b);
     prt_pack_cells(reinterpret_cast<prt_d2*>(base + o_rcell), rin, n_r);
     prt_pack_cells(reinterpret_cast<prt_d2*>(base + o_zcell), zin, n_z);
+    prt_pack_bcells(reinterpret_cast<prt_d2*>(base + o_bcell), depth_ranges, depths, n_b);
+    prt_pack_xr(reinterpret_cast<prt_d2*>(base + o_rxr), rin, n_r);
+    prt_pack_xr(reinterpret_cast<prt_d2*>(base + o_zxr), zin, n_z);
     prt_pack_recip(reinterpret_cast<double*>(base + o_rrec), rin, n_r);
     prt_pack_recip(reinterpret_cast<double*>(base + o_zrec), zin, n_z);
     prt_pack_recip(reinterpret_cast<double*>(base + o_brec), depth_ranges, n_b);
@@ -107,6 +135,9 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
     v.bvpair = reinterpret_cast<const prt_d2*>(o_bv);
     v.rcell = reinterpret_cast<const prt_d2*>(o_rcell);
     v.zcell = reinterpret_cast<const prt_d2*>(o_zcell);
+    v.bcell = reinterpret_cast<const prt_d2*>(o_bcell);
+    v.rxr = reinterpret_cast<const prt_d2*>(o_rxr);
+    v.zxr = reinterpret_cast<const prt_d2*>(o_zxr);
     v.rrecip = reinterpret_cast<const double*>(o_rrec);
     v.zrecip = reinterpret_cast<const double*>(o_zrec);
     v.brecip = reinterpret_cast<const double*>(o_brec);
@@ -115,6 +146,7 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
     v.r0 = rin[0]; v.r_inv = prt_inv_mean_step(rin, n_r);
     v.z0 = zin[0]; v.z_inv = prt_inv_mean_step(zin, n_z);
     v.b0 = depth_ranges[0]; v.b_inv = prt_inv_mean_step(depth_ranges, n_b);
+    v.r_off = -v.r0 * v.r_inv; v.z_off = -v.z0 * v.z_inv; v.b_off = -v.b0 * v.b_inv;
     // ray_bounding_box_event tolerances (integration_processes.py:280-303)
     const double tol = 1e-6;
     v.bb_zmax = zin[n_z - 1] + tol;
@@ -136,6 +168,9 @@ static inline prt_env_view prt_env_rebase(const prt_env_view& view, const void* 
     v.bvpair = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.bvpair));
     v.rcell = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.rcell));
     v.zcell = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.zcell));
+    v.bcell = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.bcell));
+    v.rxr = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.rxr));
+    v.zxr = reinterpret_cast<const prt_d2*>(b + reinterpret_cast<size_t>(view.zxr));
     v.rrecip = reinterpret_cast<const double*>(b + reinterpret_cast<size_t>(view.rrecip));
     v.zrecip = reinterpret_cast<const double*>(b + reinterpret_cast<size_t>(view.zrecip));
     v.brecip = reinterpret_cast<const double*>(b + reinterpret_cast<size_t>(view.brecip));

@@ -123,7 +123,7 @@ struct prt_park_slot {
 //     no lane is left stepping or the oldest parked lane has waited `park_wait` iterations
 //     (neighbouring launch angles reach a boundary within a few steps of each other).
 template <bool SAVE>
-__device__ __forceinline__ void prt_integrate_warp(const prt_env_view& E, prt_ray<SAVE>& r, const prt_shot& S,
+__device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SAVE>& r, const prt_shot& S,
                                                    const prt_traj_sink& sink, int park_wait,
                                                    const prt_park_slot& park)
 {
@@ -132,10 +132,10 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_env_view& E, prt_ra
     for (;;) {
         if (!__any_sync(full, r.phase != PRT_PH_DONE)) break;
         if (r.phase == PRT_PH_INIT) r.seg_init(E, S);
-        __syncwarp(full);
+        const unsigned stepping_now = __ballot_sync(full, r.phase == PRT_PH_STEP);
         if (r.phase == PRT_PH_STEP) {
             prt_step st;
-            if (r.attempt(E, S, st)) {
+            if (r.attempt(E, S, st, stepping_now)) {
                 if (st.active) {
                     park.store(st);
                     r.phase = PRT_PH_ROOT;
@@ -178,13 +178,14 @@ __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_fan_kernel(const __gr
     const int64_t ray = warp * P.lanes + lane;
     const bool live = (lane < P.lanes) && (ray < P.n_rays);
     // ensembles: same tables, this ray's realisation of the sound-speed grid
-    prt_env_view E = E0;
+    const prt_d2* grid = E0.grid;
     int64_t angle_index = ray;
     if (P.rays_per_env > 0 && live) {
         const int64_t env = ray / P.rays_per_env;
         angle_index = ray - env * P.rays_per_env;
-        E.grid = E0.grid + env * E0.grid_stride;
+        grid = E0.grid + env * E0.grid_stride;
     }
+    const prt_envp E{E0, grid};
     prt_shot S;
     S.x_end = P.receiver_range; S.rtol = P.rtol; S.atol = P.atol;
     S.terminate_backwards = P.terminate_backwards; S.n_save = P.n_save; S.max_bounces = P.max_bounces;
@@ -396,12 +397,13 @@ __global__ void prt_refine_init_kernel(prt_refine_state S, int64_t n_br, const d
     P.out_ray_status[b] = 0;
 }
 
-__global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_refine_round_kernel(const __grid_constant__ prt_env_view E,
+__global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_refine_round_kernel(const __grid_constant__ prt_env_view E0,
                                                                const __grid_constant__ prt_refine_params P,
                                                                prt_refine_state S, const int32_t* __restrict__ list_in,
                                                                int32_t* __restrict__ list_out, const int32_t* n_in,
                                                                int32_t* n_out)
 {
+    const prt_envp E{E0, E0.grid};
     const int n_active = *n_in;
     const int lane = threadIdx.x & 31;
     const int idx = (int)(((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * P.lanes + lane);
@@ -507,6 +509,14 @@ __global__ void prt_fp64_peak_kernel(double* out, int iters, double a, double b)
 extern "C" {
 
 int prt_abi_version(void) { return PRT_ABI_VERSION; }
+#if defined(PRT_COUNT_COLD)
+PRT_API long long prt_debug_cold(void)
+{
+    unsigned long long v = 0;
+    cudaMemcpyFromSymbol(&v, prt_dbg_cold, sizeof v);
+    return (long long)v;
+}
+#endif
 int prt_set_concurrency(int n_fans)
 {
     g_concurrency.store(n_fans > 0 ? n_fans : 1);

@@ -38,7 +38,8 @@ __attribute__((visibility("default"))) int hh_shoot_fan(void* env, int64_t n_ray
                                                          int32_t* out_ns, int32_t* out_status, uint32_t* out_counters,
                                                          int max_bounces)
 {
-    const prt_env_view& E = static_cast<hh_env*>(env)->view;
+    const prt_env_view& V = static_cast<hh_env*>(env)->view;
+    const prt_envp E{V, V.grid};
     for (int64_t i = 0; i < n_rays; ++i) {
         double T, z, p;
         if (y0s) {
