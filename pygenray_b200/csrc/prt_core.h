@@ -131,14 +131,14 @@ struct prt_envp {
     const prt_d2* grid;
 };
 
-// np.nextafter(t, +inf) (scipy rk.py:119) by integer increment of the bit pattern
+// np.nextafter(t, +inf) (scipy rk.py:119) by integer increment of the bit pattern (select-only: it opens
+// every step attempt)
 PRT_HD double prt_next_up(double t)
 {
-    if (!(fabs(t) < (double)INFINITY)) return t;  // NaN, +-inf: unchanged (never reached: t is a finite range)
-    if (t == 0.0) return 4.9406564584124654e-324;
-    uint64_t b = prt_double_to_bits(t);
-    b = (t > 0.0) ? b + 1 : b - 1;
-    return prt_bits_to_double(b);
+    const uint64_t b = prt_double_to_bits(t);
+    const uint64_t nb = (t > 0.0) ? b + 1 : ((t < 0.0) ? b - 1 : (uint64_t)1);  // 0 -> smallest subnormal
+    const double nu = prt_bits_to_double(nb);
+    return (fabs(t) < (double)INFINITY) ? nu : t;  // NaN, +-inf: unchanged (never reached: t is a finite range)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -456,15 +456,17 @@ PRT_HD void prt_field(const prt_envp& E, double x, double z, double& c, double& 
 }
 
 // Speculative lookup for the Runge-Kutta stages: the same arithmetic from the guessed cell, but NO branch
-// and no extra load -- the guess is checked on the interpolation weight itself: w = (v - x[i]) / (x[i+1] - x[i])
-// is computed from the true edge and width of cell i, so PRT_W_LO < w < PRT_W_HI proves x[i] < v < x[i+1]
-// (the 1e-6 margins dwarf the 4e-16 rounding of w), i.e. that i IS searchsorted(v) - 1.  `ok` collects the
-// proofs and the caller re-runs the whole step attempt through the exact lookup when any of them failed
-// (prt_ray::attempt): abscissae within 1e-6 of a node or outside the grid, and wrong guesses on non-uniform
-// grids.  The stage code of an attempt is thus one branch-free block that the scheduler is free to
-// interleave across stages.
-#define PRT_W_LO 0x1p-20
-#define PRT_W_HI (1.0 - 0x1p-20)
+// and no extra load -- the guess is proven on the interpolation weight itself.  w = (v - x[i]) * (1/(x[i+1]-x[i]))
+// is computed from the true lower edge and width of cell i, so
+//   w > 0          <=>  v > x[i]     (an IEEE difference has the exact sign and the reciprocal is positive),
+//   w < 1 - 2^-40   =>  v < x[i+1]   (v >= x[i+1] gives w >= 1 - 2^-50 after the three roundings),
+// and both together say that i IS clamp(searchsorted(v) - 1).  In the first / last cell the lower / upper
+// test is waived, because the reference clamps there and extrapolates with the same formula.  `ok` collects
+// the proofs and the caller re-runs the whole step attempt through the exact lookup when any failed
+// (prt_ray::attempt): an abscissa on a node or within 1e-12 cell widths below one, and wrong guesses on
+// non-uniform grids.  The stage code of an attempt is thus one branch-free block that the scheduler is free
+// to interleave across stages.
+#define PRT_W_HI (1.0 - 0x1p-40)
 struct prt_xcell {
     const prt_d2* row;  // &grid[i][0]
     double wx;
@@ -478,7 +480,7 @@ PRT_HD prt_xcell prt_xlook(const prt_envp& E, double x, bool& ok)
     prt_xcell xc;
     xc.row = E.grid + i * (unsigned)V.n_z;
     xc.wx = (x - ra.x) * ra.y;
-    ok = ok & (xc.wx > PRT_W_LO) & (xc.wx < PRT_W_HI);
+    ok = ok & ((xc.wx > 0.0) | (i == 0u)) & ((xc.wx < PRT_W_HI) | (i == (unsigned)(V.n_r - 2)));
     return xc;
 }
 
@@ -490,7 +492,7 @@ PRT_HD void prt_field_spec(const prt_envp& E, const prt_xcell& xc, double z, dou
     const prt_d2 za = prt_ld2(V.zxr + j);
     const prt_d2 v00 = prt_ld2(g), v01 = prt_ld2(g + 1), v10 = prt_ld2(g + V.n_z), v11 = prt_ld2(g + V.n_z + 1);
     const double wy = (z - za.x) * za.y;
-    ok = ok & (wy > PRT_W_LO) & (wy < PRT_W_HI);
+    ok = ok & ((wy > 0.0) | (j == 0u)) & ((wy < PRT_W_HI) | (j == (unsigned)(V.n_z - 2)));
     prt_bilerp(v00, v01, v10, v11, xc.wx, wy, c, cz);
 }
 
@@ -510,6 +512,18 @@ PRT_HD double prt_bathy(const prt_envp& E, double x)
         v = prt_ld2(V.bvpair + i);
         w = (x - xe.x) * prt_ld(V.brecip + i);
     }
+    return PRT_FMA(w, v.y, (1.0 - w) * v.x);
+}
+
+// speculative bottom depth for the trial step (same proof on the weight as prt_field_spec)
+PRT_HD double prt_bathy_spec(const prt_envp& E, double x, bool& ok)
+{
+    const prt_env_view& V = E.v;
+    const unsigned g = prt_guess(x, V.b_inv, V.b_off, V.n_b - 2);
+    const prt_d2* bc = V.bcell + 3 * g;
+    const prt_d2 a = prt_ld2(bc + 1), v = prt_ld2(bc + 2);
+    const double w = (x - a.x) * a.y;
+    ok = ok & ((w > 0.0) | (g == 0u)) & ((w < PRT_W_HI) | (g == (unsigned)(V.n_b - 2)));
     return PRT_FMA(w, v.y, (1.0 - w) * v.x);
 }
 
@@ -846,6 +860,8 @@ struct prt_try {
     double c_new;        // sound speed at (t + h, y_new), by-product of the FSAL stage
     double ms;           // mean square of the scaled error = error_norm^2
     double pw;           // ms^(-1/10) = error_norm^(-1/5)
+    int g_new;           // event functions at (t + h, y_new) as a mask, the vertical-ray test still open when ...
+    bool vert_open;      // ... |p c| is within 1e-8 of 1 (then asin decides, prt_ev_vertical)
 };
 
 // EXACT = false: speculative cell lookups, no branch anywhere; `ok` tells whether every guess was right.
@@ -902,6 +918,18 @@ PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, do
     if (EXACT) prt_rhs(E, x6, v.nz, v.np_, v.k7T, v.k7z, v.k7p, v.c_new);  // f_new (FSAL)
     else prt_rhs_spec(E, xc6, v.nz, v.np_, v.k7T, v.k7z, v.k7p, v.c_new, ok);
 #undef PRT_STAGE
+    // the event functions at the step end (ivp.py:678-699) only need y_new and c_new: formed here, they overlap
+    // the tail of the last stage and the controller instead of following the accept decision
+    {
+        const double pc = v.np_ * v.c_new;
+        const double bd = EXACT ? prt_bathy(E, x6) : prt_bathy_spec(E, x6, ok);
+        int m = 0;
+        if ((v.nz < 0.0) & (pc < 0.0) & (pc >= -1.0)) m |= PRT_EV_SURFACE;
+        if ((pc > 0.0) & (pc <= 1.0) & (v.nz > bd)) m |= PRT_EV_BOTTOM;
+        if ((v.nz > E.v.bb_zmax) | (v.nz < E.v.bb_zmin) | (x6 < E.v.bb_rmin) | (x6 > E.v.bb_rmax)) m |= PRT_EV_BBOX;
+        v.g_new = m;
+        v.vert_open = (fabs(pc) > 0.99999999) & (fabs(pc) <= 1.0);
+    }
     eT = PRT_FMA(E7, v.k7T, eT); ez = PRT_FMA(E7, v.k7z, ez); ep = PRT_FMA(E7, v.k7p, ep);
     // error_norm carried as its square (mean square of the scaled error): accept iff ms < 1 and
     // error_norm ** (-1/5) = ms ** (-1/10)  -- no square root, no division by sqrt(3) (rk.py:148-165)
@@ -1055,13 +1083,15 @@ struct prt_ray {
         st.yT = nT; st.yz = nz; st.yp = np_;
         st.nf0 = k7T; st.nf1 = k7z; st.nf2 = k7p;
         st.finished = (tn - S.x_end >= 0.0);  // base.py:205-206
-        // events at the step end (ivp.py:678-699); c(st.t_new, y_new) comes from the FSAL stage, which was
-        // evaluated at t + st.h: identical unless the clipped step made t + st.h != st.t_new
+        // events at the step end (ivp.py:678-699) were formed by the trial step from c(t + h, y_new) of the FSAL
+        // stage: identical to the event functions at st.t_new unless the clipped step made t + h != st.t_new
+        int g_new = v.g_new;
+        if (v.vert_open && prt_ev_vertical(np_ * c_new)) g_new |= PRT_EV_VERTICAL;
         if (t + hh != tn) {
             double cz_unused;
             prt_field(E, tn, nz, c_new, cz_unused);
+            g_new = prt_events(E, tn, nz, np_, c_new);
         }
-        const int g_new = prt_events(E, tn, nz, np_, c_new);
         // find_active_events (ivp.py:134-157): up for direction +1, up|down for direction 0
         const int up = (~g) & g_new, down = g & (~g_new);
         st.active = (up & (PRT_EV_SURFACE | PRT_EV_BOTTOM)) | ((up | down) & (PRT_EV_VERTICAL | PRT_EV_BBOX));
