@@ -117,6 +117,11 @@ struct prt_env_view {
     int32_t n_env;          // number of realisations sharing the coordinate tables (1 for one environment)
     double r0, r_inv, z0, z_inv, b0, b_inv;  // cell-index guesses: (v - x0) * inv (any value is correct)
     double r_off, z_off, b_off;              // -x0 * inv: the same guesses as one fma, v * inv + off
+    // smooth non-uniform depth grids (flat-earth transform): the linear guess s is refined to s + s q(s / n_z) with a
+    // least-squares quadratic q fitted at staging time (prt_env_layout.h); z_cubic == 0 for uniform grids
+    double z_b1, z_b2, z_b3, z_un;
+    int32_t z_cubic;
+    int32_t spec_off;       // 1: guesses too poor on this environment (irregular grids) -> every trial step uses the exact lookup
     const prt_d2* rxr;      // [n_r-1] {rin[i], 1/(rin[i+1]-rin[i])}: all the speculative stage lookup needs per axis
     const prt_d2* zxr;      // [n_z-1] {zin[j], 1/(zin[j+1]-zin[j])}
     const prt_d2* bcell;    // [n_b-1] x 3 prt_d2: {lo, hi} (padded like rcell), {x[i], 1/(x[i+1]-x[i])}, {depth[i], depth[i+1]}
@@ -418,6 +423,19 @@ PRT_HD unsigned prt_guess(double v, double inv, double off, int m)
     return g > (unsigned)m ? (unsigned)m : g;
 }
 
+// depth axis: optionally refined guess (see prt_env_view::z_cubic)
+PRT_HD unsigned prt_guess_z(const prt_env_view& V, double z)
+{
+    double s = PRT_FMA(z, V.z_inv, V.z_off);
+    if (V.z_cubic) {
+        const double u = s * V.z_un;
+        s = PRT_FMA(s, PRT_FMA(PRT_FMA(V.z_b3, u, V.z_b2), u, V.z_b1), s);
+    }
+    const unsigned g = (unsigned)PRT_D2I(s);
+    const unsigned m = (unsigned)(V.n_z - 2);
+    return g > m ? m : g;
+}
+
 // Exact lookup, one cache round trip in the common case: every load (cell records and the four corner
 // nodes) is issued from the guessed indices at once; the guesses are verified afterwards (two compares per
 // axis against edges padded with -inf / +inf at the grid ends, false for NaN) and the rare miss
@@ -426,7 +444,7 @@ PRT_HD void prt_field(const prt_envp& E, double x, double z, double& c, double& 
 {
     const prt_env_view& V = E.v;
     unsigned i = prt_guess(x, V.r_inv, V.r_off, V.n_r - 2);
-    unsigned j = prt_guess(z, V.z_inv, V.z_off, V.n_z - 2);
+    unsigned j = prt_guess_z(V, z);
     const prt_d2* rc = V.rcell + 2 * i;
     const prt_d2* zc = V.zcell + 2 * j;
     const prt_d2 rv = prt_ld2(rc), ra = prt_ld2(rc + 1);
@@ -487,7 +505,7 @@ PRT_HD prt_xcell prt_xlook(const prt_envp& E, double x, bool& ok)
 PRT_HD void prt_field_spec(const prt_envp& E, const prt_xcell& xc, double z, double& c, double& cz, bool& ok)
 {
     const prt_env_view& V = E.v;
-    const unsigned j = prt_guess(z, V.z_inv, V.z_off, V.n_z - 2);
+    const unsigned j = prt_guess_z(V, z);
     const prt_d2* g = xc.row + j;
     const prt_d2 za = prt_ld2(V.zxr + j);
     const prt_d2 v00 = prt_ld2(g), v01 = prt_ld2(g + 1), v10 = prt_ld2(g + V.n_z), v11 = prt_ld2(g + V.n_z + 1);
@@ -1052,8 +1070,8 @@ struct prt_ray {
         // the trial step: speculative cell lookups, one branch-free block; re-run through the general lookup
         // if any of its seven guesses missed (same arithmetic, so the same bits either way)
         prt_try v;
-        bool ok = true;
-        prt_rk_try<false>(E, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, v, ok);
+        bool ok = (E.v.spec_off == 0);  // irregular grids: straight to the exact lookup
+        if (ok) prt_rk_try<false>(E, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, v, ok);
 #if defined(PRT_ASSUME_OK)
         ok = true;
 #endif

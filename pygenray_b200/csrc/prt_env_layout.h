@@ -77,6 +77,49 @@ static inline double prt_inv_mean_step(const double* a, int n)
     return (double)(n - 1) / span;
 }
 
+// Quality of the cell guess trunc(g(v)) over one axis: the largest distance, in cells, between g and the true
+// real-valued index at the nodes and cell centres.  A lookup misses when v lies within that distance of a node.
+template <class G>
+static inline double prt_guess_error(const double* a, int n, G g)
+{
+    double worst = 0.0;
+    for (int i = 0; i < n - 1; ++i) {
+        const double e0 = fabs(g(a[i]) - (double)i);
+        const double e1 = fabs(g(0.5 * (a[i] + a[i + 1])) - ((double)i + 0.5));
+        const double e2 = fabs(g(a[i + 1]) - (double)(i + 1));
+        worst = fmax(worst, fmax(e0, fmax(e1, e2)));
+    }
+    return worst;
+}
+
+// least-squares q(u) = b1 + b2 u + b3 u^2 such that s (1 + q(s / n)) ~ index, s = (a[j] - a[0]) * inv
+static inline void prt_fit_guess(const double* a, int n, double inv, double un, double b[3])
+{
+    long double M[3][4] = {{0}};
+    for (int j = 1; j < n; ++j) {
+        const long double s = (long double)(a[j] - a[0]) * inv, u = s * un;
+        const long double phi[3] = {s, s * u, s * u * u};
+        const long double y = (long double)j - s;
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) M[r][c] += phi[r] * phi[c];
+            M[r][3] += phi[r] * y;
+        }
+    }
+    for (int c = 0; c < 3; ++c) {  // Gauss-Jordan with partial pivoting
+        int piv = c;
+        for (int r = c + 1; r < 3; ++r)
+            if (fabsl(M[r][c]) > fabsl(M[piv][c])) piv = r;
+        for (int k = 0; k < 4; ++k) { long double t = M[c][k]; M[c][k] = M[piv][k]; M[piv][k] = t; }
+        if (M[c][c] == 0.0L) { b[0] = b[1] = b[2] = 0.0; return; }
+        for (int r = 0; r < 3; ++r) {
+            if (r == c) continue;
+            const long double f = M[r][c] / M[c][c];
+            for (int k = c; k < 4; ++k) M[r][k] -= f * M[c][k];
+        }
+    }
+    for (int r = 0; r < 3; ++r) b[r] = (double)(M[r][3] / M[r][r]);
+}
+
 // returns 0 on success, nonzero on invalid sizes
 // n_env >= 1 realisations of the sound-speed field (cin/cpin: [n_env][n_r][n_z]) share one set of
 // coordinate, bathymetry and spline tables (tomography ensembles, BASELINE config 5)
@@ -147,6 +190,30 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
     v.z0 = zin[0]; v.z_inv = prt_inv_mean_step(zin, n_z);
     v.b0 = depth_ranges[0]; v.b_inv = prt_inv_mean_step(depth_ranges, n_b);
     v.r_off = -v.r0 * v.r_inv; v.z_off = -v.z0 * v.z_inv; v.b_off = -v.b0 * v.b_inv;
+    // How good are the guesses?  (They only decide speed: a trial step whose guess missed is redone exactly.)
+    // Linear guess within 1e-6 cells: nothing to do.  Smooth depth stretching (flat-earth): refine with the
+    // fitted quadratic.  Anything worse: the speculative trial step would mostly be wasted, switch it off.
+    const double tol_ok = 1e-4;
+    v.z_cubic = 0; v.z_b1 = v.z_b2 = v.z_b3 = 0.0; v.z_un = 1.0 / (double)n_z;
+    v.spec_off = 0;
+    const double r_inv = v.r_inv, r_off = v.r_off, z_inv = v.z_inv, z_off = v.z_off, b_inv = v.b_inv, b_off = v.b_off;
+    const double err_r = prt_guess_error(rin, n_r, [=](double x) { return fma(x, r_inv, r_off); });
+    const double err_b = prt_guess_error(depth_ranges, n_b, [=](double x) { return fma(x, b_inv, b_off); });
+    double err_z = prt_guess_error(zin, n_z, [=](double x) { return fma(x, z_inv, z_off); });
+    if (err_z > 1e-6) {
+        double b[3];
+        const double un = v.z_un;
+        prt_fit_guess(zin, n_z, z_inv, un, b);
+        const double err_c = prt_guess_error(zin, n_z, [=](double x) {
+            const double s = fma(x, z_inv, z_off), u = s * un;
+            return fma(s, fma(fma(b[2], u, b[1]), u, b[0]), s);
+        });
+        if (err_c < err_z) {
+            v.z_cubic = 1; v.z_b1 = b[0]; v.z_b2 = b[1]; v.z_b3 = b[2];
+            err_z = err_c;
+        }
+    }
+    if (err_r > tol_ok || err_b > tol_ok || err_z > tol_ok) v.spec_off = 1;
     // ray_bounding_box_event tolerances (integration_processes.py:280-303)
     const double tol = 1e-6;
     v.bb_zmax = zin[n_z - 1] + tol;
