@@ -134,6 +134,7 @@ struct prt_env_view {
 struct prt_envp {
     const prt_env_view& v;
     const prt_d2* grid;
+    bool zc;  // == (v.z_cubic != 0); a compile-time constant in each kernel instantiation, so uniform grids pay nothing
 };
 
 // np.nextafter(t, +inf) (scipy rk.py:119) by integer increment of the bit pattern (select-only: it opens
@@ -424,10 +425,11 @@ PRT_HD unsigned prt_guess(double v, double inv, double off, int m)
 }
 
 // depth axis: optionally refined guess (see prt_env_view::z_cubic)
-PRT_HD unsigned prt_guess_z(const prt_env_view& V, double z)
+PRT_HD unsigned prt_guess_z(const prt_envp& E, double z)
 {
+    const prt_env_view& V = E.v;
     double s = PRT_FMA(z, V.z_inv, V.z_off);
-    if (V.z_cubic) {
+    if (E.zc) {
         const double u = s * V.z_un;
         s = PRT_FMA(s, PRT_FMA(PRT_FMA(V.z_b3, u, V.z_b2), u, V.z_b1), s);
     }
@@ -444,7 +446,7 @@ PRT_HD void prt_field(const prt_envp& E, double x, double z, double& c, double& 
 {
     const prt_env_view& V = E.v;
     unsigned i = prt_guess(x, V.r_inv, V.r_off, V.n_r - 2);
-    unsigned j = prt_guess_z(V, z);
+    unsigned j = prt_guess_z(E, z);
     const prt_d2* rc = V.rcell + 2 * i;
     const prt_d2* zc = V.zcell + 2 * j;
     const prt_d2 rv = prt_ld2(rc), ra = prt_ld2(rc + 1);
@@ -505,7 +507,7 @@ PRT_HD prt_xcell prt_xlook(const prt_envp& E, double x, bool& ok)
 PRT_HD void prt_field_spec(const prt_envp& E, const prt_xcell& xc, double z, double& c, double& cz, bool& ok)
 {
     const prt_env_view& V = E.v;
-    const unsigned j = prt_guess_z(V, z);
+    const unsigned j = prt_guess_z(E, z);
     const prt_d2* g = xc.row + j;
     const prt_d2 za = prt_ld2(V.zxr + j);
     const prt_d2 v00 = prt_ld2(g), v01 = prt_ld2(g + 1), v10 = prt_ld2(g + V.n_z), v11 = prt_ld2(g + V.n_z + 1);
@@ -968,7 +970,7 @@ PRT_HD_NOINLINE void prt_rk_try_exact(const prt_env_view* V, const prt_d2* grid,
                                       double hh, double T, double z, double p, double f0, double f1, double f2,
                                       prt_try* out)
 {
-    const prt_envp E{*V, grid};
+    const prt_envp E{*V, grid, V->z_cubic != 0};
     bool ok = true;
 #if defined(PRT_COUNT_COLD) && !defined(__CUDACC__)
     extern long long prt_cold_count;

@@ -168,7 +168,7 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SA
 #ifndef PRT_MIN_BLOCKS
 #define PRT_MIN_BLOCKS 4
 #endif
-template <bool SAVE>
+template <bool SAVE, bool ZC>
 __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_fan_kernel(const __grid_constant__ prt_env_view E0,
                                                       const __grid_constant__ prt_fan_params P)
 {
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_fan_kernel(const __gr
         angle_index = ray - env * P.rays_per_env;
         grid = E0.grid + env * E0.grid_stride;
     }
-    const prt_envp E{E0, grid};
+    const prt_envp E{E0, grid, ZC};
     prt_shot S;
     S.x_end = P.receiver_range; S.rtol = P.rtol; S.atol = P.atol;
     S.terminate_backwards = P.terminate_backwards; S.n_save = P.n_save; S.max_bounces = P.max_bounces;
@@ -397,13 +397,14 @@ __global__ void prt_refine_init_kernel(prt_refine_state S, int64_t n_br, const d
     P.out_ray_status[b] = 0;
 }
 
+template <bool ZC>
 __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_refine_round_kernel(const __grid_constant__ prt_env_view E0,
                                                                const __grid_constant__ prt_refine_params P,
                                                                prt_refine_state S, const int32_t* __restrict__ list_in,
                                                                int32_t* __restrict__ list_out, const int32_t* n_in,
                                                                int32_t* n_out)
 {
-    const prt_envp E{E0, E0.grid};
+    const prt_envp E{E0, E0.grid, ZC};
     const int n_active = *n_in;
     const int lane = threadIdx.x & 31;
     const int idx = (int)(((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * P.lanes + lane);
@@ -642,8 +643,14 @@ static int shoot_fan_impl(const prt_env_t* env, int64_t n_rays, int64_t rays_per
     const int64_t n_warps = (n_rays + P.lanes - 1) / P.lanes;
     const unsigned grid = (unsigned)((n_warps * 32 + block - 1) / block);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (save) prt_fan_kernel<true><<<grid, block, 0, s>>>(env->view, P);
-    else prt_fan_kernel<false><<<grid, block, 0, s>>>(env->view, P);
+    const bool zc = env->view.z_cubic != 0;  // refined depth guess compiled in only for stretched depth grids
+    if (save) {
+        if (zc) prt_fan_kernel<true, true><<<grid, block, 0, s>>>(env->view, P);
+        else prt_fan_kernel<true, false><<<grid, block, 0, s>>>(env->view, P);
+    } else {
+        if (zc) prt_fan_kernel<false, true><<<grid, block, 0, s>>>(env->view, P);
+        else prt_fan_kernel<false, false><<<grid, block, 0, s>>>(env->view, P);
+    }
     g_launches.fetch_add(1);
     PRT_CUDA(cudaGetLastError());
     if (out_p_sign_changes_dev) {
@@ -850,7 +857,8 @@ int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev
         const int block = 128;
         const int64_t n_warps = ((int64_t)n_active + P.lanes - 1) / P.lanes;
         const unsigned grid = (unsigned)((n_warps * 32 + block - 1) / block);
-        prt_refine_round_kernel<<<grid, block, 0, s>>>(env->view, P, S, list_in, list_out, n_in, n_out);
+        if (env->view.z_cubic) prt_refine_round_kernel<true><<<grid, block, 0, s>>>(env->view, P, S, list_in, list_out, n_in, n_out);
+        else prt_refine_round_kernel<false><<<grid, block, 0, s>>>(env->view, P, S, list_in, list_out, n_in, n_out);
         g_launches.fetch_add(1);
         PRT_CUDA(cudaGetLastError());
         PRT_CUDA(cudaMemcpyAsync(&n_active, n_out, sizeof(int32_t), cudaMemcpyDeviceToHost, s));

@@ -236,23 +236,31 @@ def _fingerprint(*arrays):
 
 
 def _device_environment(environment, flatearth, backwards, device=None):
-    """Unpack (+ mirror) the environment and stage it once per (content, orientation, device)."""
+    """Unpack (+ mirror) the environment and stage it once per (content, orientation, device).
+
+    The cache key is a checksum of the arrays the environment holds (so in-place edits are seen); the depth
+    derivative (``np.gradient``, the expensive part of ``_unpack_envi``) is only formed on a miss."""
     import torch  # noqa: PLC0415
 
-    cin, cpin, rin, zin, depths, depth_ranges, bottom_angles = _unpack_envi(environment, flatearth=flatearth)
-    _check_monotonic(rin, zin, depth_ranges)
-    if backwards:
-        cin, cpin, rin, depths, depth_ranges, bottom_angles = _mirror_envi_arrays(
-            cin, cpin, rin, depths, depth_ranges, bottom_angles
-        )
+    if flatearth and not hasattr(environment, "sound_speed_fe"):
+        _unpack_envi(environment, flatearth=True)  # raises the reference's exception
+    ss, bathy = ((environment.sound_speed_fe, environment.bathymetry_fe) if flatearth
+                 else (environment.sound_speed, environment.bathymetry))
     if device is None:
         _lib.require_gpu()
         device = torch.cuda.current_device()
     key = (bool(flatearth), bool(backwards), int(device),
-           _fingerprint(cin, rin, zin, depths, depth_ranges, bottom_angles))
+           _fingerprint(_xr.values_of(ss), _xr.coord_of(ss, "range"), _xr.coord_of(ss, "depth"), _xr.values_of(bathy),
+                        _xr.coord_of(bathy, "range"), np.asarray(environment.bottom_angle)))
     cache = environment.__dict__.setdefault("_prt_device_cache", {})
     denv = cache.get(key)
     if denv is None:
+        cin, cpin, rin, zin, depths, depth_ranges, bottom_angles = _unpack_envi(environment, flatearth=flatearth)
+        _check_monotonic(rin, zin, depth_ranges)
+        if backwards:
+            cin, cpin, rin, depths, depth_ranges, bottom_angles = _mirror_envi_arrays(
+                cin, cpin, rin, depths, depth_ranges, bottom_angles
+            )
         denv = DeviceEnvironment(cin, cpin, rin, zin, depths, depth_ranges, bottom_angles, device=device)
         if len(cache) >= 4:
             cache.pop(next(iter(cache))).close()
@@ -345,6 +353,16 @@ def shoot_fan_arrays(denv, source_depth, source_range, receiver_range, angles=No
 
 _PIPELINE_MIN_RAYS = 4096
 _PIPELINE_CHUNKS = 8
+_STREAM_POOL = {}
+
+
+def _streams(dev, n):
+    pool = _STREAM_POOL.setdefault(dev.index, [])
+    import torch  # noqa: PLC0415
+
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
 
 
 def _shoot_fan_pipelined(denv, source_depth, source_range, receiver_range, angles, num_range_save, rtol,
@@ -353,8 +371,9 @@ def _shoot_fan_pipelined(denv, source_depth, source_range, receiver_range, angle
     separate streams, and each chunk's surviving rays are copied to the host while the slower chunks (steep,
     reflecting rays at the ends of the fan) are still integrating.  Survivors are compacted per chunk on the
     device and placed from the middle of the fan outwards, so the host arrays are contiguous without a
-    host-side pass.  Same result dict as ``shoot_fan_arrays(..., stored_convention=True, ray_id_counts=True,
-    compact=True)``."""
+    host-side pass.  The host only ever waits for a chunk's kernel (to learn how many rays survived), never for
+    its copies: the PCIe link stays busy from the first finished chunk to the last.  Same result dict as
+    ``shoot_fan_arrays(..., stored_convention=True, ray_id_counts=True, compact=True)``."""
     L = _lib.require_gpu()
     import torch  # noqa: PLC0415
 
@@ -368,40 +387,38 @@ def _shoot_fan_pipelined(denv, source_depth, source_range, receiver_range, angle
     dev = torch.device("cuda", denv.device)
     rs_np = np.linspace(source_range, receiver_range, n_save)
 
-    def ptr(t):
-        return None if t is None else C.c_void_p(t.data_ptr())
-
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream()
         ang_d = torch.from_numpy(ang).pin_memory().to(dev, non_blocking=True)
         rs_d = torch.from_numpy(rs_np).to(dev)
         traj_h = torch.empty((3, n, n_save), dtype=torch.float64, pin_memory=True)
         final_h = torch.empty((3, n), dtype=torch.float64, pin_memory=True)
-        nb_h = torch.empty(n, dtype=torch.int32, pin_memory=True)
-        ns_h = torch.empty(n, dtype=torch.int32, pin_memory=True)
-        fl_h = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        i32_h = torch.empty((3, n), dtype=torch.int32, pin_memory=True)   # n_bottom, n_surface, p sign changes
+        idx_h = torch.empty(n, dtype=torch.int64, pin_memory=True)
+        # one device allocation per kind; chunk c owns rows [a, b) of each (its trajectory block is [3][m][N])
+        traj_d = torch.empty(3 * n * n_save, dtype=torch.float64, device=dev)
+        final_d = torch.empty(3 * n, dtype=torch.float64, device=dev)
+        i32_d = torch.empty((4, n), dtype=torch.int32, device=dev)         # n_bottom, n_surface, status, flips
+        streams = _streams(dev, n_chunks)
         chunks = []
         L.prt_set_concurrency(n_chunks)
         try:
-            for (a, b) in bounds:
+            for k, (a, b) in enumerate(bounds):
                 m = b - a
-                st = torch.cuda.Stream(device=dev)
+                st = streams[k]
                 st.wait_stream(main)
-                with torch.cuda.stream(st):
-                    c = dict(a=a, b=b, stream=st,
-                             traj=torch.empty((3, m, n_save), dtype=torch.float64, device=dev),
-                             final=torch.empty((3, m), dtype=torch.float64, device=dev),
-                             nb=torch.empty(m, dtype=torch.int32, device=dev),
-                             ns=torch.empty(m, dtype=torch.int32, device=dev),
-                             status=torch.empty(m, dtype=torch.int32, device=dev),
-                             flips=torch.empty(m, dtype=torch.int32, device=dev))
-                    rc = L.prt_shoot_fan(
-                        denv.handle, m, C.c_void_p(ang_d.data_ptr() + 8 * a), None, float(source_depth),
-                        float(source_range), float(receiver_range), float(rtol), ATOL,
-                        int(bool(terminate_backwards)), n_save, ptr(rs_d), ptr(c["traj"]), ptr(c["final"]),
-                        ptr(c["nb"]), ptr(c["ns"]), ptr(c["status"]), None, 1, ptr(c["flips"]), int(max_bounces),
-                        C.c_void_p(st.cuda_stream))
-                    _lib.check(rc, "prt_shoot_fan")
+                c = dict(a=a, b=b, stream=st, traj=traj_d[3 * a * n_save:3 * b * n_save].view(3, m, n_save),
+                         final=final_d[3 * a:3 * b].view(3, m), nb=i32_d[0, a:b], ns=i32_d[1, a:b],
+                         status=i32_d[2, a:b], flips=i32_d[3, a:b])
+                rc = L.prt_shoot_fan(
+                    denv.handle, m, C.c_void_p(ang_d.data_ptr() + 8 * a), None, float(source_depth),
+                    float(source_range), float(receiver_range), float(rtol), ATOL,
+                    int(bool(terminate_backwards)), n_save, C.c_void_p(rs_d.data_ptr()),
+                    C.c_void_p(c["traj"].data_ptr()), C.c_void_p(c["final"].data_ptr()),
+                    C.c_void_p(c["nb"].data_ptr()), C.c_void_p(c["ns"].data_ptr()),
+                    C.c_void_p(c["status"].data_ptr()), None, 1, C.c_void_p(c["flips"].data_ptr()), int(max_bounces),
+                    C.c_void_p(st.cuda_stream))
+                _lib.check(rc, "prt_shoot_fan")
                 chunks.append(c)
         finally:
             L.prt_set_concurrency(1)
@@ -410,12 +427,11 @@ def _shoot_fan_pipelined(denv, source_depth, source_range, receiver_range, angle
         centre = (n_chunks - 1) / 2.0
         order = sorted(range(n_chunks), key=lambda k: (abs(k - centre), k))
         left = right = None
-        kept_parts = {}
+        kept_slices = {}
         for k in order:
             c = chunks[k]
             with torch.cuda.stream(c["stream"]):
-                ok = c["status"] == 0
-                idx = torch.nonzero(ok).squeeze(1)  # synchronises this chunk's stream only
+                idx = torch.nonzero(c["status"] == 0).squeeze(1)  # waits for this chunk's kernel only
                 kc = int(idx.shape[0])
                 m = c["b"] - c["a"]
                 src = {key: c[key] for key in ("traj", "final", "nb", "ns", "flips")}
@@ -434,18 +450,21 @@ def _shoot_fan_pipelined(denv, source_depth, source_range, receiver_range, angle
                     for q in range(3):  # plane by plane: each destination slice is contiguous (a strided
                         traj_h[q, lo:lo + kc].copy_(src["traj"][q], non_blocking=True)  # D2H would be staged)
                         final_h[q, lo:lo + kc].copy_(src["final"][q], non_blocking=True)
-                    nb_h[lo:lo + kc].copy_(src["nb"], non_blocking=True)
-                    ns_h[lo:lo + kc].copy_(src["ns"], non_blocking=True)
-                    fl_h[lo:lo + kc].copy_(src["flips"], non_blocking=True)
-                kept_parts[k] = idx.cpu().numpy() + c["a"]
-                c["keep_alive"] = src
+                    i32_h[0, lo:lo + kc].copy_(src["nb"], non_blocking=True)
+                    i32_h[1, lo:lo + kc].copy_(src["ns"], non_blocking=True)
+                    i32_h[2, lo:lo + kc].copy_(src["flips"], non_blocking=True)
+                    idx_h[lo:lo + kc].copy_(idx, non_blocking=True)
+                kept_slices[k] = (lo, kc, c["a"])
+                c["keep_alive"] = (src, idx)
         for c in chunks:
             c["stream"].synchronize()
             main.wait_stream(c["stream"])
-    kept = np.concatenate([kept_parts[k] for k in range(n_chunks)]) if n_chunks else np.zeros(0, np.int64)
+    idx_np = idx_h.numpy()
+    parts = [idx_np[lo:lo + kc] + a for (lo, kc, a) in (kept_slices[k] for k in range(n_chunks))]
+    kept = np.concatenate(parts) if parts else np.zeros(0, np.int64)
     return dict(range_save=rs_np, traj=traj_h[:, left:right].numpy(), final=final_h[:, left:right].numpy(),
-                n_bottom=nb_h[left:right].numpy(), n_surface=ns_h[left:right].numpy(),
-                status=np.zeros(right - left, dtype=np.int32), p_sign_changes=fl_h[left:right].numpy(), kept=kept)
+                n_bottom=i32_h[0, left:right].numpy(), n_surface=i32_h[1, left:right].numpy(),
+                status=np.zeros(right - left, dtype=np.int32), p_sign_changes=i32_h[2, left:right].numpy(), kept=kept)
 
 
 _RAISING = {
