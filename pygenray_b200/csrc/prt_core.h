@@ -880,6 +880,8 @@ struct prt_try {
     double c_new;        // sound speed at (t + h, y_new), by-product of the FSAL stage
     double ms;           // mean square of the scaled error = error_norm^2
     double pw;           // ms^(-1/10) = error_norm^(-1/5)
+    prt_q3 qT, qz, qp;   // dense-output rows Q = K^T P and rcp(h): only filled by prt_rk_try<.., DENSE = true>
+    double inv_h;
     int g_new;           // event functions at (t + h, y_new) as a mask, the vertical-ray test still open when ...
     bool vert_open;      // ... |p c| is within 1e-8 of 1 (then asin decides, prt_ev_vertical)
 };
@@ -887,7 +889,9 @@ struct prt_try {
 // EXACT = false: speculative cell lookups, no branch anywhere; `ok` tells whether every guess was right.
 // EXACT = true : the general lookup (prt_field) in every stage; same arithmetic, hence the same bits
 //                whenever the speculative version reports ok.
-template <bool EXACT>
+// DENSE = true : also forms the dense-output rows and rcp(h) (trajectory-saving kernels, where nearly every
+//                accepted step needs them: inside this block they fill the stalls of the stage chain)
+template <bool EXACT, bool DENSE>
 PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, double hh, double T, double z,
                        double p, double f0, double f1, double f2, prt_try& v, bool& ok)
 {
@@ -960,12 +964,19 @@ PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, do
     ms = ms * 0x1.5555555555555p-2;
     v.ms = ms;
     v.pw = prt_pow_m01(ms);
+    if (DENSE) {
+        v.qT = prt_dense_q(f0, v.k3T, v.k4T, v.k5T, v.k6T, v.k7T);
+        v.qz = prt_dense_q(f1, v.k3z, v.k4z, v.k5z, v.k6z, v.k7z);
+        v.qp = prt_dense_q(f2, v.k3p, v.k4p, v.k5p, v.k6p, v.k7p);
+        v.inv_h = prt_rcp(hh);  // contract: dense-output abscissa (t - t_old) * rcp(h), rk.py:722
+    }
 }
 
 #if defined(PRT_COUNT_COLD) && defined(__CUDACC__)
 __device__ unsigned long long prt_dbg_cold;
 #endif
 // cold path of prt_ray::attempt: the same trial step through the general cell lookup
+template <bool DENSE>
 PRT_HD_NOINLINE void prt_rk_try_exact(const prt_env_view* V, const prt_d2* grid, double rtol, double atol, double t,
                                       double hh, double T, double z, double p, double f0, double f1, double f2,
                                       prt_try* out)
@@ -978,7 +989,7 @@ PRT_HD_NOINLINE void prt_rk_try_exact(const prt_env_view* V, const prt_d2* grid,
 #elif defined(PRT_COUNT_COLD) && defined(__CUDA_ARCH__)
     atomicAdd(&prt_dbg_cold, 1ULL);
 #endif
-    prt_rk_try<true>(E, rtol, atol, t, hh, T, z, p, f0, f1, f2, *out, ok);
+    prt_rk_try<true, DENSE>(E, rtol, atol, t, hh, T, z, p, f0, f1, f2, *out, ok);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1005,6 +1016,7 @@ template <bool SAVE>
 struct prt_ray {
     // persistent ODE state (solver.t, solver.y, solver.f, solver.h_abs)
     double t, T, z, p, f0, f1, f2, h_abs;
+    double rs_cur;  // SAVE: range_save[cursor], loaded when the cursor moves (never on the path of a step decision)
     int32_t g, n_ts, cursor, n_surface, n_bottom, status, phase;
     bool rejected;
     uint32_t c_att, c_acc, c_seg, c_bis, c_dense;  // RHS evaluations = 2 c_seg + 6 c_att
@@ -1015,6 +1027,7 @@ struct prt_ray {
         n_surface = n_bottom = 0;
         status = PRT_RAY_OK;
         cursor = 0;
+        rs_cur = (SAVE && S.n_save > 0) ? prt_ld(S.range_save) : 0.0;
         c_att = c_acc = c_seg = c_bis = c_dense = 0;
         rejected = false;
         phase = (x0 < S.x_end) ? PRT_PH_INIT : PRT_PH_DONE;  // launch_rays.py:404
@@ -1073,13 +1086,13 @@ struct prt_ray {
         // if any of its seven guesses missed (same arithmetic, so the same bits either way)
         prt_try v;
         bool ok = (E.v.spec_off == 0);  // irregular grids: straight to the exact lookup
-        if (ok) prt_rk_try<false>(E, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, v, ok);
+        if (ok) prt_rk_try<false, SAVE>(E, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, v, ok);
 #if defined(PRT_ASSUME_OK)
         ok = true;
 #endif
         if (!ok) {
             prt_try cold;
-            prt_rk_try_exact(&E.v, E.grid, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, &cold);
+            prt_rk_try_exact<SAVE>(&E.v, E.grid, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, &cold);
             v = cold;
         }
         // controller (rk.py:153-165); one power serves accepting and rejecting lanes.  ms == 0 needs no special
@@ -1117,9 +1130,12 @@ struct prt_ray {
         st.active = (up & (PRT_EV_SURFACE | PRT_EV_BOTTOM)) | ((up | down) & (PRT_EV_VERTICAL | PRT_EV_BBOX));
         g = g_new;
         bool need_dense = (st.active != 0);
-        if (SAVE && !need_dense) need_dense = (cursor < S.n_save - 1) && (prt_ld(S.range_save + cursor) <= tn);
-        if (need_dense) {
-            ++c_dense;
+        if (SAVE && !need_dense) need_dense = (cursor < S.n_save - 1) && (rs_cur <= tn);
+        if (need_dense) ++c_dense;
+        if (SAVE) {  // formed by the trial step
+            st.qT = v.qT; st.qz = v.qz; st.qp = v.qp;
+            st.inv_h = v.inv_h;
+        } else if (need_dense) {
             st.qT = prt_dense_q(f0, k3T, k4T, k5T, k6T, k7T);
             st.qz = prt_dense_q(f1, k3z, k4z, k5z, k6z, k7z);
             st.qp = prt_dense_q(f2, k3p, k4p, k5p, k6p, k7p);
@@ -1141,11 +1157,10 @@ struct prt_ray {
     {
         if (SAVE) {
             const int ub = S.n_save - 1;
-            while (cursor < ub) {
-                const double rsv = prt_ld(S.range_save + cursor);
-                if (!(rsv <= st.t_new)) break;
-                emit(sink, st, cursor, rsv);
+            while ((cursor < ub) && (rs_cur <= st.t_new)) {
+                emit(sink, st, cursor, rs_cur);
                 ++cursor;
+                rs_cur = prt_ld(S.range_save + cursor);  // cursor <= n_save - 1
             }
         }
         T = st.yT; z = st.yz; p = st.yp;
@@ -1227,6 +1242,7 @@ struct prt_ray {
                 }
             }
             cursor = ub;  // the next segment owns indices >= idx2
+            rs_cur = prt_ld(S.range_save + cursor);
         }
         if (!popped) {
             const double xx = (st.root - st.t_old) * st.inv_h;
