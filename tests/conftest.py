@@ -60,8 +60,20 @@ class HostHarness:
         self.lib.hh_env_create.restype = vp
         self.lib.hh_env_create.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]
         self.lib.hh_env_destroy.argtypes = [vp]
+        self.lib.hh_env_flags.argtypes = [vp, vp]
         self.lib.hh_shoot_fan.argtypes = [vp, C.c_int64, vp, vp, d, d, d, d, d, C.c_int, C.c_int, vp, vp, vp, vp,
                                           vp, vp, vp, C.c_int]
+
+    def env_flags(self, oenv):
+        """(z_cubic, spec_off): how the staging code rated the cell guesses of this environment."""
+        e = oenv
+        h = self.lib.hh_env_create(len(e.rin), len(e.zin), e.rin.ctypes.data, e.zin.ctypes.data, e.cin.ctypes.data,
+                                   e.cpin.ctypes.data, len(e.depths), e.depth_ranges.ctypes.data,
+                                   e.depths.ctypes.data, len(e.ba_x), e.ba_x.ctypes.data, e.ba_c.ctypes.data)
+        out = (C.c_int * 2)()
+        self.lib.hh_env_flags(h, out)
+        self.lib.hh_env_destroy(h)
+        return int(out[0]), int(out[1])
 
     def shoot_fan(self, oenv, source_depth, source_range, receiver_range, angles, range_save=None, rtol=1e-9,
                   atol=1e-6, terminate_backwards=True, max_bounces=1 << 20):

@@ -29,6 +29,14 @@ __attribute__((visibility("default"))) void* hh_env_create(int n_r, int n_z, con
 
 __attribute__((visibility("default"))) void hh_env_destroy(void* e) { delete static_cast<hh_env*>(e); }
 
+// staging-time decisions about the cell guess: out = {z_cubic, spec_off}
+__attribute__((visibility("default"))) void hh_env_flags(void* e, int* out)
+{
+    const prt_env_view& V = static_cast<hh_env*>(e)->view;
+    out[0] = V.z_cubic;
+    out[1] = V.spec_off;
+}
+
 // same output layout as prt_shoot_fan: traj [3][n_rays][n_save], final [3][n_rays], counters [6][n_rays]
 __attribute__((visibility("default"))) int hh_shoot_fan(void* env, int64_t n_rays, const double* angles_deg,
                                                          const double* y0s, double source_depth, double source_range,

@@ -88,6 +88,32 @@ def test_nonuniform_grid_and_short_bathymetry(harness):
     assert_same_fan(o, h, "non-uniform grid")
 
 
+def test_cell_guess_rating(harness):
+    """Uniform grids keep the linear guess, the flat-earth depth grid gets the refined one, irregular grids
+    switch the speculative trial step off (results are exact in every case; this only decides speed)."""
+    assert harness.env_flags(oracle_env_from(make_env(cases.config2_arrays()), False)) == (0, 0)
+    assert harness.env_flags(oracle_env_from(make_env(cases.config1_arrays(), flat=True), True)) == (1, 0)
+    rng = np.random.default_rng(3)
+    a = cases.config2_arrays(n_r=40, n_z=90, R=1e5)
+    z = np.sort(np.concatenate(([0.0, 5500.0], rng.uniform(0, 5500.0, 88))))
+    a.update(z=z, c=np.array([cases.munk_ssp(z, 1300.0) for _ in a["r"]]))
+    assert harness.env_flags(oracle_env_from(make_env(a), False))[1] == 1
+
+
+def test_abscissae_on_grid_nodes(harness):
+    """Source depth, receiver range and save points exactly on grid nodes, launch angles including 0: weights
+    of exactly 0 and 1 cannot be proven by the speculative lookup, so these steps take the exact re-run."""
+    a = cases.config2_arrays(n_r=51, n_z=551, R=1e5)  # 2 km x 10 m grid: nodes at round numbers
+    assert a["z"][100] == 1000.0 and a["r"][25] == 50e3
+    oenv = oracle_env_from(make_env(a), False)
+    ang = np.array([-9.0, -3.0, -1e-9, 0.0, 1e-9, 3.0, 9.0, 14.0])
+    for R, n_save in ((50e3, 26), (1e5, 51)):
+        o, h = _both(harness, oenv, 1000.0, 0.0, R, ang, n_save)
+        assert_same_fan(o, h, f"node-aligned, R={R}")
+    o, h = _both(harness, oenv, 0.0, 2e3, 8e4, np.linspace(-5, 12, 9), 40)  # source on the surface node and a range node
+    assert_same_fan(o, h, "source on the surface")
+
+
 def test_backwards_mirrored_environment(harness):
     a = cases.config2_arrays()
     oenv = oracle_env_from(make_env(a), False, mirror=True)

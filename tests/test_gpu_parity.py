@@ -50,11 +50,27 @@ CASES = {
     "mirrored": dict(env="cfg2", flat=False, zs=300.0, r0=-4e5, R=-1e5, ang=np.linspace(-15, 15, 97), n=120, mirror=True),
     "single_ray": dict(env="cfg2", flat=False, zs=1000.0, r0=0.0, R=200e3, ang=np.array([7.5]), n=33),
     "ragged_33_rays": dict(env="cfg2", flat=False, zs=1000.0, r0=0.0, R=200e3, ang=np.linspace(-14, 14, 33), n=2),
+    # source depth, receiver range and save points exactly on grid nodes: weights of exactly 0 / 1 force the exact re-run
+    "node_aligned": dict(env="round", flat=False, zs=1000.0, r0=0.0, R=50e3,
+                         ang=np.array([-9.0, -3.0, -1e-9, 0.0, 1e-9, 3.0, 9.0, 14.0]), n=26),
+    "source_on_surface": dict(env="round", flat=False, zs=0.0, r0=2e3, R=8e4, ang=np.linspace(-5, 12, 9), n=40),
+    # irregular depth grid: the staging code switches the speculative trial step off
+    "irregular_depths": dict(env="irregular", flat=False, zs=700.0, r0=0.0, R=1e5, ang=np.linspace(-20, 20, 65), n=90),
 }
 
 
 def _env(pr, name):
-    return pr.OceanEnvironment2D() if name == "default" else make_env(cases.config2_arrays())
+    if name == "default":
+        return pr.OceanEnvironment2D()
+    if name == "round":
+        return make_env(cases.config2_arrays(n_r=51, n_z=551, R=1e5))  # 2 km x 10 m grid, nodes at round numbers
+    if name == "irregular":
+        rng = np.random.default_rng(3)
+        a = cases.config2_arrays(n_r=40, n_z=90, R=1e5)
+        z = np.sort(np.concatenate(([0.0, 5500.0], rng.uniform(0, 5500.0, 88))))
+        a.update(z=z, c=np.array([cases.munk_ssp(z, 1300.0) for _ in a["r"]]))
+        return make_env(a)
+    return make_env(cases.config2_arrays())
 
 
 @pytest.mark.parametrize("name", list(CASES))
