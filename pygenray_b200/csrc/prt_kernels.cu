@@ -80,35 +80,34 @@ static int park_wait_setting()
     return g_park_wait;
 }
 
-// Parked step records: [field][thread] doubles in shared memory (structure of arrays: conflict-free)
-#define PRT_PARK_FIELDS 20
+// A lane whose accepted step fired an event parks until the warp's root searches run.  Only the step's end
+// abscissa and its event mask are parked (2 doubles per thread in shared memory): the ray still holds the
+// state at the START of that step, so the step record (stage values -> dense-output rows) is rebuilt by
+// repeating the trial step -- same inputs, same arithmetic, same bits -- once per reflection.  Keeping the
+// parked record this small leaves the kernel with 2 KB of shared memory per block, i.e. practically the
+// whole 256 KB of an SM as L1 for the sound-speed grid (the 2001 x 1201 internal-wave grid of config 3 runs
+// 3.6x slower when a third of the L1 is taken away; profiles/r01_variants.md).
+#define PRT_PARK_FIELDS 2
 struct prt_park_slot {
     double* base;  // &park[0][threadIdx.x]
     __device__ __forceinline__ void store(const prt_step& st) const
     {
-        double* q = base;
-        const int n = blockDim.x;
-        q[0 * n] = st.t_old; q[1 * n] = st.t_new; q[2 * n] = st.h; q[3 * n] = st.inv_h;
-        q[4 * n] = st.yT; q[5 * n] = st.yz; q[6 * n] = st.yp;
-        q[7 * n] = st.nf0; q[8 * n] = st.nf1; q[9 * n] = st.nf2;
-        q[10 * n] = st.qT.q1; q[11 * n] = st.qT.q2; q[12 * n] = st.qT.q3;
-        q[13 * n] = st.qz.q1; q[14 * n] = st.qz.q2; q[15 * n] = st.qz.q3;
-        q[16 * n] = st.qp.q1; q[17 * n] = st.qp.q2; q[18 * n] = st.qp.q3;
-        q[19 * n] = __longlong_as_double(((long long)st.active << 1) | (st.finished ? 1 : 0));
+        base[0] = st.t_new;
+        base[blockDim.x] = __longlong_as_double((long long)st.active);
     }
-    __device__ __forceinline__ void load(prt_step& st) const
+    // rebuild the step record of the parked step of ray r (state still at the start of that step)
+    template <bool SAVE>
+    __device__ __forceinline__ void rebuild(const prt_envp& E, const prt_shot& S, const prt_ray<SAVE>& r, prt_step& st) const
     {
-        const double* q = base;
-        const int n = blockDim.x;
-        st.t_old = q[0 * n]; st.t_new = q[1 * n]; st.h = q[2 * n]; st.inv_h = q[3 * n];
-        st.yT = q[4 * n]; st.yz = q[5 * n]; st.yp = q[6 * n];
-        st.nf0 = q[7 * n]; st.nf1 = q[8 * n]; st.nf2 = q[9 * n];
-        st.qT.q1 = q[10 * n]; st.qT.q2 = q[11 * n]; st.qT.q3 = q[12 * n];
-        st.qz.q1 = q[13 * n]; st.qz.q2 = q[14 * n]; st.qz.q3 = q[15 * n];
-        st.qp.q1 = q[16 * n]; st.qp.q2 = q[17 * n]; st.qp.q3 = q[18 * n];
-        const long long f = __double_as_longlong(q[19 * n]);
-        st.active = (int32_t)(f >> 1);
-        st.finished = (f & 1) != 0;
+        const double tn = base[0];
+        st.active = (int32_t)__double_as_longlong(base[blockDim.x]);
+        st.t_old = r.t; st.t_new = tn; st.h = tn - r.t;
+        st.finished = (tn - S.x_end >= 0.0);
+        prt_try v;
+        prt_rk_try_exact<true>(&E.v, E.grid, S.rtol, S.atol, r.t, st.h, r.T, r.z, r.p, r.f0, r.f1, r.f2, &v);
+        st.qT = v.qT; st.qz = v.qz; st.qp = v.qp; st.inv_h = v.inv_h;
+        st.yT = v.nT; st.yz = v.nz; st.yp = v.np_;
+        st.nf0 = v.k7T; st.nf1 = v.k7z; st.nf2 = v.k7p;
         st.root = 0.0;
         st.event = -1;
     }
@@ -152,7 +151,7 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SA
             if (!stepping || waited > park_wait) {
                 if (r.phase == PRT_PH_ROOT) {
                     prt_step st;
-                    park.load(st);
+                    park.rebuild<SAVE>(E, S, r, st);
                     r.solve_roots(E, st);
                     r.finish_terminal(E, S, sink, st);
                 }
@@ -644,6 +643,17 @@ static int shoot_fan_impl(const prt_env_t* env, int64_t n_rays, int64_t rays_per
     const unsigned grid = (unsigned)((n_warps * 32 + block - 1) / block);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool zc = env->view.z_cubic != 0;  // refined depth guess compiled in only for stretched depth grids
+    static int carve = -2;  // dev experiment: PRT_CARVEOUT = preferred shared-memory carve-out in percent
+    if (carve == -2) {
+        const char* e = getenv("PRT_CARVEOUT");
+        carve = e ? atoi(e) : -1;
+        if (carve >= 0) {
+            cudaFuncSetAttribute(prt_fan_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(prt_fan_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(prt_fan_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+            cudaFuncSetAttribute(prt_fan_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        }
+    }
     if (save) {
         if (zc) prt_fan_kernel<true, true><<<grid, block, 0, s>>>(env->view, P);
         else prt_fan_kernel<true, false><<<grid, block, 0, s>>>(env->view, P);

@@ -16,9 +16,12 @@ w = bench.workload(a.workload)
 env = bench.make_env(pr, w["arrays"], w["flatearth"])
 denv = pr.DeviceEnvironment(*pr._unpack_envi(env, flatearth=w["flatearth"]), device=0)
 ang = np.linspace(-a.lim, a.lim, a.n)
+best = 1e9
 for _ in range(a.reps):
     torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     res = pr.shoot_fan_arrays(denv, w["source_depth"], 0.0, w["receiver_range"], angles=ang, num_range_save=a.save, counters=True, to_host=False)
     e1.record(); torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1))
     print(f"n={a.n} save={a.save}: {e0.elapsed_time(e1):.2f} ms")
+print(f"{a.workload} n={a.n} save={a.save} lim={a.lim}: best of {a.reps} = {best:.2f} ms")
