@@ -17,10 +17,22 @@ BLOCK = 32
 RECORD_WIDTH = 6  # T, z, p, n_bottom, n_surface, status
 
 
+_SHARD_CACHE = {}
+
+
 def shard_indices(n_rays, rank, world, block=BLOCK):
-    """Indices of the rays owned by ``rank``: blocks of ``block`` consecutive angles dealt round-robin."""
-    idx = np.arange(n_rays, dtype=np.int64)
-    return idx[(idx // block) % world == rank]
+    """Indices of the rays owned by ``rank``: blocks of ``block`` consecutive angles dealt round-robin.
+    (Cached per fan shape: for a 1M-ray fan the index arithmetic costs more host time than a rank's kernel.)"""
+    key = (int(n_rays), int(rank), int(world), int(block))
+    mine = _SHARD_CACHE.get(key)
+    if mine is None:
+        idx = np.arange(n_rays, dtype=np.int64)
+        mine = idx[(idx // block) % world == rank]
+        mine.setflags(write=False)
+        if len(_SHARD_CACHE) >= 64:
+            _SHARD_CACHE.clear()
+        _SHARD_CACHE[key] = mine
+    return mine
 
 
 def shard_sizes(n_rays, world, block=BLOCK):
