@@ -261,8 +261,12 @@ __global__ void prt_sign_changes_kernel(int64_t n_rays, int32_t n_save, const do
 // thread-level parallelism instead of idle schedulers.  Large fans use full warps.
 static std::atomic<int> g_concurrency{1};
 
+static std::atomic<int> g_lanes_override{0};
+
 static int pick_lanes(int64_t n_units, int device)
 {
+    const int ov = g_lanes_override.load();
+    if (ov == 1 || ov == 2 || ov == 4 || ov == 8 || ov == 16 || ov == 32) return ov;
     n_units *= g_concurrency.load();  // several fans in flight on different streams share the chip
     static int forced = -1;
     if (forced < 0) {
@@ -520,6 +524,11 @@ PRT_API long long prt_debug_cold(void)
 int prt_set_concurrency(int n_fans)
 {
     g_concurrency.store(n_fans > 0 ? n_fans : 1);
+    return PRT_SUCCESS;
+}
+int prt_set_lanes(int lanes)
+{
+    g_lanes_override.store(lanes);
     return PRT_SUCCESS;
 }
 const char* prt_last_error(void) { return g_last_error.c_str(); }
