@@ -65,6 +65,7 @@ struct prt_fan_params {
     int32_t park_wait;
     int32_t lanes;  // rays per warp (32, 16, 8, 4, 2 or 1): small fans use partly filled warps, see pick_lanes()
     int64_t rays_per_env;  // ensembles: ray r belongs to realisation r / rays_per_env and uses angles[r % rays_per_env]
+    int32_t reorder;       // 1: second half of the blocks takes its chunks in reverse order (see prt_fan_kernel)
 };
 
 // Lanes that hit a boundary wait (at most this many step attempts of the other lanes) so that the
@@ -173,7 +174,13 @@ __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_fan_kernel(const __gr
 {
     // P.lanes rays per warp (lanes >= P.lanes idle); whole warps stay in the kernel: the driver is warp-synchronous
     const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // Blocks start roughly in index order and the cost of a ray grows with |launch angle| (reflections), so a fan
+    // sorted by angle would start its most expensive chunks LAST and end on a long, poorly filled tail.  The second
+    // half of the blocks therefore walks the fan backwards: both halves go from steep to shallow and the launch
+    // ends on the cheapest rays.  (Any order is correct; unsorted fans are no worse off than before.)
+    const unsigned nb = gridDim.x, half = nb >> 1;
+    const unsigned blk = (blockIdx.x < half || P.reorder == 0) ? blockIdx.x : nb - 1u - (blockIdx.x - half);
+    const int64_t warp = ((int64_t)blk * blockDim.x + threadIdx.x) >> 5;
     const int64_t ray = warp * P.lanes + lane;
     const bool live = (lane < P.lanes) && (ray < P.n_rays);
     // ensembles: same tables, this ray's realisation of the sound-speed grid
@@ -645,6 +652,14 @@ static int shoot_fan_impl(const prt_env_t* env, int64_t n_rays, int64_t rays_per
     P.stored_convention = stored_convention;
     P.park_wait = park_wait_setting();
     P.rays_per_env = rays_per_env;
+    {
+        static int reorder = -1;  // PRT_REORDER=0 switches the block order off (experiments)
+        if (reorder < 0) {
+            const char* e = getenv("PRT_REORDER");
+            reorder = e ? atoi(e) : 1;
+        }
+        P.reorder = reorder;
+    }
     if (P.rtol < 100.0 * PRT_EPS) P.rtol = 100.0 * PRT_EPS;  // validate_tol (scipy common.py:44-60)
     P.lanes = pick_lanes(n_rays, env->device);
     const int block = 128;
