@@ -91,6 +91,25 @@ def test_fan_options_bit_identical(pr, rtol, tb):
     assert_same_fan(o, g, f"rtol={rtol} terminate_backwards={tb}")
 
 
+def test_launch_hints_do_not_change_results(pr):
+    """Rays per warp (prt_set_lanes) and the concurrency hint only lay rays out over warps differently: the
+    arrival table, trajectories and work counters are bit-identical for every setting."""
+    env = make_env(cases.config2_arrays())
+    ang = np.linspace(-15, 15, 203)
+    L = pr._lib.load()
+    ref = _gpu_fan(pr, env, False, 1000.0, 0.0, 300e3, ang, 61)
+    try:
+        for lanes in (1, 2, 4, 8, 16, 32):
+            assert L.prt_set_lanes(lanes) == 0
+            assert_same_fan(ref, _gpu_fan(pr, env, False, 1000.0, 0.0, 300e3, ang, 61), f"lanes={lanes}")
+        L.prt_set_lanes(0)
+        L.prt_set_concurrency(8)
+        assert_same_fan(ref, _gpu_fan(pr, env, False, 1000.0, 0.0, 300e3, ang, 61), "concurrency hint")
+    finally:
+        L.prt_set_lanes(0)
+        L.prt_set_concurrency(1)
+
+
 def test_empty_fan_and_argument_errors(pr):
     env = make_env(cases.config2_arrays())
     denv = pr.DeviceEnvironment(*pr._unpack_envi(env, flatearth=False))
