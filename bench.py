@@ -389,8 +389,8 @@ def run_b200(args):
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / (fp64_peak / 1e12) if fp64_peak > 0 else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload from the
-                         # ncu --set full capture summarised in profiles/r01_ncu_fan.md (12.4 MB + 199.4 MB)
-                         "traffic": 211.7e6 if (w["name"] == "cfg2" and world == 1) else None,
+                         # ncu --set full capture summarised in profiles/r01_ncu_fan.md (11.8 MB + 200.3 MB)
+                         "traffic": 212.0e6 if (w["name"] == "cfg2" and world == 1) else None,
                          "traffic_algorithmic_bytes": out_bytes,
                          "kernel": "prt_fan_kernel", "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
                          "peak_source": "DFMA microbenchmark (prt_measure_fp64_peak) in this run; "
