@@ -1087,9 +1087,6 @@ struct prt_ray {
         prt_try v;
         bool ok = (E.v.spec_off == 0);  // irregular grids: straight to the exact lookup
         if (ok) prt_rk_try<false, SAVE>(E, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, v, ok);
-#if defined(PRT_ASSUME_OK)
-        ok = true;
-#endif
         if (!ok) {
             prt_try cold;
             prt_rk_try_exact<SAVE>(&E.v, E.grid, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, &cold);
