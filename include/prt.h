@@ -119,6 +119,18 @@ PRT_API int prt_ensemble_create(int device, int32_t n_env, int32_t n_r, int32_t 
                                 const double *zin, const double *cin, const double *cpin, int32_t n_b,
                                 const double *depth_ranges, const double *depths, int32_t n_ba,
                                 const double *ba_x, const double *ba_c, prt_env_t **out);
+/*
+ * The same for sound-speed grids that already live in device memory (c_dev: [n_env][n_r][n_z] doubles on
+ * `device`), e.g. perturbed realisations generated on the GPU: the depth derivative the reference takes in
+ * _unpack_envi (sound_speed.differentiate("depth") = np.gradient(c, z, axis=depth, edge_order=1),
+ * launch_rays.py:728-733) is formed by a kernel with numpy's operations in numpy's order (bit-identical to the
+ * host route), interleaved with c, and nothing but the coordinate tables crosses PCIe.  n_env = 1 stages a
+ * single environment.  Synchronises `stream` before returning.
+ */
+PRT_API int prt_ensemble_create_dev(int device, int32_t n_env, int32_t n_r, int32_t n_z, const double *rin,
+                                    const double *zin, const double *c_dev, int32_t n_b,
+                                    const double *depth_ranges, const double *depths, int32_t n_ba,
+                                    const double *ba_x, const double *ba_c, void *stream, prt_env_t **out);
 PRT_API int prt_env_destroy(prt_env_t *env);
 /* bytes of device memory held by the environment */
 PRT_API int64_t prt_env_device_bytes(const prt_env_t *env);

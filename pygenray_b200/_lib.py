@@ -22,6 +22,7 @@ DEFAULT_MAX_BOUNCES = 1 << 20
 
 EXPORTS = (
     "prt_abi_version", "prt_set_concurrency", "prt_set_lanes", "prt_last_error", "prt_device_count", "prt_env_create", "prt_ensemble_create",
+    "prt_ensemble_create_dev",
     "prt_shoot_ensemble", "prt_env_destroy",
     "prt_env_device_bytes", "prt_shoot_fan", "prt_shoot_fan_host", "prt_pack_arrivals", "prt_count_brackets", "prt_fill_brackets",
     "prt_refine_workspace_bytes", "prt_refine_brackets", "prt_launch_count", "prt_measure_fp64_peak",
@@ -58,6 +59,8 @@ def load():
     L.prt_env_create.argtypes = [C.c_int, i32, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, C.POINTER(vp)]
     L.prt_ensemble_create.restype = C.c_int
     L.prt_ensemble_create.argtypes = [C.c_int, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, C.POINTER(vp)]
+    L.prt_ensemble_create_dev.restype = C.c_int
+    L.prt_ensemble_create_dev.argtypes = [C.c_int, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, C.POINTER(vp)]
     L.prt_env_destroy.restype = C.c_int
     L.prt_env_destroy.argtypes = [vp]
     L.prt_env_device_bytes.restype = i64

@@ -18,9 +18,40 @@
 #include "prt_core.h"
 
 struct prt_env_blob {
-    std::vector<unsigned char> bytes;
-    prt_env_view view;  // pointers hold byte OFFSETS into bytes
+    std::vector<unsigned char> bytes;  // the layout from byte `grid_bytes` on (everything when grid_bytes == 0)
+    prt_env_view view;                 // pointers hold byte OFFSETS into the full layout
+    size_t total_bytes = 0, grid_bytes = 0;
 };
+
+// np.gradient(f, z, axis=depth, edge_order=1) as coefficient tables (numpy/lib/_function_base_impl.py gradient):
+// uniform spacing (all diff(z) equal): interior (f[j+1] - f[j-1]) / (2 dz); otherwise a f[j-1] + b f[j] + c f[j+1];
+// one-sided first differences at the two ends.  Same operations in the same order as numpy, hence the same bits.
+struct prt_gradient_tables {
+    int uniform;
+    double two_dz, dz_first, dz_last;
+    std::vector<double> a, b, c;  // [n_z], interior entries only
+};
+
+static inline prt_gradient_tables prt_gradient_coefficients(const double* z, int n)
+{
+    prt_gradient_tables g;
+    std::vector<double> d((size_t)n - 1);
+    for (int j = 0; j < n - 1; ++j) d[j] = z[j + 1] - z[j];
+    g.uniform = 1;
+    for (int j = 1; j < n - 1; ++j)
+        if (d[j] != d[0]) g.uniform = 0;
+    g.two_dz = 2.0 * d[0];
+    g.dz_first = d[0];
+    g.dz_last = g.uniform ? d[0] : d[n - 2];
+    g.a.assign(n, 0.0); g.b.assign(n, 0.0); g.c.assign(n, 0.0);
+    for (int j = 1; j < n - 1; ++j) {
+        const double dx1 = d[j - 1], dx2 = d[j];
+        g.a[j] = -(dx2) / (dx1 * (dx1 + dx2));
+        g.b[j] = (dx2 - dx1) / (dx1 * dx2);
+        g.c[j] = dx1 / (dx2 * (dx1 + dx2));
+    }
+    return g;
+}
 
 static inline size_t prt_align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
@@ -127,6 +158,9 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
                                const double* cpin, int n_b, const double* depth_ranges, const double* depths,
                                int n_ba, const double* ba_x, const double* ba_c, prt_env_blob& out, int n_env = 1)
 {
+    // cin == cpin == nullptr: tables only -- the grid (first region of the layout) is filled on the device by
+    // prt_stage_grid_kernel; out.bytes then holds the layout from the end of the grid region on (out.grid_bytes)
+    const bool host_grid = (cin != nullptr);
     if (n_r < 2 || n_z < 2 || n_b < 2 || n_ba < 2 || n_env < 1) return 1;
     size_t o_grid = 0;
     size_t o_rpair = o_grid + prt_align256(sizeof(prt_d2) * (size_t)n_r * n_z * (size_t)n_env);
@@ -144,13 +178,17 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
     size_t o_bax = o_zxr + prt_align256(sizeof(prt_d2) * (size_t)(n_z - 1));
     size_t o_bac = o_bax + prt_align256(sizeof(double) * (size_t)n_ba);
     size_t total = o_bac + prt_align256(sizeof(double) * 4 * (size_t)(n_ba - 1));
-    out.bytes.assign(total, 0);
-    unsigned char* base = out.bytes.data();
-    prt_d2* grid = reinterpret_cast<prt_d2*>(base + o_grid);
-    const size_t n_nodes = (size_t)n_r * n_z * (size_t)n_env;
-    for (size_t k = 0; k < n_nodes; ++k) {
-        grid[k].x = cin[k];
-        grid[k].y = cpin[k];
+    out.total_bytes = total;
+    out.grid_bytes = host_grid ? 0 : o_rpair;
+    out.bytes.assign(total - out.grid_bytes, 0);
+    unsigned char* base = out.bytes.data() - out.grid_bytes;  // offsets below stay those of the full layout
+    if (host_grid) {
+        prt_d2* grid = reinterpret_cast<prt_d2*>(base + o_grid);
+        const size_t n_nodes = (size_t)n_r * n_z * (size_t)n_env;
+        for (size_t k = 0; k < n_nodes; ++k) {
+            grid[k].x = cin[k];
+            grid[k].y = cpin[k];
+        }
     }
     prt_pack_pairs(reinterpret_cast<prt_d2*>(base + o_rpair), rin, n_r);
     prt_pack_pairs(reinterpret_cast<prt_d2*>(base + o_zpair), zin, n_z);

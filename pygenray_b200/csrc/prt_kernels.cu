@@ -499,6 +499,35 @@ __global__ void prt_pack_arrivals_kernel(int64_t n, const double* __restrict__ f
 }
 
 // ---------------------------------------------------------------------------------------------
+// Device-side staging of sound-speed grids that already live in HBM (perturbed realisations of a tomography
+// ensemble generated on the GPU): grid[k] = {c, dc/dz} with dc/dz = np.gradient(c, z, axis=depth, edge_order=1),
+// the derivative _unpack_envi takes (launch_rays.py:728-733); same operations in numpy's order, hence its bits.
+__global__ void prt_stage_grid_kernel(int64_t n_nodes, int32_t n_z, const double* __restrict__ c, int uniform,
+                                      double two_dz, double dz_first, double dz_last, const double* __restrict__ ga,
+                                      const double* __restrict__ gb, const double* __restrict__ gc,
+                                      prt_d2* __restrict__ grid)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_nodes) return;
+    const int j = (int)(k % n_z);
+    const double f = c[k];
+    double d;
+    if (j == 0) {
+        d = __ddiv_rn(__dsub_rn(c[k + 1], f), dz_first);
+    } else if (j == n_z - 1) {
+        d = __ddiv_rn(__dsub_rn(f, c[k - 1]), dz_last);
+    } else if (uniform) {
+        d = __ddiv_rn(__dsub_rn(c[k + 1], c[k - 1]), two_dz);
+    } else {
+        d = __dadd_rn(__dadd_rn(__dmul_rn(ga[j], c[k - 1]), __dmul_rn(gb[j], f)), __dmul_rn(gc[j], c[k + 1]));
+    }
+    prt_d2 v;
+    v.x = f;
+    v.y = d;
+    grid[k] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP64 FMA-pipe peak: 8 independent DFMA chains per thread
 __global__ void prt_fp64_peak_kernel(double* out, int iters, double a, double b)
 {
@@ -602,6 +631,52 @@ int prt_ensemble_create(int device, int32_t n_env, int32_t n_r, int32_t n_z, con
     env->device = device;
     env->dev_blob = dev;
     env->bytes = blob.bytes.size();
+    env->view = prt_env_rebase(blob.view, dev);
+    *out = env;
+    return PRT_SUCCESS;
+}
+
+int prt_ensemble_create_dev(int device, int32_t n_env, int32_t n_r, int32_t n_z, const double* rin, const double* zin,
+                            const double* c_dev, int32_t n_b, const double* depth_ranges, const double* depths,
+                            int32_t n_ba, const double* ba_x, const double* ba_c, void* stream, prt_env_t** out)
+{
+    if (!out || !rin || !zin || !c_dev || !depth_ranges || !depths || !ba_x || !ba_c)
+        return fail(PRT_ERR_ARG, "prt_ensemble_create_dev: null pointer");
+    if (prt_device_count() <= device || device < 0)
+        return fail(PRT_ERR_NO_DEVICE, "prt_ensemble_create_dev: no such CUDA device (this library has no CPU path)");
+    prt_env_blob blob;
+    if (prt_env_pack(n_r, n_z, rin, zin, nullptr, nullptr, n_b, depth_ranges, depths, n_ba, ba_x, ba_c, blob, n_env))
+        return fail(PRT_ERR_ARG, "prt_ensemble_create_dev: n_env >= 1 and every grid needs at least 2 points");
+    PRT_CUDA(cudaSetDevice(device));
+    const prt_gradient_tables g = prt_gradient_coefficients(zin, n_z);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned char* dev = nullptr;
+    double* coef = nullptr;
+    PRT_CUDA(cudaMalloc(&dev, blob.total_bytes));
+    cudaError_t e = cudaMalloc(&coef, sizeof(double) * 3 * (size_t)n_z);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dev + blob.grid_bytes, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(coef, g.a.data(), sizeof(double) * n_z, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(coef + n_z, g.b.data(), sizeof(double) * n_z, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(coef + 2 * (size_t)n_z, g.c.data(), sizeof(double) * n_z, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        const int64_t n_nodes = (int64_t)n_env * n_r * n_z;
+        prt_stage_grid_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s>>>(
+            n_nodes, n_z, c_dev, g.uniform, g.two_dz, g.dz_first, g.dz_last, coef, coef + n_z, coef + 2 * (size_t)n_z,
+            reinterpret_cast<prt_d2*>(dev));
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // the host tables and `coef` go out of scope
+    cudaFree(coef);
+    if (e != cudaSuccess) {
+        cudaFree(dev);
+        return fail(PRT_ERR_CUDA, std::string("prt_ensemble_create_dev: ") + cudaGetErrorString(e));
+    }
+    prt_env* env = new prt_env;
+    env->device = device;
+    env->dev_blob = dev;
+    env->bytes = blob.total_bytes;
     env->view = prt_env_rebase(blob.view, dev);
     *out = env;
     return PRT_SUCCESS;

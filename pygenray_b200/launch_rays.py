@@ -167,6 +167,45 @@ class DeviceEnsemble(DeviceEnvironment):
         self.device_bytes = int(L.prt_env_device_bytes(handle))
 
 
+def _ensemble_from_device(cls, c_stack, rin, zin, depths, depth_ranges, bottom_angles):
+    """``n_env`` realisations that already live on the GPU: ``c_stack`` is a CUDA float64 tensor
+    ``[n_env][range][depth]`` (e.g. perturbations generated with torch).  The depth derivative
+    (``sound_speed.differentiate("depth")`` of the reference, launch_rays.py:728-733) is formed on the device with
+    numpy's operations in numpy's order -- results are bit-identical to staging ``np.gradient`` from the host --
+    and only the coordinate tables cross PCIe (``prt_ensemble_create_dev``)."""
+    L = _lib.require_gpu()
+    import torch  # noqa: PLC0415
+
+    if not (isinstance(c_stack, torch.Tensor) and c_stack.is_cuda and c_stack.dtype == torch.float64):
+        raise TypeError("c_stack must be a CUDA float64 tensor [n_env][range][depth]")
+    rin, zin = _as_f64(rin), _as_f64(zin)
+    depths, depth_ranges = _as_f64(depths), _as_f64(depth_ranges)
+    if c_stack.ndim == 2:
+        c_stack = c_stack.unsqueeze(0)
+    if c_stack.ndim != 3 or tuple(c_stack.shape[1:]) != (rin.shape[0], zin.shape[0]):
+        raise ValueError(f"ensemble sound speed must be [n_env][range][depth], got {tuple(c_stack.shape)}")
+    c_stack = c_stack.contiguous()
+    ba_x, ba_c = bottom_angle_ppoly(depth_ranges, bottom_angles)
+    self = cls.__new__(cls)
+    self.device = int(c_stack.device.index)
+    handle = C.c_void_p()
+    with torch.cuda.device(c_stack.device):
+        rc = L.prt_ensemble_create_dev(
+            self.device, c_stack.shape[0], rin.shape[0], zin.shape[0], rin.ctypes.data, zin.ctypes.data,
+            C.c_void_p(c_stack.data_ptr()), depths.shape[0], depth_ranges.ctypes.data, depths.ctypes.data,
+            ba_x.shape[0], ba_x.ctypes.data, ba_c.ctypes.data, C.c_void_p(torch.cuda.current_stream().cuda_stream),
+            C.byref(handle),
+        )
+    _lib.check(rc, "prt_ensemble_create_dev")
+    self._h = handle
+    self.n_env, self.n_r, self.n_z = int(c_stack.shape[0]), rin.shape[0], zin.shape[0]
+    self.device_bytes = int(L.prt_env_device_bytes(handle))
+    return self
+
+
+DeviceEnsemble.from_device = classmethod(_ensemble_from_device)
+
+
 def shoot_ensemble_arrays(dens, source_depth, source_range, receiver_range, angles, n_env=None, num_range_save=0,
                           rtol=1e-9, terminate_backwards=True, counters=False, max_bounces=_lib.DEFAULT_MAX_BOUNCES,
                           to_host=True):

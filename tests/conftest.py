@@ -61,6 +61,7 @@ class HostHarness:
         self.lib.hh_env_create.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]
         self.lib.hh_env_destroy.argtypes = [vp]
         self.lib.hh_env_flags.argtypes = [vp, vp]
+        self.lib.hh_gradient.argtypes = [vp, C.c_int, vp, vp]
         self.lib.hh_shoot_fan.argtypes = [vp, C.c_int64, vp, vp, d, d, d, d, d, C.c_int, C.c_int, vp, vp, vp, vp,
                                           vp, vp, vp, C.c_int]
 

@@ -29,6 +29,18 @@ __attribute__((visibility("default"))) void* hh_env_create(int n_r, int n_z, con
 
 __attribute__((visibility("default"))) void hh_env_destroy(void* e) { delete static_cast<hh_env*>(e); }
 
+// np.gradient(f, z, edge_order=1) through the coefficient tables the device staging kernel uses (same operations)
+__attribute__((visibility("default"))) void hh_gradient(const double* z, int n, const double* f, double* out)
+{
+    const prt_gradient_tables g = prt_gradient_coefficients(z, n);
+    for (int j = 0; j < n; ++j) {
+        if (j == 0) out[j] = (f[1] - f[0]) / g.dz_first;
+        else if (j == n - 1) out[j] = (f[j] - f[j - 1]) / g.dz_last;
+        else if (g.uniform) out[j] = (f[j + 1] - f[j - 1]) / g.two_dz;
+        else out[j] = (g.a[j] * f[j - 1] + g.b[j] * f[j]) + g.c[j] * f[j + 1];
+    }
+}
+
 // staging-time decisions about the cell guess: out = {z_cubic, spec_off}
 __attribute__((visibility("default"))) void hh_env_flags(void* e, int* out)
 {

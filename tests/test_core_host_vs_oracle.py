@@ -100,6 +100,21 @@ def test_cell_guess_rating(harness):
     assert harness.env_flags(oracle_env_from(make_env(a), False))[1] == 1
 
 
+def test_depth_derivative_tables_equal_numpy_gradient(harness):
+    """The device-side staging of GPU-resident sound-speed grids (prt_ensemble_create_dev) forms dc/dz from
+    coefficient tables; they must reproduce np.gradient(c, z, edge_order=1) -- what _unpack_envi hands to the
+    integrator -- bit for bit, on uniform, linspace, stretched and irregular depth grids."""
+    rng = np.random.default_rng(11)
+    grids = [np.arange(0.0, 6000.0, 1.0), np.linspace(0, 5500, 500), np.linspace(0, 5500, 500) * (1 + 1e-4 * np.linspace(0, 1, 500)),
+             np.sort(np.concatenate(([0.0, 4000.0], rng.uniform(0, 4000, 77)))), np.array([0.0, 10.0]), np.array([0.0, 3.0, 11.0])]
+    for z in grids:
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        f = np.ascontiguousarray(cases.munk_ssp(z, 1300.0) + rng.normal(0, 0.3, z.shape))
+        out = np.empty_like(f)
+        harness.lib.hh_gradient(z.ctypes.data, len(z), f.ctypes.data, out.ctypes.data)
+        assert np.array_equal(out, np.gradient(f, z, edge_order=1)), len(z)
+
+
 def test_abscissae_on_grid_nodes(harness):
     """Source depth, receiver range and save points exactly on grid nodes, launch angles including 0: weights
     of exactly 0 and 1 cannot be proven by the speculative lookup, so these steps take the exact re-run."""

@@ -281,6 +281,35 @@ def test_ensemble_launch_bit_identical_per_realisation(pr):
         pr.shoot_fan_arrays(dens, 1000.0, 0.0, 1e5, angles=ang)  # an ensemble handle needs the ensemble call
 
 
+@pytest.mark.parametrize("grid", ["linspace", "flat_earth", "irregular"])
+def test_ensemble_staged_on_device_equals_host_staging(pr, grid):
+    """prt_ensemble_create_dev: sound-speed realisations that already live in HBM, depth derivative formed by a
+    kernel == the host route (np.gradient, interleaving, one big H2D copy): bit-identical fans, also when the depth
+    grid is not uniform (np.gradient switches to its three-point non-uniform formula)."""
+    import torch
+
+    a = cases.config2_arrays()
+    if grid == "flat_earth":
+        a["z"] = a["z"] * (1 + a["z"] / 6.371e6 * (0.5 + a["z"] / 6.371e6 / 3))
+    elif grid == "irregular":
+        rng = np.random.default_rng(5)
+        a["z"] = np.sort(np.concatenate(([0.0, 5500.0], rng.uniform(0, 5500.0, len(a["z"]) - 2))))
+    stack = np.stack([cases.config5_realisation(i)["c"] for i in range(4)])
+    env = make_env(dict(a, c=stack[0]))
+    arrs = pr._unpack_envi(env, flatearth=False)
+    cp_stack = np.gradient(stack, arrs[3], axis=2, edge_order=1)
+    host = pr.DeviceEnsemble(stack, cp_stack, *arrs[2:])
+    dev = pr.DeviceEnsemble.from_device(torch.from_numpy(stack).cuda(), *arrs[2:])
+    assert dev.n_env == 4 and dev.device_bytes == host.device_bytes
+    ang = np.linspace(-13, 13, 64)
+    gh = pr.shoot_ensemble_arrays(host, 1000.0, 0.0, 150e3, ang, num_range_save=31, counters=True)
+    gd = pr.shoot_ensemble_arrays(dev, 1000.0, 0.0, 150e3, ang, num_range_save=31, counters=True)
+    for k in ("final", "traj", "n_bottom", "n_surface", "status", "counters"):
+        assert np.array_equal(gh[k], gd[k], equal_nan=(k in ("final", "traj"))), (grid, k)
+    assert (gh["status"] == 0).any()
+    host.close(); dev.close()
+
+
 @pytest.mark.parametrize("seed", range(100, 130))
 def test_fuzz_random_environments_gpu(pr, seed):
     """Seeded random environments / shots (tests/fuzz_cases.py): libprt.so == oracle, bit for bit."""
