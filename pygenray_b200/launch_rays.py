@@ -439,10 +439,14 @@ def _shoot_fan_pipelined(denv, source_depth, source_range, receiver_range, angle
         final_d = torch.empty(3 * n, dtype=torch.float64, device=dev)
         i32_d = torch.empty((4, n), dtype=torch.int32, device=dev)         # n_bottom, n_surface, status, flips
         streams = _streams(dev, n_chunks)
-        chunks = []
+        # middle chunks first (they finish first: launch them first too), growing a contiguous block of host rows outwards
+        centre = (n_chunks - 1) / 2.0
+        order = sorted(range(n_chunks), key=lambda k: (abs(k - centre), k))
+        chunks = [None] * n_chunks
         L.prt_set_concurrency(n_chunks)
         try:
-            for k, (a, b) in enumerate(bounds):
+            for k in order:
+                a, b = bounds[k]
                 m = b - a
                 st = streams[k]
                 st.wait_stream(main)
@@ -458,13 +462,10 @@ def _shoot_fan_pipelined(denv, source_depth, source_range, receiver_range, angle
                     C.c_void_p(c["status"].data_ptr()), None, 1, C.c_void_p(c["flips"].data_ptr()), int(max_bounces),
                     C.c_void_p(st.cuda_stream))
                 _lib.check(rc, "prt_shoot_fan")
-                chunks.append(c)
+                chunks[k] = c
         finally:
             L.prt_set_concurrency(1)
 
-        # middle chunks first (they finish first), growing a contiguous block of host rows outwards
-        centre = (n_chunks - 1) / 2.0
-        order = sorted(range(n_chunks), key=lambda k: (abs(k - centre), k))
         left = right = None
         kept_slices = {}
         for k in order:
