@@ -1,6 +1,6 @@
 // prt_kernels.cu -- sm_100a kernels + the C ABI of libprt.so (include/prt.h).
 //
-// K1  prt_fan_kernel<SAVE>      one FP64 thread per launch angle: the whole ray (all solve_ivp
+// K1  prt_fan_kernel<SAVE, ZC>  one FP64 thread per launch angle: the whole ray (all solve_ivp
 //                               segments, events, reflections, save-grid resampling) in registers.
 // K2  prt_refine_round_kernel   one regula-falsi trial shot per active eigenray bracket.
 // K3  prt_count/fill_brackets   sign-change bracketing of the arrival table.
