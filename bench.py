@@ -182,7 +182,11 @@ def run_b200(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
     if world > 1:
+        from pygenray_b200.dist import bind_to_gpu_numa
+        if os.environ.get("PRT_NUMA_BIND", "1") != "0":
+            numa = bind_to_gpu_numa(local_rank)  # before the first pinned allocation (first touch places it)
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.require_gpu()
 
@@ -402,6 +406,7 @@ def run_b200(args):
             "config": {"workload": w["label"], "rays_per_gpu": n, "range_km": R_km, "n_save": n_save, "rtol": 1e-9,
                        "atol": 1e-6, "l2": "256 MiB buffer zeroed between timed steps (untimed)",
                        **({"ensemble_staging": staging} if staging else {}),
+                       **({"numa_node_rank0": numa} if world > 1 else {}),
                        "parallelism": f"launch angles interleaved over {world} rank(s); arrival tables all-gathered"
                        if world > 1 else "single GPU, one thread per ray"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
