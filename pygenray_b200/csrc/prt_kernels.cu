@@ -130,8 +130,7 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SA
     const unsigned full = 0xffffffffu;
     int waited = 0;
     for (;;) {
-        if (!__any_sync(full, r.phase != PRT_PH_DONE)) break;
-        if (r.phase == PRT_PH_INIT) r.seg_init(E, S);
+        if (r.phase == PRT_PH_INIT) r.seg_init(E, S);  // INIT -> STEP, always
         const unsigned stepping_now = __ballot_sync(full, r.phase == PRT_PH_STEP);
         if (r.phase == PRT_PH_STEP) {
             prt_step st;
@@ -144,9 +143,10 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SA
                 }
             }
         }
-        __syncwarp(full);
-        const unsigned parked = __ballot_sync(full, r.phase == PRT_PH_ROOT);
-        if (parked) {
+        const unsigned parked = __ballot_sync(full, r.phase == PRT_PH_ROOT);  // (also re-converges the warp)
+        if (!parked) {
+            if (!stepping_now) break;  // nobody stepped, nobody is parked, no segment was waiting to start: all done
+        } else {
             const unsigned stepping = __ballot_sync(full, r.phase == PRT_PH_STEP);
             ++waited;
             if (!stepping || waited > park_wait) {
