@@ -480,8 +480,10 @@ PRT_HD void prt_field(const prt_envp& E, double x, double z, double& c, double& 
 // is computed from the true lower edge and width of cell i, so
 //   w > 0          <=>  v > x[i]     (an IEEE difference has the exact sign and the reciprocal is positive),
 //   w < 1 - 2^-40   =>  v < x[i+1]   (v >= x[i+1] gives w >= 1 - 2^-50 after the three roundings),
-// and both together say that i IS clamp(searchsorted(v) - 1).  In the first / last cell the lower / upper
-// test is waived, because the reference clamps there and extrapolates with the same formula.  `ok` collects
+// and both together say that i IS clamp(searchsorted(v) - 1).  Only the lower test of the first DEPTH cell is
+// waived (a ray overshoots the surface by part of a step before every surface reflection; the reference clamps
+// there and extrapolates with the same formula) -- the other ends of the grids are reached once per ray at most
+// (the receiver range is usually the last range node) and are left to the exact re-run.  `ok` collects
 // the proofs and the caller re-runs the whole step attempt through the exact lookup when any failed
 // (prt_ray::attempt): an abscissa on a node or within 1e-12 cell widths below one, and wrong guesses on
 // non-uniform grids.  The stage code of an attempt is thus one branch-free block that the scheduler is free
@@ -500,7 +502,7 @@ PRT_HD prt_xcell prt_xlook(const prt_envp& E, double x, bool& ok)
     prt_xcell xc;
     xc.row = E.grid + i * (unsigned)V.n_z;
     xc.wx = (x - ra.x) * ra.y;
-    ok = ok & ((xc.wx > 0.0) | (i == 0u)) & ((xc.wx < PRT_W_HI) | (i == (unsigned)(V.n_r - 2)));
+    ok = ok & (xc.wx > 0.0) & (xc.wx < PRT_W_HI);
     return xc;
 }
 
@@ -512,7 +514,7 @@ PRT_HD void prt_field_spec(const prt_envp& E, const prt_xcell& xc, double z, dou
     const prt_d2 za = prt_ld2(V.zxr + j);
     const prt_d2 v00 = prt_ld2(g), v01 = prt_ld2(g + 1), v10 = prt_ld2(g + V.n_z), v11 = prt_ld2(g + V.n_z + 1);
     const double wy = (z - za.x) * za.y;
-    ok = ok & ((wy > 0.0) | (j == 0u)) & ((wy < PRT_W_HI) | (j == (unsigned)(V.n_z - 2)));
+    ok = ok & ((wy > 0.0) | (j == 0u)) & (wy < PRT_W_HI);  // waiver: above the surface (overshoot before a reflection)
     prt_bilerp(v00, v01, v10, v11, xc.wx, wy, c, cz);
 }
 
@@ -543,7 +545,7 @@ PRT_HD double prt_bathy_spec(const prt_envp& E, double x, bool& ok)
     const prt_d2* bc = V.bcell + 3 * g;
     const prt_d2 a = prt_ld2(bc + 1), v = prt_ld2(bc + 2);
     const double w = (x - a.x) * a.y;
-    ok = ok & ((w > 0.0) | (g == 0u)) & ((w < PRT_W_HI) | (g == (unsigned)(V.n_b - 2)));
+    ok = ok & (w > 0.0) & (w < PRT_W_HI);
     return PRT_FMA(w, v.y, (1.0 - w) * v.x);
 }
 
