@@ -490,7 +490,7 @@ PRT_HD void prt_field(const prt_envp& E, double x, double z, double& c, double& 
 // to interleave across stages.
 #define PRT_W_HI (1.0 - 0x1p-40)
 struct prt_xcell {
-    const prt_d2* row;  // &grid[i][0]
+    unsigned row;  // i * n_z: element index of grid[i][0] (32-bit on purpose: one IMAD.WIDE per node address)
     double wx;
 };
 
@@ -500,7 +500,7 @@ PRT_HD prt_xcell prt_xlook(const prt_envp& E, double x, bool& ok)
     const unsigned i = prt_guess(x, V.r_inv, V.r_off, V.n_r - 2);
     const prt_d2 ra = prt_ld2(V.rxr + i);
     prt_xcell xc;
-    xc.row = E.grid + i * (unsigned)V.n_z;
+    xc.row = i * (unsigned)V.n_z;
     xc.wx = (x - ra.x) * ra.y;
     ok = ok & (xc.wx > 0.0) & (xc.wx < PRT_W_HI);
     return xc;
@@ -510,9 +510,10 @@ PRT_HD void prt_field_spec(const prt_envp& E, const prt_xcell& xc, double z, dou
 {
     const prt_env_view& V = E.v;
     const unsigned j = prt_guess_z(E, z);
-    const prt_d2* g = xc.row + j;
+    const unsigned e0 = xc.row + j, e1 = e0 + (unsigned)V.n_z;
+    const prt_d2 *g0 = E.grid + e0, *g1 = E.grid + e1;
     const prt_d2 za = prt_ld2(V.zxr + j);
-    const prt_d2 v00 = prt_ld2(g), v01 = prt_ld2(g + 1), v10 = prt_ld2(g + V.n_z), v11 = prt_ld2(g + V.n_z + 1);
+    const prt_d2 v00 = prt_ld2(g0), v01 = prt_ld2(g0 + 1), v10 = prt_ld2(g1), v11 = prt_ld2(g1 + 1);
     const double wy = (z - za.x) * za.y;
     ok = ok & ((wy > 0.0) | (j == 0u)) & (wy < PRT_W_HI);  // waiver: above the surface (overshoot before a reflection)
     prt_bilerp(v00, v01, v10, v11, xc.wx, wy, c, cz);
