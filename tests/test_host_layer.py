@@ -219,3 +219,12 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["metric"] == "ray_km_per_s" and line["unit"] == "ray-km/s"
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
+def test_numa_binding_is_best_effort():
+    """dist.bind_to_gpu_numa never fails a run: cpulist parsing, and None when the topology is not visible."""
+    from pygenray_b200 import dist
+
+    assert dist._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert dist._parse_cpulist("") == set()
+    assert dist.bind_to_gpu_numa(0) is None or isinstance(dist.bind_to_gpu_numa(0), int)
