@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PRT_ABI_VERSION 1
+#define PRT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define PRT_API __attribute__((visibility("default")))
@@ -202,14 +202,19 @@ PRT_API int prt_pack_arrivals(int64_t n_rays, const double *final_dev, const int
  *   z_end_dev [n_rays]   final depths of the surviving fan rays in STORED convention (= -z)
  *   thetas_dev [n_rays]  their launch angles in the fan's stored (user) convention
  *   receiver_depths_dev [n_rcv]
- * Two passes: prt_count_brackets fills counts_dev[n_rcv]; after an exclusive scan into
- * offsets_dev[n_rcv] (caller), prt_fill_brackets writes, in (receiver, ray) order,
- *   br_z1/z2/th1/th2/rd [n_brackets] and br_rcv [n_brackets] (receiver index).
+ * Two passes over a caller-provided scratch of prt_bracket_workspace_bytes(n_rays, n_rcv) bytes:
+ * prt_count_brackets counts the sign changes per (receiver, tile of 2048 rays), scans them into output
+ * positions (kept in work_dev) and fills counts_dev[n_rcv]; the caller reads the counts, allocates
+ * n_brackets = sum(counts) entries, and prt_fill_brackets writes, in (receiver, ray) order,
+ *   br_z1/z2/th1/th2/rd [n_brackets], br_rcv [n_brackets] (receiver index), br_k [n_brackets] (ray index k
+ *   of the pair (k, k + 1)).
+ * Both passes must see the same inputs and the same work_dev.
  */
+PRT_API int64_t prt_bracket_workspace_bytes(int64_t n_rays, int32_t n_rcv);
 PRT_API int prt_count_brackets(int64_t n_rays, const double *z_end_dev, int32_t n_rcv,
-                       const double *receiver_depths_dev, int32_t *counts_dev, void *stream);
+                       const double *receiver_depths_dev, int32_t *counts_dev, void *work_dev, void *stream);
 PRT_API int prt_fill_brackets(int64_t n_rays, const double *z_end_dev, const double *thetas_dev, int32_t n_rcv,
-                      const double *receiver_depths_dev, const int64_t *offsets_dev, double *br_z1_dev,
+                      const double *receiver_depths_dev, const void *work_dev, double *br_z1_dev,
                       double *br_z2_dev, double *br_th1_dev, double *br_th2_dev, double *br_rd_dev,
                       int32_t *br_rcv_dev, int64_t *br_k_dev, void *stream);
 
@@ -221,7 +226,8 @@ PRT_API int prt_fill_brackets(int64_t n_rays, const double *z_end_dev, const dou
  *   out_theta_dev [n_br]  converged user launch angle (NaN otherwise)
  *   out_final_dev [3][n_br], out_n_bottom_dev, out_n_surface_dev, out_status_dev (PRT_EIG_*),
  *   out_shots_dev [n_br], out_ray_status_dev [n_br] (PRT_RAY_* of the dropped trial)
- * Synchronous with respect to the host (the round loop reads the active count back).
+ * Asynchronous on `stream`: max_iter + 2 rounds are enqueued (trial shots of the brackets still active, then an
+ * order-preserving compaction of the active list); the active count never leaves the device.
  */
 PRT_API int64_t prt_refine_workspace_bytes(int64_t n_br);
 PRT_API int prt_refine_brackets(const prt_env_t *env, int64_t n_br, const double *z1_dev, const double *z2_dev,

@@ -224,10 +224,60 @@ def case_eigen():
     save("ref_eigen", **out)
 
 
+def case_cfg3_sub():
+    """BASELINE config 3 sub-sample: Munk + internal waves on the 2001 x 1201 grid, 1000 km; 64 rays of the
+    1 048 576-ray fan linspace(-15, 15, 1 << 20) (evenly spread ray indices, both ends included)."""
+    a = cases.config3_arrays()
+    env = make_env(a)
+    n_fan = 1 << 20
+    idx = np.round(np.linspace(0, n_fan - 1, 64)).astype(np.int64)
+    internal = np.linspace(-15.0, 15.0, n_fan)[idx]
+    al = array_level(env, False, 1000.0, 0.0, 1000e3, internal, 101)
+    cin, cpin, rin, zin, depths, dr, ba = _unpack_envi(env, flatearth=False)
+    save("ref_cfg3_sub", cin_sha=sha(cin), cpin_sha=sha(cpin), bottom_angles=ba, ray_index=idx,
+         **{"al_" + k: v for k, v in al.items()})
+
+
+def case_cfg4_sub():
+    """BASELINE config 4 in miniature: the reference's own shoot_rays + find_eigenrays through 1000 km of the
+    config-3 internal-wave field -- an 81-ray fan around -9 deg (a caustic: 2-3 brackets per receiver depth),
+    3 receiver depths, ztol = 1e-3 (config 4), 0.05 and 1 (the reference's default)."""
+    a = cases.config3_arrays()
+    env = make_env(a)
+    user = np.linspace(-9.02, -8.98, 81)
+    rf = pr.shoot_rays(1000.0, 0.0, user, 1000e3, 11, env, rtol=1e-9, n_processes=8, debug=False, flatearth=False)
+    rds = [1130.0, 1160.0, 1190.0]
+    out = fan_dict(rf)
+    out["receiver_depths"] = np.array(rds)
+    out["user_angles"] = user
+    for tag, ztol in (("z3", 1e-3), ("z05", 0.05), ("z1", 1.0)):
+        try:
+            er = pr.find_eigenrays(rf, rds, 1000.0, 0.0, 1000e3, 11, env, ztol=ztol, max_iter=20, num_workers=8,
+                                   debug=False, flatearth=False)
+        except Exception as e:  # noqa: BLE001
+            # the reference cannot build an EigenRays when a receiver depth has no converged eigenray
+            # (RayFan([]) -> numpy AxisError, ray_objects.py:135-144): recorded, not papered over
+            out[tag + "_raised"] = np.array(type(e).__name__)
+            continue
+        for i in range(len(rds)):
+            pre = f"{tag}_e{i}_"
+            out[pre + "num"] = np.array(er.num_eigenrays[rds[i]])
+            out[pre + "found"] = np.array(er.num_eigenrays_found[i])
+            if er.num_eigenrays_found[i] == 0:
+                continue
+            out[pre + "ts_end"] = er.ts[i][:, -1]; out[pre + "zs_end"] = er.zs[i][:, -1]
+            out[pre + "ps_end"] = er.ps[i][:, -1]
+            out[pre + "launch"] = er.launch_angles[i]; out[pre + "recv"] = er.received_angles[i]
+            out[pre + "ray_id_int"] = er.ray_id_int[i]
+            out[pre + "nb"] = er.n_botts[i]; out[pre + "ns"] = er.n_surfs[i]
+    save("ref_cfg4_sub", **out)
+
+
 CASES = dict(cfg1=case_cfg1, fixture=case_fixture, cfg2_sub=case_cfg2_sub, bounce_fine=case_bounce_fine,
-             physics=case_physics, eigen=case_eigen)
+             physics=case_physics, eigen=case_eigen, cfg3_sub=case_cfg3_sub,
+             cfg4_sub=case_cfg4_sub)
 # cases re-run without the JIT to measure the reference's own self-consistency envelope
-NOJIT_CASES = ("cfg1", "cfg2_sub", "bounce_fine")
+NOJIT_CASES = ("cfg1", "cfg2_sub", "bounce_fine", "cfg3_sub", "cfg4_sub")
 
 if __name__ == "__main__":
     want = sys.argv[1:] or list(CASES)

@@ -24,7 +24,7 @@ EXPORTS = (
     "prt_abi_version", "prt_set_concurrency", "prt_set_lanes", "prt_last_error", "prt_device_count", "prt_env_create", "prt_ensemble_create",
     "prt_ensemble_create_dev",
     "prt_shoot_ensemble", "prt_env_destroy",
-    "prt_env_device_bytes", "prt_shoot_fan", "prt_shoot_fan_host", "prt_pack_arrivals", "prt_count_brackets", "prt_fill_brackets",
+    "prt_env_device_bytes", "prt_shoot_fan", "prt_shoot_fan_host", "prt_pack_arrivals", "prt_bracket_workspace_bytes", "prt_count_brackets", "prt_fill_brackets",
     "prt_refine_workspace_bytes", "prt_refine_brackets", "prt_launch_count", "prt_measure_fp64_peak",
 )
 
@@ -75,7 +75,9 @@ def load():
     L.prt_pack_arrivals.restype = C.c_int
     L.prt_pack_arrivals.argtypes = [i64, vp, vp, vp, vp, vp, vp]
     L.prt_count_brackets.restype = C.c_int
-    L.prt_count_brackets.argtypes = [i64, vp, i32, vp, vp, vp]
+    L.prt_bracket_workspace_bytes.restype = i64
+    L.prt_bracket_workspace_bytes.argtypes = [i64, i32]
+    L.prt_count_brackets.argtypes = [i64, vp, i32, vp, vp, vp, vp]
     L.prt_fill_brackets.restype = C.c_int
     L.prt_fill_brackets.argtypes = [i64, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.prt_refine_workspace_bytes.restype = i64

@@ -748,37 +748,10 @@ PRT_HD double prt_rms3(double a, double b, double c)
     return sqrt(s) / PRT_SQRT3;
 }
 
-// Q = K^T P for one component (scipy rk.py:178-180); Q0 = K1 because P[:,0] = e_1
+// Q = K^T P for one component (scipy rk.py:178-180), accumulated by prt_rk_try; Q0 = K1 because P[:,0] = e_1
 struct prt_q3 {
     double q1, q2, q3;
 };
-PRT_HD prt_q3 prt_dense_q(double k1, double k3, double k4, double k5, double k6, double k7)
-{
-    prt_q3 q;
-    double a = P11 * k1;
-    a = PRT_FMA(P31, k3, a);
-    a = PRT_FMA(P41, k4, a);
-    a = PRT_FMA(P51, k5, a);
-    a = PRT_FMA(P61, k6, a);
-    a = PRT_FMA(P71, k7, a);
-    q.q1 = a;
-    a = P12 * k1;
-    a = PRT_FMA(P32, k3, a);
-    a = PRT_FMA(P42, k4, a);
-    a = PRT_FMA(P52, k5, a);
-    a = PRT_FMA(P62, k6, a);
-    a = PRT_FMA(P72, k7, a);
-    q.q2 = a;
-    a = P13 * k1;
-    a = PRT_FMA(P33, k3, a);
-    a = PRT_FMA(P43, k4, a);
-    a = PRT_FMA(P53, k5, a);
-    a = PRT_FMA(P63, k6, a);
-    a = PRT_FMA(P73, k7, a);
-    q.q3 = a;
-    return q;
-}
-
 // RkDenseOutput._call_impl (scipy rk.py:715-737) for one component; xx = (t - t_old) * (1/h)
 PRT_HD double prt_dense_eval(double q0, const prt_q3& q, double h, double y_old, double p1, double p2, double p3,
                              double p4)
@@ -878,15 +851,15 @@ struct prt_shot {
 // One trial step of RK45: rk_step (scipy rk.py:14-71) + the error estimate and the controller power of
 // _step_impl (rk.py:148-165).  Everything the accept / reject decision and an accepted step need.
 struct prt_try {
-    double k3T, k3z, k3p, k4T, k4z, k4p, k5T, k5z, k5p, k6T, k6z, k6p, k7T, k7z, k7p;  // stage values (k7 = f_new)
-    double nT, nz, np_;  // y_new
-    double c_new;        // sound speed at (t + h, y_new), by-product of the FSAL stage
-    double ms;           // mean square of the scaled error = error_norm^2
-    double pw;           // ms^(-1/10) = error_norm^(-1/5)
-    prt_q3 qT, qz, qp;   // dense-output rows Q = K^T P and rcp(h): only filled by prt_rk_try<.., DENSE = true>
+    double k7T, k7z, k7p;  // f_new (FSAL stage)
+    double nT, nz, np_;    // y_new
+    double c_new;          // sound speed at (t + h, y_new), by-product of the FSAL stage
+    double ms;             // mean square of the scaled error = error_norm^2
+    double pw;             // ms^(-1/10) = error_norm^(-1/5)
+    prt_q3 qT, qz, qp;     // dense-output rows Q = K^T P and rcp(h): only filled by prt_rk_try<.., DENSE = true>
     double inv_h;
-    int g_new;           // event functions at (t + h, y_new) as a mask, the vertical-ray test still open when ...
-    bool vert_open;      // ... |p c| is within 1e-8 of 1 (then asin decides, prt_ev_vertical)
+    int g_new;             // event functions at (t + h, y_new) as a mask, the vertical-ray test still open when ...
+    bool vert_open;        // ... |p c| is within 1e-8 of 1 (then asin decides, prt_ev_vertical)
 };
 
 // EXACT = false: speculative cell lookups, no branch anywhere; `ok` tells whether every guess was right.
@@ -894,13 +867,21 @@ struct prt_try {
 //                whenever the speculative version reports ok.
 // DENSE = true : also forms the dense-output rows and rcp(h) (trajectory-saving kernels, where nearly every
 //                accepted step needs them: inside this block they fill the stalls of the stage chain)
+//
+// Every linear combination of stage values the step needs -- the inputs of the later stages (rows of A), y_new (B),
+// the error estimate (E) and, with DENSE, the rows of Q = K^T P -- is a sum written in stage order, k1 first
+// (rk.py:59-71, 176-180).  They are accumulated here AS THE STAGE VALUES ARRIVE: each accumulator still receives
+// its terms in stage order, one fma per term, so every sum has the bits of the sum written out after the last
+// stage, but no stage value outlives the stage that produced it.  Without DENSE an attempt keeps 6 accumulators
+// alive across the last stage instead of 17 stage values, which is what lets a fifth block of 128 threads be
+// resident per SM in the arrival-table kernels (profiles/r02_variants.md).  The travel-time row never feeds a
+// stage input (the right-hand side does not depend on T): it only has the B and E sums.
 template <bool EXACT, bool DENSE>
 PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, double hh, double T, double z,
                        double p, double f0, double f1, double f2, prt_try& v, bool& ok)
 {
-    double k2T, k2z, k2p, cc, a, b;
-    (void)k2T;
-#define PRT_STAGE(xs, zs, ps, kT, kz, kp, cout)                                  \
+    double kT, kz, kp, cc;
+#define PRT_STAGE(xs, zs, ps, cout)                                              \
     do {                                                                         \
         if (EXACT) {                                                             \
             prt_rhs(E, (xs), (zs), (ps), kT, kz, kp, cout);                      \
@@ -909,27 +890,54 @@ PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, do
             prt_rhs_spec(E, xc_, (zs), (ps), kT, kz, kp, cout, ok);              \
         }                                                                        \
     } while (0)
-    PRT_STAGE(PRT_FMA(C2, hh, t), PRT_FMA(hh, A21 * f1, z), PRT_FMA(hh, A21 * f2, p), k2T, k2z, k2p, cc);
+    // stage 2 (its travel-time component enters no sum: B2 = E2 = P2 = 0)
+    double k2z, k2p, k3T, k3z, k3p, k4T, k4z, k4p, a, b;
+    PRT_STAGE(PRT_FMA(C2, hh, t), PRT_FMA(hh, A21 * f1, z), PRT_FMA(hh, A21 * f2, p), cc);
+    k2z = kz; k2p = kp;
     a = A31 * f1; a = PRT_FMA(A32, k2z, a);
     b = A31 * f2; b = PRT_FMA(A32, k2p, b);
-    PRT_STAGE(PRT_FMA(C3, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), v.k3T, v.k3z, v.k3p, cc);
-    a = A41 * f1; a = PRT_FMA(A42, k2z, a); a = PRT_FMA(A43, v.k3z, a);
-    b = A41 * f2; b = PRT_FMA(A42, k2p, b); b = PRT_FMA(A43, v.k3p, b);
-    PRT_STAGE(PRT_FMA(C4, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), v.k4T, v.k4z, v.k4p, cc);
-    a = A51 * f1; a = PRT_FMA(A52, k2z, a); a = PRT_FMA(A53, v.k3z, a); a = PRT_FMA(A54, v.k4z, a);
-    b = A51 * f2; b = PRT_FMA(A52, k2p, b); b = PRT_FMA(A53, v.k3p, b); b = PRT_FMA(A54, v.k4p, b);
-    PRT_STAGE(PRT_FMA(C5, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), v.k5T, v.k5z, v.k5p, cc);
-    a = A61 * f1; a = PRT_FMA(A62, k2z, a); a = PRT_FMA(A63, v.k3z, a); a = PRT_FMA(A64, v.k4z, a); a = PRT_FMA(A65, v.k5z, a);
-    b = A61 * f2; b = PRT_FMA(A62, k2p, b); b = PRT_FMA(A63, v.k3p, b); b = PRT_FMA(A64, v.k4p, b); b = PRT_FMA(A65, v.k5p, b);
+    PRT_STAGE(PRT_FMA(C3, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), cc);
+    k3T = kT; k3z = kz; k3p = kp;
+    a = A41 * f1; a = PRT_FMA(A42, k2z, a); a = PRT_FMA(A43, k3z, a);
+    b = A41 * f2; b = PRT_FMA(A42, k2p, b); b = PRT_FMA(A43, k3p, b);
+    PRT_STAGE(PRT_FMA(C4, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), cc);
+    k4T = kT; k4z = kz; k4p = kp;
+    a = A51 * f1; a = PRT_FMA(A52, k2z, a); a = PRT_FMA(A53, k3z, a); a = PRT_FMA(A54, k4z, a);
+    b = A51 * f2; b = PRT_FMA(A52, k2p, b); b = PRT_FMA(A53, k3p, b); b = PRT_FMA(A54, k4p, b);
+    PRT_STAGE(PRT_FMA(C5, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), cc);
+    // from here on the sums are carried, not the stage values
+    double a6z = A61 * f1; a6z = PRT_FMA(A62, k2z, a6z); a6z = PRT_FMA(A63, k3z, a6z); a6z = PRT_FMA(A64, k4z, a6z); a6z = PRT_FMA(A65, kz, a6z);
+    double a6p = A61 * f2; a6p = PRT_FMA(A62, k2p, a6p); a6p = PRT_FMA(A63, k3p, a6p); a6p = PRT_FMA(A64, k4p, a6p); a6p = PRT_FMA(A65, kp, a6p);
+    double sT = B1 * f0; sT = PRT_FMA(B3, k3T, sT); sT = PRT_FMA(B4, k4T, sT); sT = PRT_FMA(B5, kT, sT);
+    double sz = B1 * f1; sz = PRT_FMA(B3, k3z, sz); sz = PRT_FMA(B4, k4z, sz); sz = PRT_FMA(B5, kz, sz);
+    double sp = B1 * f2; sp = PRT_FMA(B3, k3p, sp); sp = PRT_FMA(B4, k4p, sp); sp = PRT_FMA(B5, kp, sp);
+    double eT = E1 * f0; eT = PRT_FMA(E3, k3T, eT); eT = PRT_FMA(E4, k4T, eT); eT = PRT_FMA(E5, kT, eT);
+    double ez = E1 * f1; ez = PRT_FMA(E3, k3z, ez); ez = PRT_FMA(E4, k4z, ez); ez = PRT_FMA(E5, kz, ez);
+    double ep = E1 * f2; ep = PRT_FMA(E3, k3p, ep); ep = PRT_FMA(E4, k4p, ep); ep = PRT_FMA(E5, kp, ep);
+    prt_q3 qT, qz, qp;
+    if (DENSE) {
+#define PRT_Q5(q, k1, k3, k4, k5)                                                                       \
+    q.q1 = P11 * k1; q.q1 = PRT_FMA(P31, k3, q.q1); q.q1 = PRT_FMA(P41, k4, q.q1); q.q1 = PRT_FMA(P51, k5, q.q1); \
+    q.q2 = P12 * k1; q.q2 = PRT_FMA(P32, k3, q.q2); q.q2 = PRT_FMA(P42, k4, q.q2); q.q2 = PRT_FMA(P52, k5, q.q2); \
+    q.q3 = P13 * k1; q.q3 = PRT_FMA(P33, k3, q.q3); q.q3 = PRT_FMA(P43, k4, q.q3); q.q3 = PRT_FMA(P53, k5, q.q3)
+        PRT_Q5(qT, f0, k3T, k4T, kT);
+        PRT_Q5(qz, f1, k3z, k4z, kz);
+        PRT_Q5(qp, f2, k3p, k4p, kp);
+#undef PRT_Q5
+    }
     // stages 6 and 7 (FSAL) share the abscissa t + h, hence the range cell and its weight
     const double x6 = t + hh;
     prt_xcell xc6;
     if (!EXACT) xc6 = prt_xlook(E, x6, ok);
-    if (EXACT) prt_rhs(E, x6, PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), v.k6T, v.k6z, v.k6p, cc);
-    else prt_rhs_spec(E, xc6, PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), v.k6T, v.k6z, v.k6p, cc, ok);
-    double sT = B1 * f0; sT = PRT_FMA(B3, v.k3T, sT); sT = PRT_FMA(B4, v.k4T, sT); sT = PRT_FMA(B5, v.k5T, sT); sT = PRT_FMA(B6, v.k6T, sT);
-    double sz = B1 * f1; sz = PRT_FMA(B3, v.k3z, sz); sz = PRT_FMA(B4, v.k4z, sz); sz = PRT_FMA(B5, v.k5z, sz); sz = PRT_FMA(B6, v.k6z, sz);
-    double sp = B1 * f2; sp = PRT_FMA(B3, v.k3p, sp); sp = PRT_FMA(B4, v.k4p, sp); sp = PRT_FMA(B5, v.k5p, sp); sp = PRT_FMA(B6, v.k6p, sp);
+    if (EXACT) prt_rhs(E, x6, PRT_FMA(hh, a6z, z), PRT_FMA(hh, a6p, p), kT, kz, kp, cc);
+    else prt_rhs_spec(E, xc6, PRT_FMA(hh, a6z, z), PRT_FMA(hh, a6p, p), kT, kz, kp, cc, ok);
+    sT = PRT_FMA(B6, kT, sT); sz = PRT_FMA(B6, kz, sz); sp = PRT_FMA(B6, kp, sp);
+    eT = PRT_FMA(E6, kT, eT); ez = PRT_FMA(E6, kz, ez); ep = PRT_FMA(E6, kp, ep);
+    if (DENSE) {
+        qT.q1 = PRT_FMA(P61, kT, qT.q1); qT.q2 = PRT_FMA(P62, kT, qT.q2); qT.q3 = PRT_FMA(P63, kT, qT.q3);
+        qz.q1 = PRT_FMA(P61, kz, qz.q1); qz.q2 = PRT_FMA(P62, kz, qz.q2); qz.q3 = PRT_FMA(P63, kz, qz.q3);
+        qp.q1 = PRT_FMA(P61, kp, qp.q1); qp.q2 = PRT_FMA(P62, kp, qp.q2); qp.q3 = PRT_FMA(P63, kp, qp.q3);
+    }
     v.nT = PRT_FMA(hh, sT, T); v.nz = PRT_FMA(hh, sz, z); v.np_ = PRT_FMA(hh, sp, p);
     // error scales and their reciprocals (rk.py:148-152): known before the last stage, so the three
     // divisions of the reference become one reciprocal (of the product) formed in the shadow of that stage
@@ -939,9 +947,6 @@ PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, do
     const double sTz = scT * scz, szp = scz * scp, sTp = scT * scp;
     const double inv3 = prt_rcp(sTz * scp);
     const double iT = inv3 * szp, iz = inv3 * sTp, ip = inv3 * sTz;
-    double eT = E1 * f0; eT = PRT_FMA(E3, v.k3T, eT); eT = PRT_FMA(E4, v.k4T, eT); eT = PRT_FMA(E5, v.k5T, eT); eT = PRT_FMA(E6, v.k6T, eT);
-    double ez = E1 * f1; ez = PRT_FMA(E3, v.k3z, ez); ez = PRT_FMA(E4, v.k4z, ez); ez = PRT_FMA(E5, v.k5z, ez); ez = PRT_FMA(E6, v.k6z, ez);
-    double ep = E1 * f2; ep = PRT_FMA(E3, v.k3p, ep); ep = PRT_FMA(E4, v.k4p, ep); ep = PRT_FMA(E5, v.k5p, ep); ep = PRT_FMA(E6, v.k6p, ep);
     if (EXACT) prt_rhs(E, x6, v.nz, v.np_, v.k7T, v.k7z, v.k7p, v.c_new);  // f_new (FSAL)
     else prt_rhs_spec(E, xc6, v.nz, v.np_, v.k7T, v.k7z, v.k7p, v.c_new, ok);
 #undef PRT_STAGE
@@ -968,9 +973,10 @@ PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, do
     v.ms = ms;
     v.pw = prt_pow_m01(ms);
     if (DENSE) {
-        v.qT = prt_dense_q(f0, v.k3T, v.k4T, v.k5T, v.k6T, v.k7T);
-        v.qz = prt_dense_q(f1, v.k3z, v.k4z, v.k5z, v.k6z, v.k7z);
-        v.qp = prt_dense_q(f2, v.k3p, v.k4p, v.k5p, v.k6p, v.k7p);
+        qT.q1 = PRT_FMA(P71, v.k7T, qT.q1); qT.q2 = PRT_FMA(P72, v.k7T, qT.q2); qT.q3 = PRT_FMA(P73, v.k7T, qT.q3);
+        qz.q1 = PRT_FMA(P71, v.k7z, qz.q1); qz.q2 = PRT_FMA(P72, v.k7z, qz.q2); qz.q3 = PRT_FMA(P73, v.k7z, qz.q3);
+        qp.q1 = PRT_FMA(P71, v.k7p, qp.q1); qp.q2 = PRT_FMA(P72, v.k7p, qp.q2); qp.q3 = PRT_FMA(P73, v.k7p, qp.q3);
+        v.qT = qT; v.qz = qz; v.qp = qp;
         v.inv_h = prt_rcp(hh);  // contract: dense-output abscissa (t - t_old) * rcp(h), rk.py:722
     }
 }
@@ -1015,7 +1021,8 @@ struct prt_step {
     bool finished;     // the step reached x_end
 };
 
-template <bool SAVE>
+// COUNT = false drops the work counters (5 registers the arrival-table kernels cannot spare at 5 blocks per SM)
+template <bool SAVE, bool COUNT = true>
 struct prt_ray {
     // persistent ODE state (solver.t, solver.y, solver.f, solver.h_abs)
     double t, T, z, p, f0, f1, f2, h_abs;
@@ -1039,7 +1046,7 @@ struct prt_ray {
     // RK45.__init__ (rk.py:85-103) + select_initial_step (common.py:68-134) + g = [st.event(t0, y0)]
     PRT_HD void seg_init(const prt_envp& E, const prt_shot& S)
     {
-        ++c_seg;
+        if (COUNT) ++c_seg;
         double c_here;
         prt_rhs(E, t, z, p, f0, f1, f2, c_here);
         g = prt_events(E, t, z, p, c_here);
@@ -1067,6 +1074,9 @@ struct prt_ray {
     // of the warp that make this attempt together (device only): the prologue is select-only and the lanes
     // are re-converged explicitly before the trial step, so that its ~700 instructions are never executed
     // once per divergent sub-group.
+    // ROWS = false (warp driver of the arrival-table kernels): the dense-output rows of a step that fired an
+    // event are left to the root phase, which rebuilds the whole step record anyway (prt_park_slot::rebuild).
+    template <bool ROWS = true>
     PRT_HD bool attempt(const prt_envp& E, const prt_shot& S, prt_step& st, unsigned lanes = 0xffffffffu)
     {
         const double min_step = 10.0 * fabs(prt_next_up(t) - t);
@@ -1083,7 +1093,7 @@ struct prt_ray {
             phase = PRT_PH_DONE;
             return false;
         }
-        ++c_att;
+        if (COUNT) ++c_att;
         h_abs = fabs(hh);
         // the trial step: speculative cell lookups, one branch-free block; re-run through the general lookup
         // if any of its seven guesses missed (same arithmetic, so the same bits either way)
@@ -1106,10 +1116,8 @@ struct prt_ray {
         if (rejected) factor = prt_py_min(1.0, factor);
         h_abs *= factor;
         rejected = false;
-        ++c_acc;
+        if (COUNT) ++c_acc;
         const double nT = v.nT, nz = v.nz, np_ = v.np_;
-        const double k3T = v.k3T, k3z = v.k3z, k3p = v.k3p, k4T = v.k4T, k4z = v.k4z, k4p = v.k4p;
-        const double k5T = v.k5T, k5z = v.k5z, k5p = v.k5p, k6T = v.k6T, k6z = v.k6z, k6p = v.k6p;
         const double k7T = v.k7T, k7z = v.k7z, k7p = v.k7p;
         double c_new = v.c_new;
         st.t_old = t; st.t_new = tn; st.h = hh;
@@ -1131,15 +1139,17 @@ struct prt_ray {
         g = g_new;
         bool need_dense = (st.active != 0);
         if (SAVE && !need_dense) need_dense = (cursor < S.n_save - 1) && (rs_cur <= tn);
-        if (need_dense) ++c_dense;
+        if (COUNT && need_dense) ++c_dense;
         if (SAVE) {  // formed by the trial step
             st.qT = v.qT; st.qz = v.qz; st.qp = v.qp;
             st.inv_h = v.inv_h;
-        } else if (need_dense) {
-            st.qT = prt_dense_q(f0, k3T, k4T, k5T, k6T, k7T);
-            st.qz = prt_dense_q(f1, k3z, k4z, k5z, k6z, k7z);
-            st.qp = prt_dense_q(f2, k3p, k4p, k5p, k6p, k7p);
-            st.inv_h = prt_rcp(hh);  // contract: dense-output abscissa (t - t_old) * rcp(h), rk.py:722
+        } else if (need_dense && ROWS) {
+            // arrival-table mode keeps no stage values: the rows of the rare step that needs them (an event fired)
+            // come from repeating the trial step with DENSE -- same inputs, same arithmetic, same bits
+            prt_try d;
+            prt_rk_try_exact<true>(&E.v, E.grid, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, &d);
+            st.qT = d.qT; st.qz = d.qz; st.qp = d.qp;
+            st.inv_h = d.inv_h;
         }
         return true;
     }
@@ -1189,7 +1199,7 @@ struct prt_ray {
             if (!(st.active & (1 << e))) continue;
             double xpre = st.t_old, xcur = st.t_new, xblk = 0.0;
             bool fpre = event_at(E, st, e, st.t_old), fcur = event_at(E, st, e, st.t_new);
-            c_bis += 2;
+            if (COUNT) c_bis += 2;
             if (fpre == fcur) {
                 status = PRT_RAY_BRENTQ_SIGN;
                 return;
@@ -1208,7 +1218,7 @@ struct prt_ray {
                 if (fabs(sbis) > delta) xcur += sbis;
                 else xcur += (sbis > 0 ? delta : -delta);
                 fcur = event_at(E, st, e, xcur);
-                ++c_bis;
+                if (COUNT) ++c_bis;
             }
             if (!converged) {
                 status = PRT_RAY_BRENTQ_ITER;
@@ -1287,7 +1297,7 @@ struct prt_ray {
         res.n_bottom = n_bottom;
         res.n_surface = n_surface;
         res.status = status;
-        if (cnt) {
+        if (COUNT && cnt) {
             cnt[PRT_CNT_NFEV] = 2u * c_seg + 6u * c_att; cnt[PRT_CNT_ATTEMPTS] = c_att; cnt[PRT_CNT_ACCEPTED] = c_acc;
             cnt[PRT_CNT_SEGMENTS] = c_seg; cnt[PRT_CNT_BISECT] = c_bis; cnt[PRT_CNT_DENSE] = c_dense;
         }

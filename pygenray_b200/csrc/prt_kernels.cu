@@ -97,8 +97,8 @@ struct prt_park_slot {
         base[blockDim.x] = __longlong_as_double((long long)st.active);
     }
     // rebuild the step record of the parked step of ray r (state still at the start of that step)
-    template <bool SAVE>
-    __device__ __forceinline__ void rebuild(const prt_envp& E, const prt_shot& S, const prt_ray<SAVE>& r, prt_step& st) const
+    template <bool SAVE, bool COUNT>
+    __device__ __forceinline__ void rebuild(const prt_envp& E, const prt_shot& S, const prt_ray<SAVE, COUNT>& r, prt_step& st) const
     {
         const double tn = base[0];
         st.active = (int32_t)__double_as_longlong(base[blockDim.x]);
@@ -122,8 +122,8 @@ struct prt_park_slot {
 //     root search, the reflection and the next segment's start-up run once for all parked lanes, when
 //     no lane is left stepping or the oldest parked lane has waited `park_wait` iterations
 //     (neighbouring launch angles reach a boundary within a few steps of each other).
-template <bool SAVE>
-__device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SAVE>& r, const prt_shot& S,
+template <bool SAVE, bool COUNT>
+__device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SAVE, COUNT>& r, const prt_shot& S,
                                                    const prt_traj_sink& sink, int park_wait,
                                                    const prt_park_slot& park)
 {
@@ -134,7 +134,7 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SA
         const unsigned stepping_now = __ballot_sync(full, r.phase == PRT_PH_STEP);
         if (r.phase == PRT_PH_STEP) {
             prt_step st;
-            if (r.attempt(E, S, st, stepping_now)) {
+            if (r.template attempt<SAVE>(E, S, st, stepping_now)) {
                 if (st.active) {
                     park.store(st);
                     r.phase = PRT_PH_ROOT;
@@ -152,7 +152,7 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SA
             if (!stepping || waited > park_wait) {
                 if (r.phase == PRT_PH_ROOT) {
                     prt_step st;
-                    park.rebuild<SAVE>(E, S, r, st);
+                    park.rebuild(E, S, r, st);
                     r.solve_roots(E, st);
                     r.finish_terminal(E, S, sink, st);
                 }
@@ -162,14 +162,25 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SA
     }
 }
 
-// 4 resident blocks of 128 threads per SM = 128 registers per thread.  Measured on B200 (1M-ray fan):
-// 3 blocks / 142 regs, no spills: 160 ms; 4 blocks / 128 regs, ~100 B spilled: 100 ms; 5 blocks / 96
-// regs, ~300 B spilled: 98 ms (profiles/r01_variants.md) -- occupancy beats spill-free code here.
+// Resident blocks of 128 threads per SM.  Trajectory-saving kernels: 4 (128 registers per thread; measured on B200,
+// 1M-ray fan: 3 blocks / 142 regs 160 ms, 4 blocks 100 ms).  Arrival-table kernels keep no stage values across the
+// trial step (prt_rk_try) and fit 5 blocks (102 registers): the ray ODE is one long dependent FP64 chain, so the
+// FP64 pipe is fed by resident warps, not by ILP (profiles/r02_variants.md).
 #ifndef PRT_MIN_BLOCKS
 #define PRT_MIN_BLOCKS 4
 #endif
-template <bool SAVE, bool ZC>
-__global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_fan_kernel(const __grid_constant__ prt_env_view E0,
+#ifndef PRT_MIN_BLOCKS_ARR
+#define PRT_MIN_BLOCKS_ARR 5
+#endif
+#ifndef PRT_BLOCK
+#define PRT_BLOCK 128  // threads per block, trajectory-saving kernels
+#endif
+#ifndef PRT_BLOCK_ARR
+#define PRT_BLOCK_ARR 128  // threads per block, arrival-table kernels (fan without save grid, eigenray trial shots)
+#endif
+#define PRT_BLOCK_MAX (PRT_BLOCK > PRT_BLOCK_ARR ? PRT_BLOCK : PRT_BLOCK_ARR)
+template <bool SAVE, bool ZC, bool COUNT>
+__global__ void __launch_bounds__(SAVE ? PRT_BLOCK : PRT_BLOCK_ARR, SAVE ? PRT_MIN_BLOCKS : PRT_MIN_BLOCKS_ARR) prt_fan_kernel(const __grid_constant__ prt_env_view E0,
                                                       const __grid_constant__ prt_fan_params P)
 {
     // P.lanes rays per warp (lanes >= P.lanes idle); whole warps stay in the kernel: the driver is warp-synchronous
@@ -216,13 +227,13 @@ __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_fan_kernel(const __gr
         sink.z = sink.T + plane;
         sink.p = sink.z + plane;
     }
-    __shared__ double park_mem[PRT_PARK_FIELDS * 128];
+    __shared__ double park_mem[PRT_PARK_FIELDS * (SAVE ? PRT_BLOCK : PRT_BLOCK_ARR)];
     prt_park_slot park;
     park.base = park_mem + threadIdx.x;
-    prt_ray<SAVE> r;
+    prt_ray<SAVE, COUNT> r;
     r.start(T, z, p, P.source_range, S);
     if (!live) r.phase = PRT_PH_DONE;
-    prt_integrate_warp<SAVE>(E, r, S, sink, P.park_wait, park);
+    prt_integrate_warp(E, r, S, sink, P.park_wait, park);
     if (!live) return;
     prt_ray_result res;
     uint32_t cnt[PRT_CNT_N];
@@ -237,7 +248,7 @@ __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_fan_kernel(const __gr
     P.out_nb[ray] = res.n_bottom;
     P.out_ns[ray] = res.n_surface;
     P.out_status[ray] = res.status;
-    if (P.out_counters) {
+    if (COUNT) {
 #pragma unroll
         for (int k = 0; k < PRT_CNT_N; ++k) P.out_counters[(size_t)k * P.n_rays + ray] = cnt[k];
     }
@@ -270,20 +281,29 @@ static std::atomic<int> g_concurrency{1};
 
 static std::atomic<int> g_lanes_override{0};
 
-static int pick_lanes(int64_t n_units, int device)
+static int lanes_forced()
 {
     const int ov = g_lanes_override.load();
     if (ov == 1 || ov == 2 || ov == 4 || ov == 8 || ov == 16 || ov == 32) return ov;
-    n_units *= g_concurrency.load();  // several fans in flight on different streams share the chip
     static int forced = -1;
     if (forced < 0) {
         const char* e = getenv("PRT_LANES");
         forced = e ? atoi(e) : 0;
     }
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
+    return 0;
+}
+
+// warps_per_sm: resident warps per SM of the kernel about to be launched
+static int pick_lanes(int64_t n_units, int device, int warps_per_sm, int64_t* capacity_out = nullptr)
+{
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const int64_t capacity = (int64_t)sms * PRT_MIN_BLOCKS * 4;  // resident warps (128-thread blocks)
+    const int64_t capacity = (int64_t)sms * warps_per_sm;
+    if (capacity_out) *capacity_out = capacity;
+    const int f = lanes_forced();
+    if (f) return f;
+    n_units *= g_concurrency.load();  // several fans in flight on different streams share the chip
     int lanes = 32;
     while (lanes > 2 && (n_units + lanes / 2 - 1) / (lanes / 2) <= capacity) lanes /= 2;
     return lanes;
@@ -293,67 +313,155 @@ static int pick_lanes(int64_t n_units, int device)
 // K3: bracketing (eigenrays.py:62-79)
 __device__ __forceinline__ double prt_sign(double v) { return (double)((v > 0.0) - (v < 0.0)); }  // np.sign (NaN -> 0 here)
 
-__global__ void prt_count_brackets_kernel(int64_t n_rays, const double* __restrict__ z_end, int32_t n_rcv,
-                                          const double* __restrict__ rds, int32_t* __restrict__ counts)
+// Two-level ordered compaction.  A tile is PRT_BR_TILE consecutive ray pairs (k, k + 1); one block of 256 threads
+// per (receiver, tile), thread t owning the PRT_BR_PER_THREAD consecutive pairs from k0 + t * PRT_BR_PER_THREAD.
+//   count:  tile_cnt[rcv][tile] = number of sign changes of the tile            (no atomics: one writer per entry)
+//   scan:   one block turns tile_cnt, flattened in (receiver, tile) order, into exclusive offsets in place -- the
+//           output position of every tile's first bracket, which is the (receiver, ray) order the host layer
+//           promises -- and writes the per-receiver counts
+//   fill:   the same tiling again; a block-wide exclusive scan of the per-thread counts places every bracket
+#define PRT_BR_PER_THREAD 8
+#define PRT_BR_TILE (256 * PRT_BR_PER_THREAD)
+
+// np.sign propagates NaN: NaN - x != 0 is True, so a NaN neighbour counts as a change (eigenrays.py:66-70)
+__device__ __forceinline__ bool prt_bracket_here(double za, double zb, double rd)
 {
-    const int rcv = blockIdx.y;
-    const double rd = rds[rcv];
-    int local = 0;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_rays - 1;
-         k += (int64_t)gridDim.x * blockDim.x) {
-        double a = z_end[k] + rd, b = z_end[k + 1] + rd;
-        // np.sign propagates NaN: NaN - x != 0 is True, so a NaN neighbour counts as a change
-        bool change = (a != a) || (b != b) || (prt_sign(b) - prt_sign(a) != 0.0);
-        local += change ? 1 : 0;
-    }
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&counts[rcv], local);
+    const double a = za + rd, b = zb + rd;
+    return (a != a) || (b != b) || (prt_sign(b) - prt_sign(a) != 0.0);
 }
 
-// one block per receiver walks the fan in order so that brackets come out sorted by ray index
-__global__ void prt_fill_brackets_kernel(int64_t n_rays, const double* __restrict__ z_end,
-                                         const double* __restrict__ thetas, int32_t n_rcv,
-                                         const double* __restrict__ rds, const int64_t* __restrict__ offsets,
-                                         double* __restrict__ z1, double* __restrict__ z2, double* __restrict__ th1,
-                                         double* __restrict__ th2, double* __restrict__ brd, int32_t* __restrict__ brcv,
-                                         int64_t* __restrict__ bk)
+// exclusive prefix of `v` over the 256 threads of a block (returns it; `total` = block sum); scratch: 8 ints
+__device__ __forceinline__ int prt_block_exscan256(int v, int* warp_tot, int& total)
 {
-    const int rcv = blockIdx.x;
-    const double rd = rds[rcv];
-    __shared__ int warp_tot[32];
-    __shared__ long long base;
-    if (threadIdx.x == 0) base = offsets[rcv];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    for (int64_t start = 0; start < n_rays - 1; start += blockDim.x) {
-        int64_t k = start + threadIdx.x;
-        bool change = false;
-        if (k < n_rays - 1) {
-            double a = z_end[k] + rd, b = z_end[k + 1] + rd;
-            change = (a != a) || (b != b) || (prt_sign(b) - prt_sign(a) != 0.0);
+    int before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int c = warp_tot[w];
+        before += (w < warp) ? c : 0;
+        tot += c;
+    }
+    total = tot;
+    return before + incl - v;
+}
+
+__global__ void __launch_bounds__(256) prt_count_brackets_kernel(int64_t n_rays, const double* __restrict__ z_end,
+                                                                 const double* __restrict__ rds, int32_t n_tiles,
+                                                                 int64_t* __restrict__ tile_cnt)
+{
+    const int rcv = blockIdx.x, tile = blockIdx.y;
+    const double rd = rds[rcv];
+    const int64_t k0 = (int64_t)tile * PRT_BR_TILE + (int64_t)threadIdx.x * PRT_BR_PER_THREAD;
+    int local = 0;
+    if (k0 < n_rays - 1) {
+        double za = z_end[k0];
+#pragma unroll
+        for (int j = 0; j < PRT_BR_PER_THREAD; ++j) {
+            const int64_t k = k0 + j;
+            if (k < n_rays - 1) {
+                const double zb = z_end[k + 1];
+                local += prt_bracket_here(za, zb, rd) ? 1 : 0;
+                za = zb;
+            }
         }
-        unsigned ballot = __ballot_sync(0xffffffffu, change);
-        int within = __popc(ballot & ((1u << lane) - 1));
-        if (lane == 0) warp_tot[warp] = __popc(ballot);
+    }
+    __shared__ int warp_tot[8];
+    int total;
+    (void)prt_block_exscan256(local, warp_tot, total);
+    if (threadIdx.x == 0) tile_cnt[(int64_t)rcv * n_tiles + tile] = total;
+}
+
+__global__ void __launch_bounds__(1024) prt_scan_brackets_kernel(int64_t n_items, int32_t n_tiles, int32_t n_rcv,
+                                                                 int64_t* __restrict__ tile_cnt,
+                                                                 int32_t* __restrict__ counts)
+{
+    __shared__ long long warp_tot[32];
+    __shared__ long long carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_items; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const long long v = (i < n_items) ? tile_cnt[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
-        int before = 0, total = 0;
-        for (int w = 0; w < n_warps; ++w) {
-            if (w < warp) before += warp_tot[w];
-            total += warp_tot[w];
+        long long before = carry, tot = 0;
+        for (int w = 0; w < 32; ++w) {
+            const long long c = warp_tot[w];
+            before += (w < warp) ? c : 0;
+            tot += c;
         }
-        if (change) {
-            long long o = base + before + within;
-            z1[o] = z_end[k];
-            z2[o] = z_end[k + 1];
+        if (i < n_items) tile_cnt[i] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    // per-receiver counts = difference of the offsets of consecutive receivers' first tiles
+    for (int r = threadIdx.x; r < n_rcv; r += 1024) {
+        const long long lo = tile_cnt[(int64_t)r * n_tiles];
+        const long long hi = (r + 1 < n_rcv) ? tile_cnt[(int64_t)(r + 1) * n_tiles] : carry;
+        counts[r] = (int32_t)(hi - lo);
+    }
+}
+
+__global__ void __launch_bounds__(256) prt_fill_brackets_kernel(int64_t n_rays, const double* __restrict__ z_end,
+                                                                const double* __restrict__ thetas,
+                                                                const double* __restrict__ rds, int32_t n_tiles,
+                                                                const int64_t* __restrict__ tile_off,
+                                                                double* __restrict__ z1, double* __restrict__ z2,
+                                                                double* __restrict__ th1, double* __restrict__ th2,
+                                                                double* __restrict__ brd, int32_t* __restrict__ brcv,
+                                                                int64_t* __restrict__ bk)
+{
+    const int rcv = blockIdx.x, tile = blockIdx.y;
+    const double rd = rds[rcv];
+    const int64_t k0 = (int64_t)tile * PRT_BR_TILE + (int64_t)threadIdx.x * PRT_BR_PER_THREAD;
+    double z[PRT_BR_PER_THREAD + 1];
+    unsigned mask = 0;
+    if (k0 < n_rays - 1) {
+        z[0] = z_end[k0];
+#pragma unroll
+        for (int j = 0; j < PRT_BR_PER_THREAD; ++j) {
+            const int64_t k = k0 + j;
+            z[j + 1] = 0.0;
+            if (k < n_rays - 1) {
+                z[j + 1] = z_end[k + 1];
+                mask |= prt_bracket_here(z[j], z[j + 1], rd) ? (1u << j) : 0u;
+            }
+        }
+    }
+    __shared__ int warp_tot[8];
+    int total;
+    const int before = prt_block_exscan256(__popc(mask), warp_tot, total);
+    if (!mask) return;
+    int64_t o = tile_off[(int64_t)rcv * n_tiles + tile] + before;
+#pragma unroll
+    for (int j = 0; j < PRT_BR_PER_THREAD; ++j) {
+        if (mask & (1u << j)) {
+            const int64_t k = k0 + j;
+            z1[o] = z[j];
+            z2[o] = z[j + 1];
             th1[o] = thetas[k];
             th2[o] = thetas[k + 1];
             brd[o] = rd;
             brcv[o] = rcv;
             bk[o] = k;
+            ++o;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) base += total;
-        __syncthreads();
     }
 }
 
@@ -362,7 +470,9 @@ __global__ void prt_fill_brackets_kernel(int64_t n_rays, const double* __restric
 struct prt_refine_state {
     double *z1, *z2, *th1, *th2, *th;  // [n_br]
     int32_t *iter, *shots;             // [n_br]
-    int32_t *list_a, *list_b;          // active bracket ids (ping-pong)
+    int32_t *list_a, *list_b;          // active bracket ids (ping-pong), always in ascending bracket order
+    int32_t* keep;                     // [n_br] per list slot: 1 = the bracket goes on to the next round
+    int32_t* blk;                      // [ceil(n_br / PRT_CP_TILE)] survivors per tile of list slots, then their offsets
     int32_t* counters;                 // [2] active counts (ping-pong)
 };
 
@@ -370,7 +480,9 @@ struct prt_refine_params {
     int64_t n_br;
     const double* rd;
     double source_depth, source_range, receiver_range, rtol, atol, ztol;
-    int32_t terminate_backwards, max_iter, max_bounces, park_wait, lanes;
+    int32_t terminate_backwards, max_iter, max_bounces, park_wait;
+    int32_t lanes;        // > 0: rays per warp fixed by the caller (prt_set_lanes); 0: chosen from the active count
+    int32_t warp_budget;  // warps the round may spread the active brackets over (resident capacity, launched warps)
     double* out_theta;
     double* out_final;
     int32_t *out_nb, *out_ns, *out_status, *out_shots, *out_ray_status;
@@ -408,17 +520,23 @@ __global__ void prt_refine_init_kernel(prt_refine_state S, int64_t n_br, const d
 }
 
 template <bool ZC>
-__global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_refine_round_kernel(const __grid_constant__ prt_env_view E0,
+__global__ void __launch_bounds__(PRT_BLOCK_ARR, PRT_MIN_BLOCKS_ARR) prt_refine_round_kernel(const __grid_constant__ prt_env_view E0,
                                                                const __grid_constant__ prt_refine_params P,
                                                                prt_refine_state S, const int32_t* __restrict__ list_in,
-                                                               int32_t* __restrict__ list_out, const int32_t* n_in,
-                                                               int32_t* n_out)
+                                                               const int32_t* n_in)
 {
     const prt_envp E{E0, E0.grid, ZC};
     const int n_active = *n_in;
+    // rays per warp: the rule of pick_lanes() on the number of brackets still active, which only the device knows
+    // (the host never waits for a round): few survivors are spread over more, partly filled warps
+    int lanes = P.lanes;
+    if (lanes == 0) {
+        lanes = 32;
+        while (lanes > 2 && (n_active + (lanes >> 1) - 1) / (lanes >> 1) <= P.warp_budget) lanes >>= 1;
+    }
     const int lane = threadIdx.x & 31;
-    const int idx = (int)(((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * P.lanes + lane);
-    const bool live = (lane < P.lanes) && (idx < n_active);
+    const int idx = (int)(((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * lanes + lane);
+    const bool live = (lane < lanes) && (idx < n_active);
     const int b = live ? list_in[idx] : 0;
     const double rd = live ? P.rd[b] : 0.0;
     const double th = live ? S.th[b] : 0.0;
@@ -432,18 +550,19 @@ __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_refine_round_kernel(c
     sink.T = sink.z = sink.p = nullptr;
     sink.stride = 1;
     sink.sgn = 1.0;
-    __shared__ double park_mem[PRT_PARK_FIELDS * 128];
+    __shared__ double park_mem[PRT_PARK_FIELDS * PRT_BLOCK_ARR];
     prt_park_slot park;
     park.base = park_mem + threadIdx.x;
-    prt_ray<false> r;
+    prt_ray<false, false> r;
     r.start(T, z, p, P.source_range, shot);
     if (!live) r.phase = PRT_PH_DONE;
-    prt_integrate_warp<false>(E, r, shot, sink, P.park_wait, park);
+    prt_integrate_warp(E, r, shot, sink, P.park_wait, park);
     if (!live) return;
     prt_ray_result res;
     r.result(shot, sink, res, nullptr);
     const int shots = ++S.shots[b];
     P.out_shots[b] = shots;
+    S.keep[idx] = 0;  // list slot idx: set to 1 below iff the bracket needs another trial shot
     if (res.status != PRT_RAY_OK) {  // ray is None, eigenrays.py:241-245
         P.out_status[b] = PRT_EIG_RAY_DROPPED;
         P.out_ray_status[b] = res.status;
@@ -479,7 +598,77 @@ __global__ void __launch_bounds__(128, PRT_MIN_BLOCKS) prt_refine_round_kernel(c
         return;
     }
     S.iter[b] = it + 1;
-    list_out[atomicAdd(n_out, 1)] = b;
+    S.keep[idx] = 1;
+}
+
+// Order-preserving compaction of the active list between rounds (count per tile of list slots -> one-block scan ->
+// scatter): the survivors keep their (receiver, ray) order, so a warp of the next round still holds neighbouring
+// launch angles of one receiver -- rays that take the same steps through the same grid cells.  (An atomic append
+// shuffled the list after round 0: warps of unrelated angles, 2x slower trial shots; profiles/r02_variants.md.)
+#define PRT_CP_PER_THREAD 4
+#define PRT_CP_TILE (256 * PRT_CP_PER_THREAD)
+__global__ void __launch_bounds__(256) prt_compact_count_kernel(const int32_t* __restrict__ keep, const int32_t* n_in,
+                                                                int32_t* __restrict__ blk)
+{
+    const int n = *n_in;
+    const int s0 = blockIdx.x * PRT_CP_TILE + threadIdx.x * PRT_CP_PER_THREAD;
+    int local = 0;
+#pragma unroll
+    for (int j = 0; j < PRT_CP_PER_THREAD; ++j) local += (s0 + j < n && keep[s0 + j]) ? 1 : 0;
+    __shared__ int warp_tot[8];
+    int total;
+    (void)prt_block_exscan256(local, warp_tot, total);
+    if (threadIdx.x == 0) blk[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) prt_compact_scan_kernel(int32_t n_blk, int32_t* __restrict__ blk, int32_t* n_out)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_blk; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = (i < n_blk) ? blk[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int before = carry, tot = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int c = warp_tot[w];
+            before += (w < warp) ? c : 0;
+            tot += c;
+        }
+        if (i < n_blk) blk[i] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_out = carry;
+}
+
+__global__ void __launch_bounds__(256) prt_compact_scatter_kernel(const int32_t* __restrict__ keep, const int32_t* n_in,
+                                                                  const int32_t* __restrict__ blk,
+                                                                  const int32_t* __restrict__ list_in,
+                                                                  int32_t* __restrict__ list_out)
+{
+    const int n = *n_in;
+    const int s0 = blockIdx.x * PRT_CP_TILE + threadIdx.x * PRT_CP_PER_THREAD;
+    unsigned mask = 0;
+#pragma unroll
+    for (int j = 0; j < PRT_CP_PER_THREAD; ++j) mask |= (s0 + j < n && keep[s0 + j]) ? (1u << j) : 0u;
+    __shared__ int warp_tot[8];
+    int total;
+    int o = blk[blockIdx.x] + prt_block_exscan256(__popc(mask), warp_tot, total);
+#pragma unroll
+    for (int j = 0; j < PRT_CP_PER_THREAD; ++j)
+        if (mask & (1u << j)) list_out[o++] = list_in[s0 + j];
 }
 
 // arrival records [n][6] = T, z, p, n_bottom, n_surface, status (the unit of the multi-GPU all-gather)
@@ -736,30 +925,21 @@ static int shoot_fan_impl(const prt_env_t* env, int64_t n_rays, int64_t rays_per
         P.reorder = reorder;
     }
     if (P.rtol < 100.0 * PRT_EPS) P.rtol = 100.0 * PRT_EPS;  // validate_tol (scipy common.py:44-60)
-    P.lanes = pick_lanes(n_rays, env->device);
-    const int block = 128;
+    const int block = save ? PRT_BLOCK : PRT_BLOCK_ARR;
+    P.lanes = pick_lanes(n_rays, env->device, (save ? PRT_MIN_BLOCKS : PRT_MIN_BLOCKS_ARR) * (block / 32));
     const int64_t n_warps = (n_rays + P.lanes - 1) / P.lanes;
     const unsigned grid = (unsigned)((n_warps * 32 + block - 1) / block);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool zc = env->view.z_cubic != 0;  // refined depth guess compiled in only for stretched depth grids
-    static int carve = -2;  // dev experiment: PRT_CARVEOUT = preferred shared-memory carve-out in percent
-    if (carve == -2) {
-        const char* e = getenv("PRT_CARVEOUT");
-        carve = e ? atoi(e) : -1;
-        if (carve >= 0) {
-            cudaFuncSetAttribute(prt_fan_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-            cudaFuncSetAttribute(prt_fan_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-            cudaFuncSetAttribute(prt_fan_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-            cudaFuncSetAttribute(prt_fan_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        }
-    }
-    if (save) {
-        if (zc) prt_fan_kernel<true, true><<<grid, block, 0, s>>>(env->view, P);
-        else prt_fan_kernel<true, false><<<grid, block, 0, s>>>(env->view, P);
-    } else {
-        if (zc) prt_fan_kernel<false, true><<<grid, block, 0, s>>>(env->view, P);
-        else prt_fan_kernel<false, false><<<grid, block, 0, s>>>(env->view, P);
-    }
+    const bool cnt = out_counters_dev != nullptr;
+#define PRT_FAN_LAUNCH(SV, Z, CN) prt_fan_kernel<SV, Z, CN><<<grid, block, 0, s>>>(env->view, P)
+#define PRT_FAN_PICK_CN(SV, Z) do { if (cnt) PRT_FAN_LAUNCH(SV, Z, true); else PRT_FAN_LAUNCH(SV, Z, false); } while (0)
+#define PRT_FAN_PICK_Z(SV) do { if (zc) PRT_FAN_PICK_CN(SV, true); else PRT_FAN_PICK_CN(SV, false); } while (0)
+    if (save) PRT_FAN_PICK_Z(true);
+    else PRT_FAN_PICK_Z(false);
+#undef PRT_FAN_PICK_Z
+#undef PRT_FAN_PICK_CN
+#undef PRT_FAN_LAUNCH
     g_launches.fetch_add(1);
     PRT_CUDA(cudaGetLastError());
     if (out_p_sign_changes_dev) {
@@ -859,35 +1039,53 @@ int prt_shoot_fan_host(const prt_env_t* env, int64_t n_rays, const double* angle
     return PRT_SUCCESS;
 }
 
+static int32_t bracket_tiles(int64_t n_rays)
+{
+    return n_rays < 2 ? 0 : (int32_t)((n_rays - 1 + PRT_BR_TILE - 1) / PRT_BR_TILE);
+}
+
+int64_t prt_bracket_workspace_bytes(int64_t n_rays, int32_t n_rcv)
+{
+    if (n_rcv <= 0) return 256;
+    return (int64_t)prt_align256(sizeof(int64_t) * (size_t)n_rcv * (size_t)(bracket_tiles(n_rays) + 1));
+}
+
 int prt_count_brackets(int64_t n_rays, const double* z_end_dev, int32_t n_rcv, const double* receiver_depths_dev,
-                       int32_t* counts_dev, void* stream)
+                       int32_t* counts_dev, void* work_dev, void* stream)
 {
     if (n_rcv <= 0) return PRT_SUCCESS;
-    if (!z_end_dev || !receiver_depths_dev || !counts_dev) return fail(PRT_ERR_ARG, "prt_count_brackets: null pointer");
+    if (!z_end_dev || !receiver_depths_dev || !counts_dev || !work_dev)
+        return fail(PRT_ERR_ARG, "prt_count_brackets: null pointer");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    PRT_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(int32_t) * (size_t)n_rcv, s));
-    if (n_rays < 2) return PRT_SUCCESS;
-    int64_t blocks = (n_rays - 1 + 255) / 256;
-    if (blocks > 1024) blocks = 1024;
-    dim3 grid((unsigned)blocks, (unsigned)n_rcv);
-    prt_count_brackets_kernel<<<grid, 256, 0, s>>>(n_rays, z_end_dev, n_rcv, receiver_depths_dev, counts_dev);
-    g_launches.fetch_add(1);
+    const int32_t n_tiles = bracket_tiles(n_rays);
+    if (n_tiles == 0) {
+        PRT_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(int32_t) * (size_t)n_rcv, s));
+        return PRT_SUCCESS;
+    }
+    if (n_tiles > 65535) return fail(PRT_ERR_ARG, "prt_count_brackets: more than 134 million rays in one table");
+    int64_t* tile_cnt = static_cast<int64_t*>(work_dev);
+    prt_count_brackets_kernel<<<dim3((unsigned)n_rcv, (unsigned)n_tiles), 256, 0, s>>>(n_rays, z_end_dev,
+                                                                                     receiver_depths_dev, n_tiles, tile_cnt);
+    prt_scan_brackets_kernel<<<1, 1024, 0, s>>>((int64_t)n_rcv * n_tiles, n_tiles, n_rcv, tile_cnt, counts_dev);
+    g_launches.fetch_add(2);
     PRT_CUDA(cudaGetLastError());
     return PRT_SUCCESS;
 }
 
 int prt_fill_brackets(int64_t n_rays, const double* z_end_dev, const double* thetas_dev, int32_t n_rcv,
-                      const double* receiver_depths_dev, const int64_t* offsets_dev, double* br_z1_dev,
+                      const double* receiver_depths_dev, const void* work_dev, double* br_z1_dev,
                       double* br_z2_dev, double* br_th1_dev, double* br_th2_dev, double* br_rd_dev,
                       int32_t* br_rcv_dev, int64_t* br_k_dev, void* stream)
 {
-    if (n_rcv <= 0 || n_rays < 2) return PRT_SUCCESS;
-    if (!z_end_dev || !thetas_dev || !receiver_depths_dev || !offsets_dev)
+    const int32_t n_tiles = bracket_tiles(n_rays);
+    if (n_rcv <= 0 || n_tiles == 0) return PRT_SUCCESS;
+    if (!z_end_dev || !thetas_dev || !receiver_depths_dev || !work_dev || !br_z1_dev || !br_z2_dev || !br_th1_dev ||
+        !br_th2_dev || !br_rd_dev || !br_rcv_dev || !br_k_dev)
         return fail(PRT_ERR_ARG, "prt_fill_brackets: null pointer");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    prt_fill_brackets_kernel<<<(unsigned)n_rcv, 256, 0, s>>>(n_rays, z_end_dev, thetas_dev, n_rcv, receiver_depths_dev,
-                                                             offsets_dev, br_z1_dev, br_z2_dev, br_th1_dev, br_th2_dev,
-                                                             br_rd_dev, br_rcv_dev, br_k_dev);
+    prt_fill_brackets_kernel<<<dim3((unsigned)n_rcv, (unsigned)n_tiles), 256, 0, s>>>(
+        n_rays, z_end_dev, thetas_dev, receiver_depths_dev, n_tiles, static_cast<const int64_t*>(work_dev), br_z1_dev,
+        br_z2_dev, br_th1_dev, br_th2_dev, br_rd_dev, br_rcv_dev, br_k_dev);
     g_launches.fetch_add(1);
     PRT_CUDA(cudaGetLastError());
     return PRT_SUCCESS;
@@ -910,7 +1108,7 @@ int64_t prt_refine_workspace_bytes(int64_t n_br)
 {
     if (n_br < 0) return 0;
     size_t n = (size_t)n_br;
-    return (int64_t)(5 * prt_align256(n * sizeof(double)) + 4 * prt_align256(n * sizeof(int32_t)) + 256);
+    return (int64_t)(5 * prt_align256(n * sizeof(double)) + 6 * prt_align256(n * sizeof(int32_t)) + 256);
 }
 
 int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev, const double* z2_dev,
@@ -929,6 +1127,7 @@ int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev
         return fail(PRT_ERR_ARG, "prt_refine_brackets: null pointer");
     if (!(source_range < receiver_range))
         return fail(PRT_ERR_ARG, "prt_refine_brackets: source_range must be < receiver_range");
+    if (max_iter < 0) return fail(PRT_ERR_ARG, "prt_refine_brackets: max_iter < 0");
     PRT_CUDA(cudaSetDevice(env->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t n = (size_t)n_br;
@@ -939,7 +1138,8 @@ int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev
     S.th = (double*)(w + 4 * dsz);
     unsigned char* wi = w + 5 * dsz;
     S.iter = (int32_t*)wi; S.shots = (int32_t*)(wi + isz); S.list_a = (int32_t*)(wi + 2 * isz);
-    S.list_b = (int32_t*)(wi + 3 * isz); S.counters = (int32_t*)(wi + 4 * isz);
+    S.list_b = (int32_t*)(wi + 3 * isz); S.keep = (int32_t*)(wi + 4 * isz); S.blk = (int32_t*)(wi + 5 * isz);
+    S.counters = (int32_t*)(wi + 6 * isz);
     prt_refine_params P;
     P.n_br = n_br; P.rd = rd_dev; P.source_depth = source_depth; P.source_range = source_range;
     P.receiver_range = receiver_range; P.rtol = rtol; P.atol = atol; P.ztol = ztol;
@@ -953,25 +1153,32 @@ int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev
                                                                           rd_dev, P);
     g_launches.fetch_add(1);
     PRT_CUDA(cudaGetLastError());
-    int32_t n_active = (int32_t)n_br;
+    // Every round is launched for the first round's size: the number of brackets still active lives on the device
+    // only (no read-back, no host synchronisation between rounds), surplus warps find nothing and exit, and the
+    // rays-per-warp rule is applied by the kernel itself.  At most max_iter + 2 trial shots per bracket
+    // (eigenrays.py:265-268).
+    int64_t capacity = 0;
+    const int lanes0 = pick_lanes(n_br, env->device, PRT_MIN_BLOCKS_ARR * (PRT_BLOCK_ARR / 32), &capacity);
+    const int block = PRT_BLOCK_ARR;
+    const int64_t n_warps = (n_br + lanes0 - 1) / lanes0;
+    const unsigned grid = (unsigned)((n_warps * 32 + block - 1) / block);
+    const bool fixed = (lanes_forced() != 0);
+    P.lanes = fixed ? lanes0 : 0;
+    P.warp_budget = (int32_t)(n_warps < capacity ? n_warps : capacity);
+    const int n_blk = (int)((n_br + PRT_CP_TILE - 1) / PRT_CP_TILE);
     int flip = 0;
-    // at most max_iter + 2 trial shots per bracket (eigenrays.py:265-268)
-    for (int round = 0; round < max_iter + 3 && n_active > 0; ++round) {
+    for (int round = 0; round < max_iter + 2; ++round) {
         int32_t* list_in = flip ? S.list_b : S.list_a;
         int32_t* list_out = flip ? S.list_a : S.list_b;
         int32_t* n_in = S.counters + flip;
         int32_t* n_out = S.counters + (1 - flip);
-        PRT_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int32_t), s));
-        P.lanes = pick_lanes(n_active, env->device);
-        const int block = 128;
-        const int64_t n_warps = ((int64_t)n_active + P.lanes - 1) / P.lanes;
-        const unsigned grid = (unsigned)((n_warps * 32 + block - 1) / block);
-        if (env->view.z_cubic) prt_refine_round_kernel<true><<<grid, block, 0, s>>>(env->view, P, S, list_in, list_out, n_in, n_out);
-        else prt_refine_round_kernel<false><<<grid, block, 0, s>>>(env->view, P, S, list_in, list_out, n_in, n_out);
-        g_launches.fetch_add(1);
+        if (env->view.z_cubic) prt_refine_round_kernel<true><<<grid, block, 0, s>>>(env->view, P, S, list_in, n_in);
+        else prt_refine_round_kernel<false><<<grid, block, 0, s>>>(env->view, P, S, list_in, n_in);
+        prt_compact_count_kernel<<<n_blk, 256, 0, s>>>(S.keep, n_in, S.blk);
+        prt_compact_scan_kernel<<<1, 1024, 0, s>>>(n_blk, S.blk, n_out);
+        prt_compact_scatter_kernel<<<n_blk, 256, 0, s>>>(S.keep, n_in, S.blk, list_in, list_out);
+        g_launches.fetch_add(4);
         PRT_CUDA(cudaGetLastError());
-        PRT_CUDA(cudaMemcpyAsync(&n_active, n_out, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        PRT_CUDA(cudaStreamSynchronize(s));
         flip = 1 - flip;
     }
     return PRT_SUCCESS;

@@ -1,4 +1,5 @@
-"""Multi-GPU fan shooting: one process per GPU (torchrun), launch angles sharded, arrival tables gathered.
+"""Multi-GPU fan shooting and eigenray search: one process per GPU (torchrun), launch angles / eigenray brackets /
+ensemble realisations sharded, fixed-width result records gathered.
 
 The reference's only parallelism is a multiprocessing pool over launch angles
 (/root/reference/src/pygenray/launch_rays.py:133-164); rays never exchange data, so the fan shards
@@ -7,14 +8,24 @@ neighbouring angles stays together, cost per ray grows with |angle| so contiguou
 imbalance), every rank stages its own copy of the environment (<= tens of MB), and the only
 collective is ONE all-gather of the fixed-size arrival records (T, z, p, n_bottom, n_surface, status:
 6 doubles per ray) over NCCL/NVLink.  Trajectories stay sharded on the GPU that produced them.
-Eigenray bracketing needs neighbouring rays in angle order, so it runs on the gathered table.
+Eigenray bracketing needs neighbouring rays in angle order, so it runs on the gathered table -- on every rank, it
+is a sub-millisecond kernel and deterministic, so all ranks hold the same bracket list without a broadcast --
+and the brackets (receiver x ray pair), whose regula-falsi trial shots are the expensive part, are dealt to the
+ranks in cyclic blocks of 32 (the reference's only eigenray parallelism is a process pool over brackets,
+/root/reference/src/pygenray/eigenrays.py:122-164); ONE all-gather of 10-double eigenray records returns the
+table to every rank.  Tomography ensembles shard by realisation (contiguous blocks; every realisation costs the
+same), again with one all-gather of the arrival records.
 """
 import numpy as np
 
-__all__ = ["shard_indices", "all_gather_arrivals", "shoot_fan_sharded", "bind_to_gpu_numa", "RECORD_WIDTH"]
+__all__ = ["shard_indices", "all_gather_rows", "all_gather_arrivals", "shoot_fan_sharded", "find_eigenrays_sharded",
+           "shard_realisations", "shoot_ensemble_sharded", "bind_to_gpu_numa", "RECORD_WIDTH", "EIGEN_WIDTH",
+           "EIGEN_FIELDS"]
 
 BLOCK = 32
 RECORD_WIDTH = 6  # T, z, p, n_bottom, n_surface, status
+EIGEN_FIELDS = ("rcv", "k", "theta", "T", "z", "p", "n_bottom", "n_surface", "status", "shots")
+EIGEN_WIDTH = len(EIGEN_FIELDS)
 
 
 _SHARD_CACHE = {}
@@ -98,29 +109,41 @@ def _gather_index(n_rays, world, block, device):
     return idx
 
 
-def all_gather_arrivals(local_records, n_rays, rank, world, block=BLOCK, group=None):
-    """All-gather the per-rank arrival records and put them back in launch-angle order.
+def all_gather_rows(local_rows, n_total, rank, world, block=BLOCK, group=None):
+    """All-gather fixed-width rows that were dealt to the ranks by :func:`shard_indices` and put them back in order.
 
-    ``local_records``: float64 tensor [n_local, RECORD_WIDTH] on the rank's device (CUDA with NCCL, CPU
-    with gloo).  Returns a [n_rays, RECORD_WIDTH] tensor on the same device, identical on every rank.
-    One collective + one gather by a cached index (no per-rank Python work in the step).
+    ``local_rows``: float64 tensor [n_local, width] on the rank's device (CUDA with NCCL, CPU with gloo).  Returns a
+    [n_total, width] tensor on the same device, identical on every rank.  One collective + one gather by a cached
+    index (no per-rank Python work in the step).
     """
     import torch  # noqa: PLC0415
     import torch.distributed as dist  # noqa: PLC0415
 
+    if local_rows.ndim != 2:
+        raise ValueError("all_gather_rows: local_rows must be [n_local, width]")
     if world == 1:
-        assert local_records.shape[0] == n_rays
-        return local_records
-    src, sizes, pad = _gather_index(n_rays, world, block, local_records.device)
-    assert local_records.shape[0] == sizes[rank], "local shard has the wrong number of rays"
+        if local_rows.shape[0] != n_total:
+            raise ValueError(f"all_gather_rows: {local_rows.shape[0]} local rows for {n_total} in total at world size 1")
+        return local_rows
+    width = local_rows.shape[1]
+    src, sizes, pad = _gather_index(n_total, world, block, local_rows.device)
+    if local_rows.shape[0] != sizes[rank]:
+        raise ValueError(f"all_gather_rows: rank {rank} holds {local_rows.shape[0]} rows, its shard has {sizes[rank]}")
     if sizes[rank] == pad:
-        buf = local_records.contiguous()
+        buf = local_rows.contiguous()
     else:
-        buf = torch.zeros((pad, RECORD_WIDTH), dtype=torch.float64, device=local_records.device)
-        buf[: sizes[rank]] = local_records
-    gathered = torch.empty((world * pad, RECORD_WIDTH), dtype=torch.float64, device=local_records.device)
+        buf = torch.zeros((pad, width), dtype=local_rows.dtype, device=local_rows.device)
+        buf[: sizes[rank]] = local_rows
+    gathered = torch.empty((world * pad, width), dtype=local_rows.dtype, device=local_rows.device)
     dist.all_gather_into_tensor(gathered, buf, group=group)
     return gathered.index_select(0, src)
+
+
+def all_gather_arrivals(local_records, n_rays, rank, world, block=BLOCK, group=None):
+    """All-gather the per-rank arrival records [n_local, RECORD_WIDTH] and put them back in launch-angle order."""
+    if local_records.shape[1] != RECORD_WIDTH:
+        raise ValueError(f"all_gather_arrivals: records must be [n, {RECORD_WIDTH}]")
+    return all_gather_rows(local_records, n_rays, rank, world, block=block, group=group)
 
 
 def records_from_result(res):
@@ -149,18 +172,121 @@ def records_from_result(res):
     return rec
 
 
-def shoot_fan_sharded(denv, source_depth, source_range, receiver_range, angles, rank, world, **kwargs):
+def shoot_fan_sharded(denv, source_depth, source_range, receiver_range, angles, rank, world, group=None, **kwargs):
     """Shoot this rank's share of ``angles`` (internal angles, full fan on every rank) and all-gather.
 
     Returns ``(table, local)``: the gathered [n_rays, 6] arrival table (device tensor, same on all ranks)
     and this rank's own shoot_fan_arrays result (trajectories stay local).  ``kwargs`` go to
-    :func:`pygenray_b200.shoot_fan_arrays`.
+    :func:`pygenray_b200.shoot_fan_arrays` (``to_host`` / ``compact`` are fixed: the table needs every ray).
     """
     from .launch_rays import shoot_fan_arrays  # noqa: PLC0415
 
+    for fixed in ("to_host", "compact"):
+        if kwargs.pop(fixed, None):
+            raise ValueError(f"shoot_fan_sharded: {fixed} is not available here (records of ALL rays are gathered)")
     angles = np.ascontiguousarray(angles, dtype=np.float64)
     mine = shard_indices(angles.shape[0], rank, world)
-    kwargs["to_host"] = False
-    local = shoot_fan_arrays(denv, source_depth, source_range, receiver_range, angles=angles[mine], **kwargs)
-    table = all_gather_arrivals(records_from_result(local), angles.shape[0], rank, world)
+    local = shoot_fan_arrays(denv, source_depth, source_range, receiver_range, angles=angles[mine], to_host=False,
+                             **kwargs)
+    table = all_gather_arrivals(records_from_result(local), angles.shape[0], rank, world, group=group)
     return table, local
+
+
+# ---------------------------------------------------------------------------------------------
+# eigenray search over ranks (SURVEY.md section 8e)
+def _gpu_bracket(z_end, thetas, receiver_depths):
+    from .eigenrays import find_brackets  # noqa: PLC0415
+
+    return find_brackets(z_end, thetas, receiver_depths, device=z_end.device.index)
+
+
+def _gpu_refine(denv, br, source_depth, source_range, receiver_range, **kw):
+    from .eigenrays import refine_brackets  # noqa: PLC0415
+
+    return refine_brackets(denv, br, source_depth, source_range, receiver_range, **kw)
+
+
+def find_eigenrays_sharded(denv, table, user_thetas, receiver_depths, source_depth, source_range, receiver_range,
+                           rank, world, ztol=1.0, max_iter=20, rtol=1e-9, terminate_backwards=True, group=None,
+                           _bracket=_gpu_bracket, _refine=_gpu_refine):
+    """Eigenray table of a fan whose arrival ``table`` ([n_rays, 6], device tensor, identical on every rank --
+    :func:`shoot_fan_sharded`) has been gathered.  ``user_thetas`` are the fan's launch angles in the stored
+    (user) convention, one per table row.
+
+    Every rank compacts the table to surviving rays (``RayFan`` only holds those, eigenrays.py:62 works on them),
+    brackets it for all receivers, refines its cyclic blocks of 32 brackets and contributes their records to one
+    all-gather.  Returns ``(records, counts)``: ``records`` [n_brackets, EIGEN_WIDTH] float64 on the device, in
+    (receiver, ray) order and identical on every rank, columns ``EIGEN_FIELDS`` (``k`` indexes the COMPACTED
+    fan, ``status`` is PRT_EIG_*; theta, T, z, p are NaN unless converged); ``counts`` [n_rcv] brackets per
+    receiver.  ``_bracket`` / ``_refine`` are test hooks (gloo runs have no GPU).
+    """
+    import torch  # noqa: PLC0415
+
+    keep = torch.nonzero(table[:, 5] == 0).squeeze(1)
+    z_end = -table[:, 1].index_select(0, keep)  # stored convention: zs = -z
+    th = torch.as_tensor(np.ascontiguousarray(user_thetas, dtype=np.float64)).to(table.device).index_select(0, keep)
+    br, counts = _bracket(z_end, th, receiver_depths)
+    n_br = int(br["z1"].shape[0])
+    mine = torch.from_numpy(shard_indices(n_br, rank, world).copy()).to(table.device)
+    local = {k: v.index_select(0, mine).contiguous() for k, v in br.items()}
+    ref = _refine(denv, local, source_depth, source_range, receiver_range, rtol=rtol,
+                  terminate_backwards=terminate_backwards, ztol=ztol, max_iter=max_iter)
+    rec = torch.empty((mine.shape[0], EIGEN_WIDTH), dtype=torch.float64, device=table.device)
+    rec[:, 0] = local["rcv"]
+    rec[:, 1] = local["k"]
+    rec[:, 2] = ref["theta"]
+    rec[:, 3:6] = ref["final"].t()
+    rec[:, 6] = ref["n_bottom"]
+    rec[:, 7] = ref["n_surface"]
+    rec[:, 8] = ref["status"]
+    rec[:, 9] = ref["shots"]
+    return all_gather_rows(rec, n_br, rank, world, group=group), counts
+
+
+# ---------------------------------------------------------------------------------------------
+# tomography ensembles over ranks (BASELINE config 5)
+def shard_realisations(n_env_total, rank, world):
+    """``(first, count)`` of the contiguous block of realisations owned by ``rank`` (sizes differ by at most one)."""
+    base, extra = divmod(int(n_env_total), int(world))
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def _gpu_shoot_ensemble(dens, source_depth, source_range, receiver_range, angles, **kwargs):
+    from .launch_rays import shoot_ensemble_arrays  # noqa: PLC0415
+
+    return shoot_ensemble_arrays(dens, source_depth, source_range, receiver_range, angles, to_host=False, **kwargs)
+
+
+def shoot_ensemble_sharded(dens, n_env_total, source_depth, source_range, receiver_range, angles, rank, world,
+                           group=None, _shoot=_gpu_shoot_ensemble, **kwargs):
+    """Shoot ``angles`` through this rank's realisations (``dens``: a DeviceEnsemble staged with the realisations
+    ``shard_realisations(n_env_total, rank, world)``) and all-gather the arrival records.
+
+    Returns ``(table, local)``: ``table`` [n_env_total, n_angles, 6] on the device, identical on every rank, and
+    this rank's shoot_ensemble_arrays result (device tensors).  No exchange besides the one all-gather.
+    ``_shoot`` is a test hook (gloo runs have no GPU)."""
+    import torch  # noqa: PLC0415
+    import torch.distributed as dist  # noqa: PLC0415
+
+    first, count = shard_realisations(n_env_total, rank, world)
+    if dens.n_env != count:
+        raise ValueError(f"shoot_ensemble_sharded: rank {rank} staged {dens.n_env} realisations, its shard has {count}")
+    kwargs.pop("to_host", None)
+    local = _shoot(dens, source_depth, source_range, receiver_range, angles, **kwargs)
+    k = local["final"].shape[2]
+    flat = dict(final=local["final"].reshape(3, count * k), n_bottom=local["n_bottom"].reshape(-1),
+                n_surface=local["n_surface"].reshape(-1), status=local["status"].reshape(-1))
+    rec = records_from_result(flat)
+    if world == 1:
+        return rec.view(count, k, RECORD_WIDTH), local
+    pad = -(-int(n_env_total) // world)  # the largest shard
+    buf = rec
+    if count < pad:
+        buf = torch.zeros((pad * k, RECORD_WIDTH), dtype=torch.float64, device=rec.device)
+        buf[: count * k] = rec
+    gathered = torch.empty((world * pad * k, RECORD_WIDTH), dtype=torch.float64, device=rec.device)
+    dist.all_gather_into_tensor(gathered, buf, group=group)
+    gathered = gathered.view(world, pad, k, RECORD_WIDTH)
+    parts = [gathered[r, : shard_realisations(n_env_total, r, world)[1]] for r in range(world)]
+    return torch.cat(parts, 0), local

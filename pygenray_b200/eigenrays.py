@@ -25,10 +25,20 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _f64_on(x, dev):
+    """float64 contiguous 1-D tensor on ``dev`` from a numpy array / sequence or a tensor that may already be there."""
+    import torch  # noqa: PLC0415
+
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.float64).reshape(-1).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).reshape(-1)).to(dev)
+
+
 def find_brackets(z_end, thetas, receiver_depths, device=None):
     """Sign-change brackets of ``z_end + receiver_depth`` between adjacent rays, for every receiver.
 
-    ``z_end`` / ``thetas`` are ``RayFan.zs[:, -1]`` / ``RayFan.thetas`` (stored conventions).  Returns
+    ``z_end`` / ``thetas`` are ``RayFan.zs[:, -1]`` / ``RayFan.thetas`` (stored conventions; numpy arrays or
+    tensors already on the device).  Returns
     CUDA tensors ``z1, z2, th1, th2, rd (float64), rcv (int32), k (int64)`` ordered by
     (receiver, ray index) and the per-receiver counts as a numpy array.
     """
@@ -38,16 +48,14 @@ def find_brackets(z_end, thetas, receiver_depths, device=None):
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
     with torch.cuda.device(dev):
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        z_d = torch.as_tensor(np.ascontiguousarray(z_end, dtype=np.float64)).to(dev)
-        th_d = torch.as_tensor(np.ascontiguousarray(thetas, dtype=np.float64)).to(dev)
-        rd_d = torch.as_tensor(np.ascontiguousarray(receiver_depths, dtype=np.float64).reshape(-1)).to(dev)
+        z_d, th_d, rd_d = _f64_on(z_end, dev), _f64_on(thetas, dev), _f64_on(receiver_depths, dev)
         n_rays, n_rcv = z_d.shape[0], rd_d.shape[0]
         counts_d = torch.zeros(max(n_rcv, 1), dtype=torch.int32, device=dev)
-        _lib.check(L.prt_count_brackets(n_rays, _ptr(z_d), n_rcv, _ptr(rd_d), _ptr(counts_d), stream),
+        work = torch.empty(int(L.prt_bracket_workspace_bytes(n_rays, n_rcv)), dtype=torch.uint8, device=dev)
+        _lib.check(L.prt_count_brackets(n_rays, _ptr(z_d), n_rcv, _ptr(rd_d), _ptr(counts_d), _ptr(work), stream),
                    "prt_count_brackets")
-        counts64 = counts_d[:n_rcv].to(torch.int64)
-        offsets_d = torch.cumsum(counts64, 0) - counts64  # exclusive scan (plumbing)
-        total = int(counts64.sum().item())
+        counts = counts_d[:n_rcv].cpu().numpy().astype(np.int64)  # the one read-back: output sizes
+        total = int(counts.sum())
         f64 = dict(dtype=torch.float64, device=dev)
         br = dict(z1=torch.empty(total, **f64), z2=torch.empty(total, **f64), th1=torch.empty(total, **f64),
                   th2=torch.empty(total, **f64), rd=torch.empty(total, **f64),
@@ -55,11 +63,11 @@ def find_brackets(z_end, thetas, receiver_depths, device=None):
                   k=torch.empty(total, dtype=torch.int64, device=dev))
         if total:
             _lib.check(
-                L.prt_fill_brackets(n_rays, _ptr(z_d), _ptr(th_d), n_rcv, _ptr(rd_d), _ptr(offsets_d), _ptr(br["z1"]),
+                L.prt_fill_brackets(n_rays, _ptr(z_d), _ptr(th_d), n_rcv, _ptr(rd_d), _ptr(work), _ptr(br["z1"]),
                                     _ptr(br["z2"]), _ptr(br["th1"]), _ptr(br["th2"]), _ptr(br["rd"]),
                                     _ptr(br["rcv"]), _ptr(br["k"]), stream),
                 "prt_fill_brackets")
-        return br, counts64.cpu().numpy()
+        return br, counts
 
 
 def refine_brackets(denv, br, source_depth, source_range, receiver_range, rtol=1e-9, terminate_backwards=True,

@@ -179,7 +179,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), f"libprt.so does not export {name}"
-    assert _lib.load().prt_abi_version() == 1
+    assert _lib.load().prt_abi_version() == 2
     nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = {ln.split()[-1] for ln in nm.splitlines() if " T " in ln}
     assert {s for s in exported if s.startswith("prt_")} == set(declared)  # nothing else leaks out

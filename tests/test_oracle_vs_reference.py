@@ -116,13 +116,12 @@ def test_reference_golden_fixture_munk_regression():
     o = orc.shoot_fan(oenv, 1300.0, 0.0, 50e3, angles_deg=user, range_save=np.linspace(0, 50e3, 50))  # internal = user
     assert (o["status"] == 0).all()
     ts, zs, ps = o["traj"][:, 0], -o["traj"][:, 1], -o["traj"][:, 2]
-    # reference tolerances: ts atol 1e-6 (+ default rtol 1e-7 -> 4.3e-6 s at t = 33 s), zs 0.1 m, counts exact.
-    # The 15 m fixture grid is in the chaotic-step regime: the reference's own two variants differ by
-    # 2.2e-6 s / 2e-2 m on it and the reference run in this container misses the stored fixture by
-    # 1.3e-6 s / 9e-3 m (SURVEY.md sections 4, 8c).  The oracle sits in the same noise class
-    # (measured 4.4e-6 s / 4e-2 m on the -8 deg ray, < 1e-6 s on the others), so the time tolerance is
-    # widened to 1e-5 s here; depth tolerance and exact counts are the reference's own.
-    np.testing.assert_allclose(ts, g["fixture_ts"], atol=1e-5)
+    # The reference's OWN assertions (tests/test_physics.py:360-386): ts atol 1e-6 + numpy's default rtol 1e-7
+    # (a 4.3e-6 s window at t = 33 s), zs / ps atol 0.1, counts exact.  The 15 m fixture grid is in the
+    # chaotic-step regime (the reference's two variants differ by 2.2e-6 s / 2e-2 m on it);
+    # the oracle's worst ray sits at 4.0e-6 s, inside the window -- any change of the arithmetic contract has to
+    # keep it there.
+    np.testing.assert_allclose(ts, g["fixture_ts"], atol=1e-6)
     assert np.median(np.abs(ts - g["fixture_ts"]).max(axis=1)) < 1e-6
     np.testing.assert_allclose(zs, g["fixture_zs"], atol=0.1)
     np.testing.assert_allclose(ps, g["fixture_ps"], atol=0.1)
@@ -293,3 +292,100 @@ def test_eigenrays_against_reference_find_eigenrays():
         ids = np.sum(np.diff(np.sign(ps)) != 0, axis=1) * np.sign(ref["theta"][conv])
         assert np.array_equal(np.array([int(v) for v in ids]), g[f"e{i}_ray_id_int"])
         assert np.abs(-o["traj"][:, 1] - g[f"e{i}_zs"]).max() < 2e-3  # both sides converged to ztol = 1e-3
+
+
+# ---- BASELINE configs 3 and 4: 1000 km through the internal-wave field (2001 x 1201 grid) ---------------------
+def _three_way(o, a, b, rows, comp):
+    """Distances oracle-jit, oracle-nojit and jit-nojit of one arrival component over `rows`."""
+    return [np.abs(x - y)[rows, comp] for x, y in ((o, a), (o, b), (a, b))]
+
+
+def test_config3_1000km_oracle_is_a_third_run_of_the_reference():
+    """64 rays of the 1 048 576-ray config-3 fan (ray indices spread evenly over the fan), 1000 km.
+
+    On this grid the reference does not reproduce itself: its JIT and no-JIT variants end 0.3 m / 1.3e-5 s apart
+    in the median and kilometres apart on rays that bounce ten times, and one steep ray survives in one variant
+    only.  What can be asserted -- and is -- is that the oracle is statistically indistinguishable from a third
+    run: over the bounce-free rays its distance to either variant is within 2x the distance between the variants
+    (median, 90th percentile and maximum; measured ratios 0.9-1.7), kept/dropped and bounce counts are exact
+    wherever the variants agree on a bounce-free ray, and the work per ray (RHS evaluations) is the reference's."""
+    g, gn = golden("ref_cfg3_sub_jit.npz"), golden("ref_cfg3_sub_nojit.npz")
+    assert np.array_equal(g["ray_index"], np.round(np.linspace(0, (1 << 20) - 1, 64)).astype(np.int64))
+    assert np.array_equal(g["al_internal_angles"], np.linspace(-15.0, 15.0, 1 << 20)[g["ray_index"]])
+    import hashlib
+    import pygenray_b200 as pr
+
+    env = make_env(cases.config3_arrays())
+    arrs = pr._unpack_envi(env, flatearth=False)
+    assert hashlib.sha256(np.ascontiguousarray(arrs[0]).tobytes()).hexdigest() == str(g["cin_sha"])
+    assert hashlib.sha256(np.ascontiguousarray(arrs[1]).tobytes()).hexdigest() == str(g["cpin_sha"])
+    assert np.array_equal(arrs[6], g["bottom_angles"])
+    oenv = oracle_env_from(env, False)
+    o = orc.shoot_fan(oenv, 1000.0, 0.0, 1000e3, angles_deg=g["al_internal_angles"], range_save=g["al_range_save"])
+    nb_g, nb_n = g["al_n_bottom"] + g["al_n_surface"], gn["al_n_bottom"] + gn["al_n_surface"]
+    free = g["al_ok"] & gn["al_ok"] & (nb_g == 0) & (nb_n == 0)
+    assert free.sum() >= 50
+    assert (o["status"][free] == 0).all() and ((o["n_bottom"] + o["n_surface"])[free] == 0).all()
+    for comp in (1, 0):  # arrival depth, arrival time
+        d_oj, d_on, d_jn = _three_way(o["final"], g["al_final"], gn["al_final"], free, comp)
+        for stat in (np.median, lambda v: np.percentile(v, 90), np.max):
+            assert max(stat(d_oj), stat(d_on)) <= 2.0 * stat(d_jn), (comp, stat(d_oj), stat(d_on), stat(d_jn))
+    # bouncing rays (|angle| > 12.9 deg, 10-28 reflections in 1000 km): chaotic in the reference itself (the two
+    # variants count different bounces on 4 of the 8).  Kept like the JIT variant; bounce counts within the
+    # variants' own spread + 3 of the nearer variant
+    bouncing = g["al_ok"] & ~free
+    assert bouncing.sum() >= 6 and (o["status"][bouncing] == 0).all()
+    for k in np.flatnonzero(bouncing):
+        vo = np.array([o["n_bottom"][k], o["n_surface"][k]])
+        vg = np.array([g["al_n_bottom"][k], g["al_n_surface"][k]])
+        vn = np.array([gn["al_n_bottom"][k], gn["al_n_surface"][k]]) if gn["al_ok"][k] else vg
+        spread = np.abs(vg - vn).sum()
+        assert min(np.abs(vo - vg).sum(), np.abs(vo - vn).sum()) <= spread + 3, (k, vo, vg, vn)
+    exact = sum(int(o["n_bottom"][k] == g["al_n_bottom"][k] and o["n_surface"][k] == g["al_n_surface"][k])
+                for k in np.flatnonzero(bouncing))
+    assert exact >= 3  # the negative steep rays (10-15 reflections) reproduce exactly
+    assert abs(o["counters"][:, 0].sum() / g["al_nfev"].sum() - 1) < 0.01
+
+
+def test_config4_eigenrays_at_1000km_against_reference_find_eigenrays():
+    """The reference's shoot_rays + find_eigenrays through 1000 km of the config-3 field: an 81-ray fan around a
+    caustic near -9 deg, 3 receiver depths.  The fan's arrival depths differ by 2-3 m between the reference's own
+    variants (fan spacing 0.0005 deg), so brackets may sit one ray apart and converged launch angles agree to
+    ~5e-6 rad, not 1e-6: the oracle is held to the variants' own spread.  ztol = 1 (reference default): same
+    eigenrays found; ztol = 0.05: the variants themselves find different sets (1 vs 2 of 3 brackets), the oracle's
+    count must lie within theirs +- 1; ztol = 1e-3 (config 4): no receiver converges everywhere and the reference
+    RAISES (RayFan([]) -> AxisError) -- recorded in the golden file, the product returns empty fans instead."""
+    g, gn = golden("ref_cfg4_sub_jit.npz"), golden("ref_cfg4_sub_nojit.npz")
+    assert str(g["z3_raised"]) == "AxisError" and str(gn["z3_raised"]) == "AxisError"
+    oenv = oracle_env_from(make_env(cases.config3_arrays()), False)
+    user = g["user_angles"]
+    assert np.array_equal(g["fan_thetas"], user) and np.array_equal(g["fan_ray_ids"], gn["fan_ray_ids"])
+    o = orc.shoot_fan(oenv, 1000.0, 0.0, 1000e3, angles_deg=-user, range_save=np.linspace(0, 1000e3, 11))
+    assert (o["status"] == 0).all() and (o["n_bottom"] + o["n_surface"]).sum() == 0
+    z_o, z_j, z_n = -o["final"][:, 1], g["fan_zs"][:, -1], gn["fan_zs"][:, -1]
+    assert max(np.abs(z_o - z_j).max(), np.abs(z_o - z_n).max()) <= 2.0 * np.abs(z_j - z_n).max()
+    t_o, t_j, t_n = o["final"][:, 0], g["fan_ts"][:, -1], gn["fan_ts"][:, -1]
+    assert max(np.abs(t_o - t_j).max(), np.abs(t_o - t_n).max()) <= 2.0 * np.abs(t_j - t_n).max()
+    ids = np.sum(np.diff(np.sign(-o["traj"][:, 2])) != 0, axis=1) * np.sign(user)
+    assert np.array_equal(np.array([str(v) for v in ids]), g["fan_ray_ids"])
+    for i, rd in enumerate(g["receiver_depths"]):
+        k_o = np.where(np.diff(np.sign(z_o + rd)))[0]
+        k_j = np.where(np.diff(np.sign(z_j + rd)))[0]
+        assert len(k_o) == len(k_j) == int(g[f"z1_e{i}_num"]) and np.abs(k_o - k_j).max() <= 1
+        args = (oenv, z_o[k_o], z_o[k_o + 1], user[k_o], user[k_o + 1], np.full(len(k_o), rd), 1000.0, 0.0, 1000e3)
+        r1 = orc.refine_brackets(*args, ztol=1.0, max_iter=20)
+        conv = r1["status"] == 0
+        assert conv.sum() == int(g[f"z1_e{i}_found"]) == int(gn[f"z1_e{i}_found"])
+        spread_th = np.abs(np.radians(gn[f"z1_e{i}_launch"] - g[f"z1_e{i}_launch"])).max()
+        spread_t = np.abs(gn[f"z1_e{i}_ts_end"] - g[f"z1_e{i}_ts_end"]).max()
+        assert np.abs(np.radians(r1["theta"][conv] - g[f"z1_e{i}_launch"])).max() <= 2.0 * spread_th
+        assert np.abs(r1["final"][conv, 0] - g[f"z1_e{i}_ts_end"]).max() <= 2.0 * spread_t
+        assert np.abs(-r1["final"][conv, 1] + rd).max() < 1.0
+        assert np.array_equal(r1["n_bottom"][conv], g[f"z1_e{i}_nb"]) and np.array_equal(r1["n_surface"][conv], g[f"z1_e{i}_ns"])
+        r05 = orc.refine_brackets(*args, ztol=0.05, max_iter=20)
+        found = int((r05["status"] == 0).sum())
+        lo, hi = sorted((int(g[f"z05_e{i}_found"]), int(gn[f"z05_e{i}_found"])))
+        assert lo - 1 <= found <= hi + 1
+        assert (np.abs(-r05["final"][r05["status"] == 0, 1] + rd) < 0.05).all()
+        r3 = orc.refine_brackets(*args, ztol=1e-3, max_iter=20)
+        assert ((r3["status"] == 0) | (r3["status"] == 2)).all() and (r3["shots"][r3["status"] == 2] == 22).all()
