@@ -1,22 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- ray-km/s of the ray-fan hot path on B200 (driver contract).
+"""bench.py -- ray-km/s and eigenrays/s of the ray-fan / eigenray hot path on B200 (driver contract).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg1|cfg3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg3|cfg2|cfg1|cfg5]
 
-One "step" = one pass of the hot path over one fan: every launch angle of the workload integrated
-from the source to the receiver range, trajectories resampled on the save grid, arrival table out.
-Default workload = BASELINE.json configs[1]: range-dependent 200x500 gridded SSP with a seamount,
-10 000-ray fan (+-15 deg) to 500 km, 1001 save points per ray  (5e6 ray-km per step).
+One "step" = one pass of the hot path over one fan: every launch angle integrated from the source to the receiver
+range, arrival table out (and, on N > 1 GPUs, gathered).  Default workload = the north-star target, BASELINE.json
+configs[2]: ONE 1 048 576-ray fan (+-15 deg) through 1000 km of Munk + internal-wave sound speed (2001 x 1201 grid),
+STRONG-scaled over the N ranks: launch angles dealt in cyclic blocks of 32, one NCCL all-gather of the arrival
+records inside the step (1e9 ray-km per step at every N).  `--workload cfg2` is BASELINE configs[1] (10k rays,
+500 km, 1001 save points per ray; weak scaling: N x 10k rays), cfg5 the tomography ensemble (weak: 128 realisations
+per GPU), cfg1 the reference's own CPU case.
 
-  value      ray-km/s with inputs resident in HBM (CUDA events around the kernels, max over ranks)
-  e2e        same metric through the public API pygenray_b200.shoot_rays(): host launch angles in,
-             host RayFan out, H2D/D2H inside the timed region
-  roofline   FP64 FMA pipe: algorithmic flops from per-ray device counters / kernel time, against a
-             DFMA microbenchmark measured in the same run (MEASURED_PEAKS.json has no FP64 figure)
-  cpu_baseline  the CPU oracle port (oracle/prt_oracle.c) on the box's host cores, same workload
-  --impl reference  times that CPU port alone (the reference itself is Python and cannot travel)
-N > 1 (torchrun): weak scaling -- every rank shoots its own 10k-ray fan (interleaved launch angles of
-an N x 10k fan) and the arrival tables are all-gathered over NCCL inside the step.
+  value         ray-km/s with inputs resident in HBM (CUDA events around kernels + gather, max over ranks)
+  e2e           the same through the public API with HOST buffers: host launch angles in, host arrival table out
+                (cfg3/cfg5: dist.shoot_fan_sharded / shoot_ensemble_sharded + D2H of the gathered table on rank 0;
+                cfg2/cfg1: pygenray_b200.shoot_rays, host RayFan out), H2D/D2H inside the timed region
+  roofline      FP64 FMA pipe: algorithmic flops (SURVEY.md section 8d formula on per-ray device counters, counted by an
+                untimed launch of the same fan) / kernel time, against a DFMA microbenchmark measured in the same run
+                (MEASURED_PEAKS.json has no FP64 figure)
+  eigenrays     BASELINE configs[3] on the step's fan: 64 receiver depths, bracketing + regula falsi, brackets
+                sharded over the ranks (dist.find_eigenrays_sharded), eigenrays/s at ztol 1e-3 and 1 m
+  cpu_baseline  the CPU oracle port (oracle/prt_oracle.c, all host threads) on a bounded sample of the same fan, and
+                -- when oracle/_ref holds the reference -- the unmodified Python reference on config 1 in full
+  --impl reference  times the CPU port alone on the same config (the reference is Python + SciPy + Numba; its own
+                rate is reported beside it as `python_reference`)
 """
 import argparse
 import json
@@ -31,42 +38,53 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from oracle import cases  # noqa: E402  (synthetic workload definitions shared with the tests)
+import workloads as cases  # noqa: E402  (synthetic workload definitions shared with the tests; pure numpy)
+
+N_FAN_CFG3 = 1 << 20
+REF_SAMPLE_RAYS = {"cfg3": 8192, "cfg2": 10000, "cfg1": 101, "cfg5": 8192}  # CPU legs: rays per step
 
 
 # ------------------------------------------------------------------------------------------------
 def workload(name, rank=0, world=1):
-    """-> dict(arrays, flatearth, source_depth, source_range, receiver_range, angles, n_save, label)."""
-    if name == "cfg1":
-        a = cases.config1_arrays()
-        n, lim, R, ns, flat = 101, 12.0, 100e3, 1001, True
-        label = "cfg1: Munk range-independent 100x6000 grid (flat-earth), 101 rays +-12deg, 100 km, 1001 save pts"
-    elif name == "cfg3":
-        a = cases.config3_arrays()
-        n, lim, R, ns, flat = 1 << 20, 15.0, 1000e3, 0, False
-        label = "cfg3: Munk + internal waves 2001x1201 grid, 1,048,576 rays +-15deg, 1000 km, arrival table only"
-    elif name == "cfg5":
+    """-> dict(arrays, flatearth, source_depth, source_range, receiver_range, angles (this rank's), all_angles,
+    n_total, n_save, scaling, label, ...).  Internal launch angles (positive = downwards)."""
+    if name == "cfg5":
         n_env = 128  # per GPU (1024 realisations over 8 GPUs)
         a = cases.config2_arrays()
         a["c_stack"] = np.stack([cases.config5_realisation(rank * n_env + i)["c"] for i in range(n_env)])
-        n, lim, R, ns, flat = 4096, 15.0, 500e3, 0, False
-        label = ("cfg5: tomography ensemble, 128 perturbed realisations (per GPU) of the 200x500 grid x 4096 rays "
-                 "+-15deg, 500 km, arrival tables only")
-        return dict(arrays=a, flatearth=flat, source_depth=1000.0, source_range=0.0, receiver_range=R,
-                    angles=np.linspace(-lim, lim, n), n_total=n * n_env * world, n_save=ns, label=label, name=name,
-                    rays_per_gpu=n * n_env, n_env=n_env)
-    else:
-        a = cases.config2_arrays()
-        n, lim, R, ns, flat = 10000, 15.0, 500e3, 1001, False
-        label = "cfg2: range-dependent 200x500 gridded SSP + seamount bathymetry, 10k rays +-15deg, 500 km, 1001 save pts"
-    # weak scaling: an N x n-ray fan dealt to the ranks in cyclic blocks of 32 angles (pygenray_b200.dist)
+        n, lim, R = 4096, 15.0, 500e3
+        ang = np.linspace(-lim, lim, n)
+        return dict(arrays=a, flatearth=False, source_depth=1000.0, source_range=0.0, receiver_range=R, angles=ang,
+                    all_angles=ang, n_total=n * n_env * world, n_save=0, name=name, rays_per_gpu=n * n_env,
+                    n_env=n_env, scaling="weak",
+                    label="cfg5: tomography ensemble, 128 perturbed realisations per GPU of the 200x500 grid x 4096 rays "
+                          "+-15deg, 500 km, arrival tables only")
     from pygenray_b200.dist import shard_indices
 
-    all_angles = np.linspace(-lim, lim, n * world)
-    mine = shard_indices(n * world, rank, world)
+    if name == "cfg1":
+        a, n, lim, R, ns, flat, scaling = cases.config1_arrays(), 101 * world, 12.0, 100e3, 1001, True, "weak"
+        label = "cfg1: Munk range-independent 100x6000 grid (flat-earth), 101 rays +-12deg, 100 km, 1001 save pts"
+    elif name == "cfg2":
+        a, n, lim, R, ns, flat, scaling = cases.config2_arrays(), 10000 * world, 15.0, 500e3, 1001, False, "weak"
+        label = ("cfg2: range-dependent 200x500 gridded SSP + seamount bathymetry, 10k rays +-15deg per GPU, 500 km, "
+                 "1001 save pts")
+    else:
+        a, n, lim, R, ns, flat, scaling = cases.config3_arrays(), N_FAN_CFG3, 15.0, 1000e3, 0, False, "strong"
+        label = ("cfg3: ONE 1,048,576-ray fan +-15deg, Munk + internal waves on a 2001x1201 grid, 1000 km, arrival "
+                 "table (strong scaling: the fan is dealt to the ranks in cyclic blocks of 32 angles)")
+    all_angles = np.linspace(-lim, lim, n)
+    mine = shard_indices(n, rank, world)
     return dict(arrays=a, flatearth=flat, source_depth=1000.0, source_range=0.0, receiver_range=R,
-                angles=np.ascontiguousarray(all_angles[mine]), n_total=n * world, n_save=ns, label=label,
-                name=name, rays_per_gpu=n)
+                angles=np.ascontiguousarray(all_angles[mine]), all_angles=all_angles, n_total=n, n_save=ns, label=label,
+                name=name, rays_per_gpu=len(mine), scaling=scaling)
+
+
+def config_block(w, world):
+    """The `config` object of the JSON line: identical for both arms (the driver compares them)."""
+    return {"workload": w["label"], "rays_total": int(w["n_total"]),
+            "range_km": abs(w["receiver_range"] - w["source_range"]) / 1e3, "n_save": int(w["n_save"]), "rtol": 1e-9,
+            "atol": 1e-6, "n_gpus": int(world), "scaling": w["scaling"],
+            "l2": "256 MiB buffer zeroed between timed steps (untimed)"}
 
 
 def make_env(pr, a, flat):
@@ -117,6 +135,7 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
+# CPU legs (the only users of oracle/ in this file; never inside a GPU-timed region)
 def oracle_env(w):
     """Oracle-side environment from the same arrays through the same (host) unpacking as the product."""
     import pygenray_b200 as pr  # host-only pieces: environment object, _unpack_envi, spline coefficients
@@ -128,8 +147,7 @@ def oracle_env(w):
     return orc, orc.OracleEnv(arrs[0], arrs[1], arrs[2], arrs[3], arrs[4], arrs[5], ba_x, ba_c)
 
 
-def time_oracle(w, angles, threads=0):
-    orc, oenv = oracle_env(w)
+def time_oracle(orc, oenv, w, angles, threads=0):
     rs = np.linspace(w["source_range"], w["receiver_range"], w["n_save"]) if w["n_save"] else None
     t0 = time.perf_counter()
     out = orc.shoot_fan(oenv, w["source_depth"], w["source_range"], w["receiver_range"], angles_deg=angles,
@@ -139,54 +157,94 @@ def time_oracle(w, angles, threads=0):
     return km / dt, dt, orc.num_threads() if threads <= 0 else threads
 
 
+def sample_angles(w, n_sample):
+    """Evenly spread sub-sample of the workload's full fan (both ends included)."""
+    full = w["all_angles"]
+    if n_sample >= len(full):
+        return full
+    return np.ascontiguousarray(full[np.round(np.linspace(0, len(full) - 1, n_sample)).astype(np.int64)])
+
+
+def python_reference_baseline(timeout=240):
+    """The unmodified Python reference (oracle/_ref, see oracle/install_ref.py) on config 1 in full, on this host."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "pygenray")):
+        return {"unavailable": "oracle/_ref/pygenray not present (python oracle/install_ref.py where /root/reference exists)"}
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "oracle", "stubs"), ref_dir])
+    env["NUMBA_CACHE_DIR"] = os.environ.get("NUMBA_CACHE_DIR", "/tmp/numba_cache_prt_ref")
+    env.pop("NUMBA_DISABLE_JIT", None)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "time_reference.py")], env=env,
+                           capture_output=True, text=True, timeout=timeout)
+        line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+        if p.returncode != 0 or not line:
+            return {"unavailable": f"time_reference.py rc={p.returncode}: {p.stderr.strip()[-200:]}"}
+        r = json.loads(line[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    return {"kind": "reference", "what": "unmodified pygenray (Python + SciPy RK45 + Numba) from oracle/_ref",
+            "sample": r["config"] + ", in full", "cores": r["cores"], "unit": "ray-km/s",
+            "sequential_per_core": r["sequential_ray_km_per_s_per_core"],
+            "value": r.get("pool_ray_km_per_s"), "value_is": "shoot_rays(n_processes=cores) wall incl. pool spawn",
+            "upper_bound_all_cores": r["sequential_ray_km_per_s_per_core"] * r["cores"]}
+
+
 def run_reference(args):
-    """--impl reference: the CPU port of the reference's path, all host threads, same config."""
+    """--impl reference: the CPU port of the reference's path, all host threads, on the arm's config; each step a
+    bounded sample of the workload.  Rank 0 alone runs."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    w = workload(args.workload)
-    angles = w["angles"] if args.ref_rays <= 0 else w["angles"][:: max(1, len(w["angles"]) // args.ref_rays)]
+    w = workload(args.workload, 0, world)
+    n_sample = args.ref_rays if args.ref_rays > 0 else REF_SAMPLE_RAYS[args.workload]
+    angles = sample_angles(w, n_sample)
+    orc, oenv = oracle_env(w)
     for _ in range(args.warmup):
-        time_oracle(w, angles[:: max(1, len(angles) // 64)])
+        time_oracle(orc, oenv, w, angles[:: max(1, len(angles) // 256)])
     vals, dts = [], []
     cores = 0
     for _ in range(args.steps):
-        v, dt, cores = time_oracle(w, angles)
+        v, dt, cores = time_oracle(orc, oenv, w, angles)
         vals.append(v); dts.append(dt)
     value = float(np.sum([v * d for v, d in zip(vals, dts)]) / np.sum(dts))
-    sample = f"{len(angles)} of {len(w['angles'])} rays of the workload per step, {cores} pthreads"
+    sample = (f"{len(angles)} rays spread evenly over the workload's {w['n_total']}-ray fan per step "
+              f"({np.mean(dts):.1f} s), oracle/prt_oracle.c on {cores} pthreads")
     line = {
-        "impl": "reference", "metric": "ray_km_per_s", "value": value, "unit": "ray-km/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": "ray_km_per_s", "value": value, "unit": "ray-km/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(dts)),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["label"], "rays_per_step": int(len(angles))},
-        "cpu_baseline": {"value": value, "unit": "ray-km/s", "cores": cores, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_block(w, world),
+        "cpu_baseline": {"value": value, "unit": "ray-km/s", "cores": cores, "kind": "port", "sample": sample,
+                         "python_reference": None if args.no_python_ref else python_reference_baseline()},
         "e2e": {"value": value, "unit": "ray-km/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference is pure Python (scipy solve_ivp + numba); it cannot travel to the GPU box, so this arm "
-                "times the plain-C restatement oracle/prt_oracle.c (about 40x faster per core than the Python "
-                "reference measured in the build container: 5.1-5.5 k ray-km/s/core, BASELINE.md)",
+        "note": "the reference is pure Python (scipy solve_ivp + numba); this arm times its plain-C restatement "
+                "oracle/prt_oracle.c on all host threads (a rate: per-step sample stated above), with the unmodified "
+                "Python reference timed beside it on config 1 (cpu_baseline.python_reference)",
     }
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
     import pygenray_b200 as pr
     from pygenray_b200 import _lib
+    from pygenray_b200 import dist as pdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa = None
     if world > 1:
-        from pygenray_b200.dist import bind_to_gpu_numa
-        if os.environ.get("PRT_NUMA_BIND", "1") != "0":
-            numa = bind_to_gpu_numa(local_rank)  # before the first pinned allocation (first touch places it)
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.require_gpu()
 
@@ -218,14 +276,17 @@ def run_b200(args):
     else:
         denv = pr.DeviceEnvironment(*arrs, device=local_rank)
     angles = w["angles"]
-    n = len(angles) * max(n_env, 1)
+    all_angles = w["all_angles"]
+    n = len(angles) * max(n_env, 1)            # rays shot by this rank per step
+    n_total = w["n_total"]
     R_km = abs(w["receiver_range"] - w["source_range"]) / 1e3
     n_save = w["n_save"]
+    zs, r0, r1 = w["source_depth"], w["source_range"], w["receiver_range"]
+    gathers = (world > 1) or (w["name"] == "cfg3")
 
     # ---- resident inputs / outputs for the device-timed leg
-    import ctypes as C
     ang_d = torch.from_numpy(angles).to(dev)
-    rs_d = torch.from_numpy(np.linspace(w["source_range"], w["receiver_range"], n_save)).to(dev) if n_save else None
+    rs_d = torch.from_numpy(np.linspace(r0, r1, n_save)).to(dev) if n_save else None
     traj_d = torch.empty((3, n, n_save), dtype=torch.float64, device=dev) if n_save else None
     final_d = torch.empty((3, n), dtype=torch.float64, device=dev)
     nb_d = torch.empty(n, dtype=torch.int32, device=dev)
@@ -233,38 +294,39 @@ def run_b200(args):
     st_d = torch.empty(n, dtype=torch.int32, device=dev)
     cnt_d = torch.empty((6, n), dtype=torch.int32, device=dev)
     flips_d = torch.empty(n, dtype=torch.int32, device=dev) if n_save else None
-    from pygenray_b200 import dist as pdist
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
     def p(t):
         return None if t is None else C.c_void_p(t.data_ptr())
 
-    def launch(flips):
+    def launch(flips, counters=None):
         if n_env:
-            return L.prt_shoot_ensemble(denv.handle, n_env, len(angles), p(ang_d), w["source_depth"], w["source_range"],
-                                        w["receiver_range"], 1e-9, 1e-6, 1, n_save, p(rs_d), p(traj_d), p(final_d),
-                                        p(nb_d), p(ns_d), p(st_d), p(cnt_d), 1, flips, 1 << 20,
-                                        C.c_void_p(stream.cuda_stream))
-        return L.prt_shoot_fan(denv.handle, n, p(ang_d), None, w["source_depth"], w["source_range"],
-                               w["receiver_range"], 1e-9, 1e-6, 1, n_save, p(rs_d), p(traj_d), p(final_d), p(nb_d),
-                               p(ns_d), p(st_d), p(cnt_d), 1, flips, 1 << 20, C.c_void_p(stream.cuda_stream))
+            return L.prt_shoot_ensemble(denv.handle, n_env, len(angles), p(ang_d), zs, r0, r1, 1e-9, 1e-6, 1, n_save,
+                                        p(rs_d), p(traj_d), p(final_d), p(nb_d), p(ns_d), p(st_d), p(counters), 1,
+                                        flips, 1 << 20, C.c_void_p(stream.cuda_stream))
+        return L.prt_shoot_fan(denv.handle, n, p(ang_d), None, zs, r0, r1, 1e-9, 1e-6, 1, n_save, p(rs_d), p(traj_d),
+                               p(final_d), p(nb_d), p(ns_d), p(st_d), p(counters), 1, flips, 1 << 20,
+                               C.c_void_p(stream.cuda_stream))
+
+    table_box = [None]
 
     def device_step():
         _lib.check(launch(p(flips_d)), "prt_shoot_fan")
-        if world > 1:  # the path's only exchange: all-gather the arrival records (6 doubles per ray)
+        if gathers:  # the path's only exchange: all-gather the arrival records (6 doubles per ray)
             rec = pdist.records_from_result(dict(final=final_d, n_bottom=nb_d, n_surface=ns_d, status=st_d))
             if n_env:  # ensembles shard by realisation: plain concatenation
                 dist.all_gather_into_tensor(torch.empty((world * n, 6), dtype=torch.float64, device=dev), rec)
             else:
-                pdist.all_gather_arrivals(rec, w["n_total"], rank, world)
+                table_box[0] = pdist.all_gather_arrivals(rec, n_total, rank, world)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 3)
+    for _ in range(n_warm):
         device_step()
     barrier()
     fp64_peak = L.prt_measure_fp64_peak(local_rank, 2000)
@@ -298,7 +360,8 @@ def run_b200(args):
     ms_per_step = float(np.mean(step_ms))
     value = total_km / (ms_per_step * 1e-3)
 
-    # ---- dominant kernel alone (no gather), for the roofline
+    # ---- dominant kernel alone (this rank's launch, no gather), for the roofline; the flops come from one more,
+    # untimed launch of the same rays with the work counters on (the timed kernels carry none)
     for _ in range(args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -309,28 +372,37 @@ def run_b200(args):
         torch.cuda.synchronize()
         _lib.check(rc, "prt_shoot_fan")
         kern_ms.append(e0.elapsed_time(e1))
+    _lib.check(launch(None, cnt_d), "prt_shoot_fan (counters)")
+    torch.cuda.synchronize()
     cnt = cnt_d.cpu().numpy().astype(np.uint32)
     flops = algorithmic_flops(cnt)
     k_ms = float(np.mean(kern_ms))
     achieved = flops / (k_ms * 1e-3) / 1e12
-    out_bytes = (3 * n * n_save + 3 * n) * 8 + 3 * n * 4 + 6 * n * 4
+    out_bytes = (3 * n * n_save + 3 * n) * 8 + 3 * n * 4
 
     # ---- end to end through the public API (host in, host out)
     e2e_dts = []
     fan = None
+    host_table = None
+    if not n_save and rank == 0:
+        shape = (n_env * world, len(angles), 6) if n_env else (n_total, 6)
+        host_table = torch.empty(shape, dtype=torch.float64, pin_memory=True)
     for i in range(args.warmup + args.steps):
         barrier()
         t0 = time.perf_counter()
         if n_save:
-            fan = pr.shoot_rays(w["source_depth"], w["source_range"], -angles, w["receiver_range"], n_save, env,
-                                rtol=1e-9, debug=False, flatearth=w["flatearth"])
+            fan = pr.shoot_rays(zs, r0, -angles, r1, n_save, env, rtol=1e-9, debug=False, flatearth=w["flatearth"])
             n_ok = len(fan)
-        elif n_env:
-            res = pr.shoot_ensemble_arrays(denv, w["source_depth"], w["source_range"], w["receiver_range"], angles)
-            n_ok = int((res["status"] == 0).sum())
         else:
-            res = pr.shoot_fan_arrays(denv, w["source_depth"], w["source_range"], w["receiver_range"], angles=angles)
-            n_ok = int((res["status"] == 0).sum())
+            if n_env:
+                tab, _ = pdist.shoot_ensemble_sharded(denv, n_env * world, zs, r0, r1, angles, rank, world)
+            else:
+                tab, _ = pdist.shoot_fan_sharded(denv, zs, r0, r1, all_angles, rank, world)
+            n_ok = 0
+            if rank == 0:
+                host_table.copy_(tab, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                n_ok = int((host_table[..., 5] == 0).sum())
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         cnt_ok = torch.tensor([float(n_ok)], dtype=torch.float64, device=dev)
@@ -340,95 +412,122 @@ def run_b200(args):
         if i >= args.warmup:
             e2e_dts.append((float(dt.item()), float(cnt_ok.item())))
     e2e_value = float(np.mean([c * R_km / d for d, c in e2e_dts]))
-    h2d = n * 8 + n_save * 8
-    d2h = out_bytes - 6 * n * 4 + (n * 4 if n_save else 0)
+    if n_save:
+        h2d = (n * 8 + n_save * 8) * world
+        d2h = (out_bytes + n * 4) * world
+        e2e_api = "pygenray_b200.shoot_rays (host RayFan out, on every rank)"
+    else:
+        h2d = len(angles) * 8 * world
+        d2h = int(host_table.numel() * 8) if rank == 0 else 0
+        e2e_api = ("pygenray_b200.dist.shoot_ensemble_sharded" if n_env else "pygenray_b200.dist.shoot_fan_sharded") + \
+                  " + D2H of the gathered arrival table on rank 0"
 
-    # ---- eigenrays/s (BASELINE config 4): 64 receiver depths at the receiver range of this fan, ztol 1e-3,
-    # brackets from this rank's fan; bracketing + regula-falsi refinement timed end to end on the device
+    # ---- eigenrays/s (BASELINE configs[3]): 64 receiver depths at the receiver range of this fan; bracketing on the
+    # gathered table + regula-falsi refinement with the brackets dealt over the ranks, timed end to end
     eig = None
-    if n_save and not args.no_eigen:
-        from pygenray_b200.eigenrays import find_brackets, refine_brackets
+    if not n_env and not args.no_eigen:
         rds = np.linspace(200.0, 4000.0, 64)
-        zs_end = fan.zs[:, -1].copy()
-        thetas = fan.thetas.copy()
-        def eig_leg(ztol):
-            dts = []
-            for i in range(1 + 2):
+        if n_save:  # cfg1/cfg2 (weak scaling): every rank searches its own fan
+            table = pdist.records_from_result(dict(final=final_d, n_bottom=nb_d, n_surface=ns_d, status=st_d))
+            thetas_user, e_rank, e_world = -angles, 0, 1
+        else:
+            table, thetas_user, e_rank, e_world = table_box[0], -all_angles, rank, world
+
+        def eig_leg(ztol, reps):
+            dts, rec_, counts_ = [], None, None
+            for _ in range(reps):
                 barrier()
                 t0 = time.perf_counter()
-                br_, counts_ = find_brackets(zs_end, thetas, rds, device=local_rank)
-                ref_ = refine_brackets(denv, br_, w["source_depth"], w["source_range"], w["receiver_range"],
-                                       ztol=ztol, max_iter=20)
-                st_ = ref_["status"].cpu().numpy()
+                rec_, counts_ = pdist.find_eigenrays_sharded(denv, table, thetas_user, rds, zs, r0, r1, e_rank, e_world,
+                                                             ztol=ztol, max_iter=20)
                 barrier()
-                if i >= 1:
-                    dts.append(time.perf_counter() - t0)
-            found_ = int((st_ == 0).sum())
-            tot = torch.tensor([float(found_)], dtype=torch.float64, device=dev)
-            dtm = torch.tensor([float(np.mean(dts))], dtype=torch.float64, device=dev)
+                dts.append(time.perf_counter() - t0)
+            dtm = torch.tensor([float(np.min(dts))], dtype=torch.float64, device=dev)
             if world > 1:
-                dist.all_reduce(tot)
                 dist.all_reduce(dtm, op=dist.ReduceOp.MAX)
-            return br_, counts_, ref_, found_, float(tot.item() / dtm.item()), 1e3 * float(dtm.item())
+            found_ = int((rec_[:, 8] == 0).sum().item())
+            mult = world if e_world == 1 else 1  # weak workloads: one table per rank
+            return rec_, counts_, found_, float(found_ * mult / dtm.item()), 1e3 * float(dtm.item())
 
-        br, counts, ref, found, rate, ms = eig_leg(1e-3)
-        _, _, ref1, found1, rate1, ms1 = eig_leg(1.0)
-        eig = {"value": rate, "unit": "eigenrays/s", "receivers": 64, "ztol_m": 1e-3,
-               "brackets_rank0": int(counts.sum()), "found_rank0": found, "ms": ms,
-               "shots_per_bracket": float(ref["shots"].float().mean().item()),
-               "note": "on this 11 m grid the arrival depth carries ~1e-2 m of step-sequence noise (DESIGN.md "
-                       "section 5), so most brackets cannot reach 1e-3 m and run to max_iter, as in the reference",
-               "ztol_1m": {"value": rate1, "found_rank0": found1, "ms": ms1,
-                           "shots_per_bracket": float(ref1["shots"].float().mean().item())}}
-        if rank == 0:
-            host = {k: v.cpu().numpy() for k, v in br.items()}
-            sub = slice(0, min(len(host["z1"]), 2048))
+        eig_leg(1.0, 1)  # warm-up (lazy kernel load, allocator)
+        rec3, counts, found3, rate3, ms3 = eig_leg(1e-3, 1)
+        rec1, _, found1, rate1, ms1 = eig_leg(1.0, 2)
+        conv1 = rec1[rec1[:, 8] == 0, 0].long()
+        per_rcv = torch.bincount(conv1, minlength=64)
+        eig = {"value": rate3, "unit": "eigenrays/s", "receivers": 64, "ztol_m": 1e-3, "max_iter": 20,
+               "brackets": int(counts.sum()), "found": found3, "ms": ms3,
+               "shots_per_bracket": float(rec3[:, 9].mean().item()),
+               "brackets_per_s": float(counts.sum() / (ms3 * 1e-3)),
+               "sharding": f"brackets dealt to {e_world} rank(s) in cyclic blocks of 32, one all-gather of 10-double records",
+               "note": "through hundreds of km of range-dependent sound speed the arrival depth carries cm-level "
+                       "step-sequence noise (DESIGN.md section 5), so most brackets cannot reach 1e-3 m and run to "
+                       "max_iter -- in the reference alike (it raises on this config, tests/golden/ref_cfg4_sub_*)",
+               "ztol_1m": {"value": rate1, "found": found1, "ms": ms1,
+                           "shots_per_bracket": float(rec1[:, 9].mean().item()),
+                           "arrivals_per_receiver_min_max": [int(per_rcv.min().item()), int(per_rcv.max().item())]}}
+        if rank == 0 and not args.no_cpu:
+            # the same refinement on the CPU port for a bounded sample of the brackets: parity + eigenrays/s baseline
+            keep = torch.nonzero(table[:, 5] == 0).squeeze(1)
+            z_end = (-table[:, 1].index_select(0, keep)).cpu().numpy()
+            th = np.asarray(thetas_user)[keep.cpu().numpy()]
+            rcv = rec3[:, 0].long().cpu().numpy()
+            k = rec3[:, 1].long().cpu().numpy()
+            pick = np.round(np.linspace(0, len(k) - 1, min(len(k), 1024))).astype(np.int64)
             orc, oenv = oracle_env(w)
             t0 = time.perf_counter()
-            o = orc.refine_brackets(oenv, host["z1"][sub], host["z2"][sub], host["th1"][sub], host["th2"][sub],
-                                    host["rd"][sub], w["source_depth"], w["source_range"], w["receiver_range"],
-                                    ztol=1e-3, max_iter=20)
+            o = orc.refine_brackets(oenv, z_end[k[pick]], z_end[k[pick] + 1], th[k[pick]], th[k[pick] + 1],
+                                    rds[rcv[pick]], zs, r0, r1, ztol=1e-3, max_iter=20)
             dtc = time.perf_counter() - t0
             eig["cpu_baseline"] = {"value": float((o["status"] == 0).sum() / dtc), "unit": "eigenrays/s",
-                                   "cores": orc.num_threads(), "kind": "port",
-                                   "sample": f"first {sub.stop} brackets, {dtc:.1f} s"}
-            eig["parity_vs_cpu"] = bool(np.array_equal(o["theta"], ref["theta"].cpu().numpy()[sub], equal_nan=True))
+                                   "brackets_per_s": float(len(pick) / dtc), "cores": orc.num_threads(), "kind": "port",
+                                   "sample": f"{len(pick)} brackets spread evenly over the list, {dtc:.1f} s"}
+            eig["parity_vs_cpu"] = bool(np.array_equal(o["theta"], rec3[:, 2].cpu().numpy()[pick], equal_nan=True)
+                                        and np.array_equal(o["status"], rec3[:, 8].cpu().numpy()[pick]))
 
-    clocks = sampler.stop() if rank == 0 else None  # sampled over the device-timed, kernel-only and e2e legs
+    clocks = sampler.stop() if rank == 0 else None  # sampled over the device-timed, kernel-only, e2e and eigenray legs
     if rank == 0:
-        # CPU oracle on the same workload (bounded: the whole 10k fan takes seconds in C)
-        sub = angles if len(angles) <= 20000 else angles[:: len(angles) // 4096]
-        cpu_v, cpu_dt, cores = time_oracle(w, sub)
+        cpu = None
+        if not args.no_cpu:
+            sub = sample_angles(w, REF_SAMPLE_RAYS[w["name"]])  # CPU oracle on a bounded sample of the same fan
+            orc, oenv = oracle_env(w)
+            cpu_v, cpu_dt, cores = time_oracle(orc, oenv, w, sub)
+            cpu = {"value": cpu_v, "unit": "ray-km/s", "cores": cores, "kind": "port",
+                   "sample": f"{len(sub)} rays spread evenly over the same fan, {cpu_dt:.1f} s, oracle/prt_oracle.c",
+                   "python_reference": None if args.no_python_ref else python_reference_baseline()}
+        # ncu --set full capture of this kernel on this workload, if one is committed (per launch, like `achieved`)
+        traffic, traffic_src = None, None
+        tr_path = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+        if os.path.exists(tr_path):
+            with open(tr_path) as f:
+                tr = json.load(f).get(f"{w['name']}_n{world}")
+            if tr:
+                traffic, traffic_src = tr["dram_bytes"], tr["source"]
         line = {
             "metric": "ray_km_per_s", "value": value, "unit": "ray-km/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["label"], "rays_per_gpu": n, "range_km": R_km, "n_save": n_save, "rtol": 1e-9,
-                       "atol": 1e-6, "l2": "256 MiB buffer zeroed between timed steps (untimed)",
-                       **({"ensemble_staging": staging} if staging else {}),
-                       **({"numa_node_rank0": numa} if world > 1 else {}),
-                       "parallelism": f"launch angles interleaved over {world} rank(s); arrival tables all-gathered"
-                       if world > 1 else "single GPU, one thread per ray"},
+            "config": config_block(w, world),
+            "run": {"rays_per_gpu": n, **({"ensemble_staging": staging} if staging else {}),
+                    "parallelism": (f"launch angles dealt to {world} ranks in cyclic blocks of 32; arrival records "
+                                    "all-gathered (NCCL) inside the step") if world > 1 else
+                                   "single GPU, one thread per ray"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / (fp64_peak / 1e12) if fp64_peak > 0 else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload from the
-                         # ncu --set full capture summarised in profiles/r01_ncu_fan.md (11.8 MB + 200.3 MB)
-                         "traffic": 212.0e6 if (w["name"] == "cfg2" and world == 1) else None,
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "traffic_algorithmic_bytes": out_bytes,
                          "kernel": "prt_fan_kernel", "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
+                         "flops_source": "SURVEY 8d formula on the per-ray device counters of an untimed launch of the "
+                                         "same rays (rank 0's share at N > 1)",
                          "peak_source": "DFMA microbenchmark (prt_measure_fp64_peak) in this run; "
-                                        "MEASURED_PEAKS.json has no FP64 figure",
+                                        "MEASURED_PEAKS.json has no FP64 figure (nominal 37.2 TFLOP/s)",
                          "hbm_output_GBps": out_bytes / (k_ms * 1e-3) / 1e9},
-            "cpu_baseline": {"value": cpu_v, "unit": "ray-km/s", "cores": cores, "kind": "port",
-                             "sample": f"{len(sub)} rays of the same fan, {cpu_dt:.1f} s, oracle/prt_oracle.c"},
+            "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "ray-km/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h),
-                    "api": "pygenray_b200.shoot_rays" if n_save else
-                           ("pygenray_b200.shoot_ensemble_arrays" if n_env else "pygenray_b200.shoot_fan_arrays")},
+                    "d2h_bytes_per_step": int(d2h), "api": e2e_api},
             "gpu_launches": int(launches), "clocks": clocks,
-            "work": {"rays_ok": int(ok_t.item()), "nfev": int(cnt[0].sum()), "attempts": int(cnt[1].sum()),
-                     "accepted": int(cnt[2].sum()), "segments": int(cnt[3].sum()), "bisect": int(cnt[4].sum()),
-                     "dense": int(cnt[5].sum())},
+            "work": {"rays_ok": int(ok_t.item()),
+                     "rank0": {"nfev": int(cnt[0].sum()), "attempts": int(cnt[1].sum()), "accepted": int(cnt[2].sum()),
+                               "segments": int(cnt[3].sum()), "bisect": int(cnt[4].sum()), "dense": int(cnt[5].sum())}},
             "wall_s_timed_region": t_wall,
             "eigenrays": eig,
         }
@@ -443,9 +542,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg5"])
     ap.add_argument("--no-eigen", action="store_true", help="skip the eigenrays/s leg")
-    ap.add_argument("--ref-rays", type=int, default=0, help="reference arm: sub-sample the fan to about this many rays")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines (development runs)")
+    ap.add_argument("--no-python-ref", action="store_true", help="skip the Python reference baseline")
+    ap.add_argument("--ref-rays", type=int, default=0, help="CPU reference arm: rays per step (default per workload)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -39,7 +39,7 @@ import pygenray as pr  # noqa: E402  (the reference)
 from pygenray.environment import OceanEnvironment2D, munk_ssp  # noqa: E402
 from pygenray.launch_rays import _interpolate_ray, _shoot_ray_array, _unpack_envi  # noqa: E402
 
-from oracle import cases  # noqa: E402
+import workloads as cases  # noqa: E402
 
 VARIANT = os.environ.get("_PRT_GOLDEN_VARIANT", "jit")
 

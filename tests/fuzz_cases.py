@@ -1,7 +1,7 @@
 """Seeded random environments / shots for parity fuzzing (used by CPU and GPU parity tests)."""
 import numpy as np
 
-from oracle import cases
+import workloads as cases
 
 
 def random_case(seed):

@@ -21,7 +21,7 @@ def _worker(rank, world, port, n_rays, out_path):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from conftest import make_env, oracle_env_from
-    from oracle import cases
+    import workloads as cases
     from oracle import oracle as orc
     from pygenray_b200 import dist as pdist
 
@@ -43,7 +43,7 @@ def _worker(rank, world, port, n_rays, out_path):
 def test_sharded_fan_equals_single_process(tmp_path, n_rays):
     sys.path.insert(0, ROOT)
     from conftest import make_env, oracle_env_from
-    from oracle import cases
+    import workloads as cases
     from oracle import oracle as orc
     from pygenray_b200 import dist as pdist
 
@@ -103,7 +103,7 @@ def _eigen_worker(rank, world, port, out_path):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from conftest import make_env, oracle_env_from
-    from oracle import cases
+    import workloads as cases
     from oracle import oracle as orc
     from pygenray_b200 import dist as pdist
 
@@ -137,7 +137,7 @@ def _eigen_worker(rank, world, port, out_path):
 def test_sharded_eigenrays_and_ensembles_equal_single_process(tmp_path):
     sys.path.insert(0, ROOT)
     from conftest import make_env, oracle_env_from
-    from oracle import cases
+    import workloads as cases
     from oracle import oracle as orc
     from pygenray_b200 import dist as pdist
 

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import assert_same_fan, golden, make_env, oracle_env_from
-from oracle import cases
+import workloads as cases
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu

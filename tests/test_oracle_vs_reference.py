@@ -18,7 +18,7 @@ import numpy as np
 import pytest
 
 from conftest import golden, make_env, oracle_env_from, oracle_shoot_ray
-from oracle import cases
+import workloads as cases
 from oracle import oracle as orc
 
 # north-star tolerances (BASELINE.json)

@@ -3,7 +3,7 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import pygenray_b200 as pr
-from oracle import cases
+import workloads as cases
 import bench
 
 def run(denv, angles, R, n_save=0, reps=3):

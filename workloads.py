@@ -1,7 +1,8 @@
 """Synthetic environments / workloads named in BASELINE.json `configs`.
 
-Pure numpy; used by oracle/make_golden.py (to feed the reference), by tests/ and by bench.py so all
-three see bit-identical inputs.  TEST/BENCH INFRASTRUCTURE -- the product package does not import it.
+Pure numpy, no dependency on the product or on the oracle; used by oracle/make_golden.py (to feed the reference),
+by tests/ and by bench.py so all three see bit-identical inputs.  TEST/BENCH INFRASTRUCTURE -- the product package
+does not import it.
 """
 import numpy as np
 
