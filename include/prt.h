@@ -238,6 +238,31 @@ PRT_API int prt_refine_brackets(const prt_env_t *env, int64_t n_br, const double
                         int32_t *out_n_surface_dev, int32_t *out_status_dev, int32_t *out_shots_dev,
                         int32_t *out_ray_status_dev, void *work_dev, int32_t max_bounces, void *stream);
 
+/*
+ * Eigenray post-processing on the device (EigenRays.__init__, ray_objects.py:505-548).
+ *
+ * prt_received_angles: ray_angle (integration_processes.py:306-334) the way that constructor calls it -- on the
+ * STORED end state (z_dev = -depth, p_dev sign-flipped) at range x and on the UN-flattened sound speed
+ * environment.sound_speed (cin_dev [n_r][n_z], rin_dev, zin_dev: device copies made by the caller; this is not the
+ * staged environment, which may be flat-earth transformed or mirrored): literal bilinear_interp, degrees(arcsin(p c)).
+ *
+ * prt_eigen_table: one row of PRT_EIG_TABLE_WIDTH doubles per converged eigenray i = 0..n-1, bracket b = idx_dev[i]
+ * of a prt_refine_brackets result (rcv_dev from prt_fill_brackets; theta/final/n_bottom/n_surface its outputs):
+ *   [receiver index, arrival time T, z (stored, = -depth), p (stored), launch angle, received angle,
+ *    ray id number, n_bottom, n_surface, bracket index]
+ * ray id number = p_sign_changes_dev[i] * sign(launch angle) (ray_objects.py:533-535) with p_sign_changes_dev the
+ * out_p_sign_changes_dev of the re-shot of the n converged rays on the save grid, or NaN when it is NULL.
+ */
+#define PRT_EIG_TABLE_WIDTH 10
+PRT_API int prt_received_angles(int64_t n, double x, const double *z_dev, const double *p_dev, int32_t n_r,
+                                int32_t n_z, const double *rin_dev, const double *zin_dev, const double *cin_dev,
+                                double *out_theta_dev, void *stream);
+PRT_API int prt_eigen_table(int64_t n, int64_t n_br, const int64_t *idx_dev, const int32_t *rcv_dev,
+                            const double *theta_dev, const double *final_dev, const int32_t *n_bottom_dev,
+                            const int32_t *n_surface_dev, const int32_t *p_sign_changes_dev, double receiver_range,
+                            int32_t n_r, int32_t n_z, const double *rin_dev, const double *zin_dev,
+                            const double *cin_dev, double *out_table_dev, void *stream);
+
 /* number of kernels this library has launched in the calling process (monotonic; for bench.py) */
 PRT_API int64_t prt_launch_count(void);
 

@@ -9,7 +9,7 @@ Everything numerical runs in libprt.so (hand-written sm_100a CUDA, C ABI in incl
 There is no CPU fallback: without the built library and a CUDA device the compute calls raise.
 """
 from . import _lib, dist
-from .eigenrays import find_brackets, find_eigenrays, refine_brackets
+from .eigenrays import eigenray_table, find_brackets, find_eigenrays, refine_brackets
 from .environment import DataArray, OceanEnvironment2D, eflat, munk_ssp
 from .launch_rays import (DeviceEnsemble, DeviceEnvironment, _mirror_envi_arrays, _unpack_envi,
                           bottom_angle_ppoly, shoot_ensemble_arrays, shoot_fan_arrays, shoot_ray, shoot_rays)
@@ -17,7 +17,8 @@ from .ray_objects import EigenRays, Ray, RayFan
 
 __all__ = [
     "OceanEnvironment2D", "DataArray", "munk_ssp", "eflat", "shoot_rays", "shoot_ray", "find_eigenrays",
-    "Ray", "RayFan", "EigenRays", "shoot_fan_arrays", "shoot_ensemble_arrays", "find_brackets", "refine_brackets", "DeviceEnvironment",
+    "Ray", "RayFan", "EigenRays", "shoot_fan_arrays", "shoot_ensemble_arrays", "find_brackets", "refine_brackets", "eigenray_table",
+    "DeviceEnvironment",
     "DeviceEnsemble", "dist",
     "bottom_angle_ppoly", "_unpack_envi", "_mirror_envi_arrays",
 ]

@@ -18,6 +18,8 @@ RAY_STATUS = {
 EIG_CONVERGED, EIG_RAY_DROPPED, EIG_MAX_ITER = 0, 1, 2
 COUNTER_NAMES = ("nfev", "attempts", "accepted", "segments", "bisect", "dense")
 N_COUNTERS = 6
+EIG_TABLE_WIDTH = 10
+EIG_TABLE_FIELDS = ("rcv", "T", "z", "p", "launch_angle", "received_angle", "ray_id", "n_bottom", "n_surface", "bracket")
 DEFAULT_MAX_BOUNCES = 1 << 20
 
 EXPORTS = (
@@ -25,7 +27,7 @@ EXPORTS = (
     "prt_ensemble_create_dev",
     "prt_shoot_ensemble", "prt_env_destroy",
     "prt_env_device_bytes", "prt_shoot_fan", "prt_shoot_fan_host", "prt_pack_arrivals", "prt_bracket_workspace_bytes", "prt_count_brackets", "prt_fill_brackets",
-    "prt_refine_workspace_bytes", "prt_refine_brackets", "prt_launch_count", "prt_measure_fp64_peak",
+    "prt_refine_workspace_bytes", "prt_refine_brackets", "prt_received_angles", "prt_eigen_table", "prt_launch_count", "prt_measure_fp64_peak",
 )
 
 
@@ -85,6 +87,10 @@ def load():
     L.prt_refine_brackets.restype = C.c_int
     L.prt_refine_brackets.argtypes = [vp, i64, vp, vp, vp, vp, vp, d, d, d, d, d, i32, d, i32,
                                       vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
+    L.prt_received_angles.restype = C.c_int
+    L.prt_received_angles.argtypes = [i64, d, vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.prt_eigen_table.restype = C.c_int
+    L.prt_eigen_table.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp, d, i32, i32, vp, vp, vp, vp, vp]
     L.prt_launch_count.restype = i64
     L.prt_measure_fp64_peak.restype = d
     L.prt_measure_fp64_peak.argtypes = [C.c_int, i32]

@@ -148,10 +148,17 @@ PRT_HD double prt_next_up(double t)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Python builtin min/max and numpy.maximum NaN semantics (scipy rk.py:155-163, common.py:117-134)
+// Python builtin min/max (scipy rk.py:155-163, common.py:117-134)
 PRT_HD double prt_py_min(double a, double b) { return (b < a) ? b : a; }
 PRT_HD double prt_py_max(double a, double b) { return (b > a) ? b : a; }
-PRT_HD double prt_np_maximum(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+// np.maximum(np.abs(a), np.abs(b)) (rk.py:148-149, common.py:117) on the bit patterns: non-negative doubles order like
+// unsigned integers and every NaN pattern lies above infinity, so the integer maximum IS the NaN-propagating maximum
+// of the magnitudes -- integer instructions instead of three FP64 compares per component on the FP64 pipe
+PRT_HD double prt_max_abs(double a, double b)
+{
+    const uint64_t x = prt_double_to_bits(a) & 0x7fffffffffffffffULL, y = prt_double_to_bits(b) & 0x7fffffffffffffffULL;
+    return prt_bits_to_double(x > y ? x : y);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Elementary functions of the rounding contract
@@ -246,11 +253,12 @@ PRT_HD double prt_pow_m01(double x)
     return y * prt_from_hilo((uint32_t)(1126u - q10) << 20, 0u);  // 2^(-q)
 }
 
-// 1/sqrt(w), normal w > 0: integer-shift seed on the high word + 4 Newton steps (<= 2.3 ulp); see oracle orc_rsqrt
-PRT_HD double prt_rsqrt(double w)
+// 1/sqrt(w), normal w > 0: integer-shift seed on the high word + 4 Newton steps (<= 2.3 ulp); see oracle orc_rsqrt.
+// Takes hw = w / 2 (what the Newton step multiplies by): halving is exact and commutes with the rounding of the
+// product that formed w, so callers form hw directly and w itself is never needed; hi32(w) = hi32(hw) + 2^20.
+PRT_HD double prt_rsqrt_half(double hw)
 {
-    double y = prt_from_hilo(0x5FE6EB50u - (prt_hi32(w) >> 1), 0u);
-    const double hw = 0.5 * w;
+    double y = prt_from_hilo(0x5FE6EB50u - ((prt_hi32(hw) + 0x00100000u) >> 1), 0u);
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const double t = y * y;
@@ -424,11 +432,10 @@ PRT_HD unsigned prt_guess(double v, double inv, double off, int m)
     return g > (unsigned)m ? (unsigned)m : g;
 }
 
-// depth axis: optionally refined guess (see prt_env_view::z_cubic)
-PRT_HD unsigned prt_guess_z(const prt_envp& E, double z)
+// depth axis: optionally refined guess (see prt_env_view::z_cubic); s = the linear guess z * z_inv + z_off
+PRT_HD unsigned prt_guess_z_from(const prt_envp& E, double s)
 {
     const prt_env_view& V = E.v;
-    double s = PRT_FMA(z, V.z_inv, V.z_off);
     if (E.zc) {
         const double u = s * V.z_un;
         s = PRT_FMA(s, PRT_FMA(PRT_FMA(V.z_b3, u, V.z_b2), u, V.z_b1), s);
@@ -437,6 +444,8 @@ PRT_HD unsigned prt_guess_z(const prt_envp& E, double z)
     const unsigned m = (unsigned)(V.n_z - 2);
     return g > m ? m : g;
 }
+
+PRT_HD unsigned prt_guess_z(const prt_envp& E, double z) { return prt_guess_z_from(E, PRT_FMA(z, E.v.z_inv, E.v.z_off)); }
 
 // Exact lookup, one cache round trip in the common case: every load (cell records and the four corner
 // nodes) is issued from the guessed indices at once; the guesses are verified afterwards (two compares per
@@ -489,6 +498,12 @@ PRT_HD void prt_field(const prt_envp& E, double x, double z, double& c, double& 
 // non-uniform grids.  The stage code of an attempt is thus one branch-free block that the scheduler is free
 // to interleave across stages.
 #define PRT_W_HI (1.0 - 0x1p-40)
+// The proof on the high word only (one integer compare, off the FP64 pipe): 1 <= hi(w) <= 0x3FEFFFFE  =>  w is a
+// positive number below 1 - 2^-20 < PRT_W_HI.  Conservative on purpose: +0, and weights within 2^-20 of 1 (an
+// abscissa within a millionth of a cell below a node) are sent to the exact re-run, which returns the same bits.
+PRT_HD bool prt_w_proven(double w) { return (prt_hi32(w) - 1u) < 0x3FEFFFFEu; }
+// first depth cell: any finite w <= -0 is also accepted (above the surface the reference clamps the cell and extrapolates)
+PRT_HD bool prt_w_negative_finite(double w) { return (prt_hi32(w) - 0x80000000u) < 0x7FF00000u; }
 struct prt_xcell {
     unsigned row;  // i * n_z: element index of grid[i][0] (32-bit on purpose: one IMAD.WIDE per node address)
     double wx;
@@ -502,20 +517,21 @@ PRT_HD prt_xcell prt_xlook(const prt_envp& E, double x, bool& ok)
     prt_xcell xc;
     xc.row = i * (unsigned)V.n_z;
     xc.wx = (x - ra.x) * ra.y;
-    ok = ok & (xc.wx > 0.0) & (xc.wx < PRT_W_HI);
+    ok = ok & prt_w_proven(xc.wx);
     return xc;
 }
 
-PRT_HD void prt_field_spec(const prt_envp& E, const prt_xcell& xc, double z, double& c, double& cz, bool& ok)
+// sg: the real-valued linear cell guess of z (any value is a correct guess; see PRT_FOLD_GUESS in prt_rk_try)
+PRT_HD void prt_field_spec(const prt_envp& E, const prt_xcell& xc, double z, double sg, double& c, double& cz, bool& ok)
 {
     const prt_env_view& V = E.v;
-    const unsigned j = prt_guess_z(E, z);
+    const unsigned j = prt_guess_z_from(E, sg);
     const unsigned e0 = xc.row + j, e1 = e0 + (unsigned)V.n_z;
     const prt_d2 *g0 = E.grid + e0, *g1 = E.grid + e1;
     const prt_d2 za = prt_ld2(V.zxr + j);
     const prt_d2 v00 = prt_ld2(g0), v01 = prt_ld2(g0 + 1), v10 = prt_ld2(g1), v11 = prt_ld2(g1 + 1);
     const double wy = (z - za.x) * za.y;
-    ok = ok & ((wy > 0.0) | (j == 0u)) & (wy < PRT_W_HI);  // waiver: above the surface (overshoot before a reflection)
+    ok = ok & (prt_w_proven(wy) | ((j == 0u) & prt_w_negative_finite(wy)));  // waiver: above the surface (overshoot before a reflection)
     prt_bilerp(v00, v01, v10, v11, xc.wx, wy, c, cz);
 }
 
@@ -546,21 +562,38 @@ PRT_HD double prt_bathy_spec(const prt_envp& E, double x, bool& ok)
     const prt_d2* bc = V.bcell + 3 * g;
     const prt_d2 a = prt_ld2(bc + 1), v = prt_ld2(bc + 2);
     const double w = (x - a.x) * a.y;
-    ok = ok & (w > 0.0) & (w < PRT_W_HI);
+    ok = ok & prt_w_proven(w);
     return PRT_FMA(w, v.y, (1.0 - w) * v.x);
 }
 
 // derivsrd (integration_processes.py:26-98) from c and dc/dz, with a single reciprocal square root:
 //   u = 1 / (c^2 sqrt(arg)) = rsqrt(c^4 arg);  [dT, dz, dp] = [c u, (c^3 p) u, -cz u]
+// (the Newton iteration works on c^4 arg / 2, formed as (c^2 (c^2 / 2)) arg: same bits as halving c^4 arg)
 // (every output is ONE multiplication after u; c^3 p is formed while the Newton iteration runs)
 PRT_HD void prt_rhs_tail(double c, double cz, double p, double& dT, double& dz, double& dp)
 {
     const double c2 = c * c;
     const double arg = PRT_FMA(-c2, p * p, 1.0);
-    const double c4 = c2 * c2;
-    const double w = (arg <= 0.0) ? c4 * 1e-30 : c4 * arg;  // "if arg <= 0: arg = 1e-30"
+    const double c4h = c2 * (0.5 * c2);  // c^4 / 2, exactly half of c2 * c2
+    const double hw = (arg <= 0.0) ? c4h * 1e-30 : c4h * arg;  // "if arg <= 0: arg = 1e-30"
     const double c3p = (c2 * c) * p;
-    const double u = prt_rsqrt(w);
+    const double u = prt_rsqrt_half(hw);
+    dT = c * u;
+    dz = c3p * u;
+    dp = (-cz) * u;
+}
+
+// the same for the speculative trial step: "if arg <= 0: arg = 1e-30" (a ray beyond vertical) is not selected on the
+// dependent chain but proven absent on the high word of arg (0 < arg <= 1 here), else the attempt is re-run exactly
+PRT_HD void prt_rhs_tail_spec(double c, double cz, double p, double& dT, double& dz, double& dp, bool& ok)
+{
+    const double c2 = c * c;
+    const double arg = PRT_FMA(-c2, p * p, 1.0);
+    const double c4h = c2 * (0.5 * c2);
+    ok = ok & ((prt_hi32(arg) - 1u) < 0x7FEFFFFFu);  // positive and finite
+    const double hw = c4h * arg;
+    const double c3p = (c2 * c) * p;
+    const double u = prt_rsqrt_half(hw);
     dT = c * u;
     dz = c3p * u;
     dp = (-cz) * u;
@@ -575,12 +608,12 @@ PRT_HD void prt_rhs(const prt_envp& E, double x, double z, double p, double& dT,
     c_out = c;
 }
 
-PRT_HD void prt_rhs_spec(const prt_envp& E, const prt_xcell& xc, double z, double p, double& dT, double& dz,
+PRT_HD void prt_rhs_spec(const prt_envp& E, const prt_xcell& xc, double z, double p, double sg, double& dT, double& dz,
                          double& dp, double& c_out, bool& ok)
 {
     double c, cz;
-    prt_field_spec(E, xc, z, c, cz, ok);
-    prt_rhs_tail(c, cz, p, dT, dz, dp);
+    prt_field_spec(E, xc, z, sg, c, cz, ok);
+    prt_rhs_tail_spec(c, cz, p, dT, dz, dp, ok);
     c_out = c;
 }
 
@@ -881,32 +914,49 @@ PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, do
                        double p, double f0, double f1, double f2, prt_try& v, bool& ok)
 {
     double kT, kz, kp, cc;
-#define PRT_STAGE(xs, zs, ps, cout)                                              \
+    // Depth-cell guess of a stage, real-valued: z_stage * z_inv + z_off.  With PRT_FOLD_GUESS it is formed as ONE fma
+    // after the last stage value the stage input waits for -- (hh z_inv A_last) k_last + [z z_inv + z_off + hh z_inv
+    // (rest of the stage sum)], the bracket being ready long before -- instead of three dependent operations (stage
+    // sum, stage input, guess): the guess differs from the literal one by rounding only, and any guess is a correct
+    // guess (the weight proves it), so results do not change; the FP64 chain of every stage gets 2 operations shorter.
+#ifndef PRT_FOLD_GUESS
+#define PRT_FOLD_GUESS 1
+#endif
+    const double hz = hh * E.v.z_inv, zz = PRT_FMA(z, E.v.z_inv, E.v.z_off);
+#define PRT_GUESS(zs, a_last, k_last, a_part) \
+    ((PRT_FOLD_GUESS && !EXACT) ? PRT_FMA(hz * (a_last), (k_last), PRT_FMA(hz, (a_part), zz)) : PRT_FMA((zs), E.v.z_inv, E.v.z_off))
+#define PRT_STAGE(xs, zs, ps, sg, cout)                                          \
     do {                                                                         \
         if (EXACT) {                                                             \
             prt_rhs(E, (xs), (zs), (ps), kT, kz, kp, cout);                      \
         } else {                                                                 \
             const prt_xcell xc_ = prt_xlook(E, (xs), ok);                        \
-            prt_rhs_spec(E, xc_, (zs), (ps), kT, kz, kp, cout, ok);              \
+            prt_rhs_spec(E, xc_, (zs), (ps), (sg), kT, kz, kp, cout, ok);        \
         }                                                                        \
     } while (0)
     // stage 2 (its travel-time component enters no sum: B2 = E2 = P2 = 0)
-    double k2z, k2p, k3T, k3z, k3p, k4T, k4z, k4p, a, b;
-    PRT_STAGE(PRT_FMA(C2, hh, t), PRT_FMA(hh, A21 * f1, z), PRT_FMA(hh, A21 * f2, p), cc);
+    double k2z, k2p, k3T, k3z, k3p, k4T, k4z, k4p, a, b, ap, zs_;
+    zs_ = PRT_FMA(hh, A21 * f1, z);
+    PRT_STAGE(PRT_FMA(C2, hh, t), zs_, PRT_FMA(hh, A21 * f2, p), PRT_FMA(zs_, E.v.z_inv, E.v.z_off), cc);
     k2z = kz; k2p = kp;
-    a = A31 * f1; a = PRT_FMA(A32, k2z, a);
+    ap = A31 * f1; a = PRT_FMA(A32, k2z, ap);
     b = A31 * f2; b = PRT_FMA(A32, k2p, b);
-    PRT_STAGE(PRT_FMA(C3, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), cc);
+    zs_ = PRT_FMA(hh, a, z);
+    PRT_STAGE(PRT_FMA(C3, hh, t), zs_, PRT_FMA(hh, b, p), PRT_GUESS(zs_, A32, k2z, ap), cc);
     k3T = kT; k3z = kz; k3p = kp;
-    a = A41 * f1; a = PRT_FMA(A42, k2z, a); a = PRT_FMA(A43, k3z, a);
+    ap = A41 * f1; ap = PRT_FMA(A42, k2z, ap); a = PRT_FMA(A43, k3z, ap);
     b = A41 * f2; b = PRT_FMA(A42, k2p, b); b = PRT_FMA(A43, k3p, b);
-    PRT_STAGE(PRT_FMA(C4, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), cc);
+    zs_ = PRT_FMA(hh, a, z);
+    PRT_STAGE(PRT_FMA(C4, hh, t), zs_, PRT_FMA(hh, b, p), PRT_GUESS(zs_, A43, k3z, ap), cc);
     k4T = kT; k4z = kz; k4p = kp;
-    a = A51 * f1; a = PRT_FMA(A52, k2z, a); a = PRT_FMA(A53, k3z, a); a = PRT_FMA(A54, k4z, a);
+    ap = A51 * f1; ap = PRT_FMA(A52, k2z, ap); ap = PRT_FMA(A53, k3z, ap); a = PRT_FMA(A54, k4z, ap);
     b = A51 * f2; b = PRT_FMA(A52, k2p, b); b = PRT_FMA(A53, k3p, b); b = PRT_FMA(A54, k4p, b);
-    PRT_STAGE(PRT_FMA(C5, hh, t), PRT_FMA(hh, a, z), PRT_FMA(hh, b, p), cc);
+    zs_ = PRT_FMA(hh, a, z);
+    PRT_STAGE(PRT_FMA(C5, hh, t), zs_, PRT_FMA(hh, b, p), PRT_GUESS(zs_, A54, k4z, ap), cc);
     // from here on the sums are carried, not the stage values
-    double a6z = A61 * f1; a6z = PRT_FMA(A62, k2z, a6z); a6z = PRT_FMA(A63, k3z, a6z); a6z = PRT_FMA(A64, k4z, a6z); a6z = PRT_FMA(A65, kz, a6z);
+    double a6z = A61 * f1; a6z = PRT_FMA(A62, k2z, a6z); a6z = PRT_FMA(A63, k3z, a6z); a6z = PRT_FMA(A64, k4z, a6z);
+    const double sg6 = PRT_GUESS(PRT_FMA(hh, PRT_FMA(A65, kz, a6z), z), A65, kz, a6z);
+    a6z = PRT_FMA(A65, kz, a6z);
     double a6p = A61 * f2; a6p = PRT_FMA(A62, k2p, a6p); a6p = PRT_FMA(A63, k3p, a6p); a6p = PRT_FMA(A64, k4p, a6p); a6p = PRT_FMA(A65, kp, a6p);
     double sT = B1 * f0; sT = PRT_FMA(B3, k3T, sT); sT = PRT_FMA(B4, k4T, sT); sT = PRT_FMA(B5, kT, sT);
     double sz = B1 * f1; sz = PRT_FMA(B3, k3z, sz); sz = PRT_FMA(B4, k4z, sz); sz = PRT_FMA(B5, kz, sz);
@@ -930,7 +980,8 @@ PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, do
     prt_xcell xc6;
     if (!EXACT) xc6 = prt_xlook(E, x6, ok);
     if (EXACT) prt_rhs(E, x6, PRT_FMA(hh, a6z, z), PRT_FMA(hh, a6p, p), kT, kz, kp, cc);
-    else prt_rhs_spec(E, xc6, PRT_FMA(hh, a6z, z), PRT_FMA(hh, a6p, p), kT, kz, kp, cc, ok);
+    else prt_rhs_spec(E, xc6, PRT_FMA(hh, a6z, z), PRT_FMA(hh, a6p, p), sg6, kT, kz, kp, cc, ok);
+    const double sg7 = PRT_GUESS(PRT_FMA(hh, PRT_FMA(B6, kz, sz), z), B6, kz, sz);
     sT = PRT_FMA(B6, kT, sT); sz = PRT_FMA(B6, kz, sz); sp = PRT_FMA(B6, kp, sp);
     eT = PRT_FMA(E6, kT, eT); ez = PRT_FMA(E6, kz, ez); ep = PRT_FMA(E6, kp, ep);
     if (DENSE) {
@@ -941,15 +992,16 @@ PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, do
     v.nT = PRT_FMA(hh, sT, T); v.nz = PRT_FMA(hh, sz, z); v.np_ = PRT_FMA(hh, sp, p);
     // error scales and their reciprocals (rk.py:148-152): known before the last stage, so the three
     // divisions of the reference become one reciprocal (of the product) formed in the shadow of that stage
-    const double scT = PRT_FMA(prt_np_maximum(fabs(T), fabs(v.nT)), rtol, atol);
-    const double scz = PRT_FMA(prt_np_maximum(fabs(z), fabs(v.nz)), rtol, atol);
-    const double scp = PRT_FMA(prt_np_maximum(fabs(p), fabs(v.np_)), rtol, atol);
+    const double scT = PRT_FMA(prt_max_abs(T, v.nT), rtol, atol);
+    const double scz = PRT_FMA(prt_max_abs(z, v.nz), rtol, atol);
+    const double scp = PRT_FMA(prt_max_abs(p, v.np_), rtol, atol);
     const double sTz = scT * scz, szp = scz * scp, sTp = scT * scp;
     const double inv3 = prt_rcp(sTz * scp);
     const double iT = inv3 * szp, iz = inv3 * sTp, ip = inv3 * sTz;
     if (EXACT) prt_rhs(E, x6, v.nz, v.np_, v.k7T, v.k7z, v.k7p, v.c_new);  // f_new (FSAL)
-    else prt_rhs_spec(E, xc6, v.nz, v.np_, v.k7T, v.k7z, v.k7p, v.c_new, ok);
+    else prt_rhs_spec(E, xc6, v.nz, v.np_, sg7, v.k7T, v.k7z, v.k7p, v.c_new, ok);
 #undef PRT_STAGE
+#undef PRT_GUESS
     // the event functions at the step end (ivp.py:678-699) only need y_new and c_new: formed here, they overlap
     // the tail of the last stage and the controller instead of following the accept decision
     {

@@ -38,6 +38,25 @@ static int fail(int code, const std::string& msg)
             return fail(PRT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
     } while (0)
 
+// entry points run on the environment's device and leave the caller's current device as they found it
+struct prt_device_guard {
+    int prev = -1;
+    cudaError_t err;
+    explicit prt_device_guard(int device)
+    {
+        cudaGetDevice(&prev);
+        err = (prev == device) ? cudaSuccess : cudaSetDevice(device);
+    }
+    ~prt_device_guard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define PRT_ON_DEVICE(dev)                                                                          \
+    prt_device_guard guard__(dev);                                                                  \
+    if (guard__.err != cudaSuccess)                                                                 \
+        return fail(PRT_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(guard__.err))
+
 struct prt_env {
     int device;
     void* dev_blob;
@@ -170,7 +189,7 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SA
 #define PRT_MIN_BLOCKS 4
 #endif
 #ifndef PRT_MIN_BLOCKS_ARR
-#define PRT_MIN_BLOCKS_ARR 5
+#define PRT_MIN_BLOCKS_ARR 4
 #endif
 #ifndef PRT_BLOCK
 #define PRT_BLOCK 128  // threads per block, trajectory-saving kernels
@@ -688,6 +707,77 @@ __global__ void prt_pack_arrivals_kernel(int64_t n, const double* __restrict__ f
 }
 
 // ---------------------------------------------------------------------------------------------
+// Eigenray post-processing: the per-receiver arrival ("time front") table of the converged eigenrays, built on the
+// device from the refinement output -- EigenRays.__init__ of the reference loops over rays on the host
+// (ray_objects.py:505-548).  The received angle is ray_angle (integration_processes.py:306-334) exactly as that
+// constructor calls it: on the STORED end state (z = -depth, p sign-flipped) and on the UN-flattened sound speed
+// `environment.sound_speed`, i.e. literal bilinear_interp (:152-174: cell = searchsorted - 1 clamped
+// to [0, n - 2], unclamped weights, four-term sum), theta = degrees(arcsin(p c)).
+__device__ __forceinline__ int prt_searchsorted_cell(const double* __restrict__ a, int n, double v)
+{
+    int lo = 0, hi = n;  // np.searchsorted(a, v, side="left"); NaN sorts last
+    if (v != v) lo = n;
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (a[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    int k = lo - 1;
+    k = k < 0 ? 0 : k;
+    return k > n - 2 ? n - 2 : k;
+}
+
+__device__ __forceinline__ double prt_received_angle(const double* __restrict__ rin, const double* __restrict__ zin,
+                                                     const double* __restrict__ cin, int n_r, int n_z, double x,
+                                                     double z, double p)
+{
+    const int i = prt_searchsorted_cell(rin, n_r, x), j = prt_searchsorted_cell(zin, n_z, z);
+    const double wx = (x - rin[i]) / (rin[i + 1] - rin[i]);
+    const double wy = (z - zin[j]) / (zin[j + 1] - zin[j]);
+    const double* c0 = cin + (size_t)i * n_z + j;
+    const double* c1 = c0 + n_z;
+    const double c = (1.0 - wx) * (1.0 - wy) * c0[0] + wx * (1.0 - wy) * c1[0] + (1.0 - wx) * wy * c0[1] + wx * wy * c1[1];
+    return prt_asin(p * c) * PRT_RAD2DEG;
+}
+
+__global__ void prt_received_angles_kernel(int64_t n, double x, const double* __restrict__ z, const double* __restrict__ p,
+                                           int32_t n_r, int32_t n_z, const double* __restrict__ rin,
+                                           const double* __restrict__ zin, const double* __restrict__ cin,
+                                           double* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = prt_received_angle(rin, zin, cin, n_r, n_z, x, z[i], p[i]);
+}
+
+// one row per converged eigenray: PRT_EIG_TABLE_WIDTH doubles (include/prt.h)
+__global__ void prt_eigen_table_kernel(int64_t n, int64_t n_br, const int64_t* __restrict__ idx,
+                                       const int32_t* __restrict__ rcv, const double* __restrict__ theta,
+                                       const double* __restrict__ fin, const int32_t* __restrict__ nb,
+                                       const int32_t* __restrict__ ns, const int32_t* __restrict__ flips, double x,
+                                       int32_t n_r, int32_t n_z, const double* __restrict__ rin,
+                                       const double* __restrict__ zin, const double* __restrict__ cin,
+                                       double* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t b = idx[i];
+    const double th = theta[b];
+    const double zs = -fin[n_br + b], ps = -fin[2 * n_br + b];  // stored convention (ray_objects.py:49-52)
+    double* o = out + PRT_EIG_TABLE_WIDTH * i;
+    o[0] = (double)rcv[b];
+    o[1] = fin[b];
+    o[2] = zs;
+    o[3] = ps;
+    o[4] = th;
+    o[5] = prt_received_angle(rin, zin, cin, n_r, n_z, x, zs, ps);
+    // ray id number = (# sign changes of p on the save grid) * sign(launch angle)  (ray_objects.py:533-535)
+    o[6] = flips ? (double)flips[i] * prt_sign(th) : (double)NAN;
+    o[7] = (double)nb[b];
+    o[8] = (double)ns[b];
+    o[9] = (double)b;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Device-side staging of sound-speed grids that already live in HBM (perturbed realisations of a tomography
 // ensemble generated on the GPU): grid[k] = {c, dc/dz} with dc/dz = np.gradient(c, z, axis=depth, edge_order=1),
 // the derivative _unpack_envi takes (launch_rays.py:728-733); same operations in numpy's order, hence its bits.
@@ -780,7 +870,7 @@ int prt_env_create(int device, int32_t n_r, int32_t n_z, const double* rin, cons
     prt_env_blob blob;
     if (prt_env_pack(n_r, n_z, rin, zin, cin, cpin, n_b, depth_ranges, depths, n_ba, ba_x, ba_c, blob))
         return fail(PRT_ERR_ARG, "prt_env_create: every grid needs at least 2 points");
-    PRT_CUDA(cudaSetDevice(device));
+    PRT_ON_DEVICE(device);
     void* dev = nullptr;
     PRT_CUDA(cudaMalloc(&dev, blob.bytes.size()));
     cudaError_t e = cudaMemcpy(dev, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice);
@@ -808,7 +898,7 @@ int prt_ensemble_create(int device, int32_t n_env, int32_t n_r, int32_t n_z, con
     prt_env_blob blob;
     if (prt_env_pack(n_r, n_z, rin, zin, cin, cpin, n_b, depth_ranges, depths, n_ba, ba_x, ba_c, blob, n_env))
         return fail(PRT_ERR_ARG, "prt_ensemble_create: n_env >= 1 and every grid needs at least 2 points");
-    PRT_CUDA(cudaSetDevice(device));
+    PRT_ON_DEVICE(device);
     void* dev = nullptr;
     PRT_CUDA(cudaMalloc(&dev, blob.bytes.size()));
     cudaError_t e = cudaMemcpy(dev, blob.bytes.data(), blob.bytes.size(), cudaMemcpyHostToDevice);
@@ -836,7 +926,7 @@ int prt_ensemble_create_dev(int device, int32_t n_env, int32_t n_r, int32_t n_z,
     prt_env_blob blob;
     if (prt_env_pack(n_r, n_z, rin, zin, nullptr, nullptr, n_b, depth_ranges, depths, n_ba, ba_x, ba_c, blob, n_env))
         return fail(PRT_ERR_ARG, "prt_ensemble_create_dev: n_env >= 1 and every grid needs at least 2 points");
-    PRT_CUDA(cudaSetDevice(device));
+    PRT_ON_DEVICE(device);
     const prt_gradient_tables g = prt_gradient_coefficients(zin, n_z);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     unsigned char* dev = nullptr;
@@ -874,7 +964,7 @@ int prt_ensemble_create_dev(int device, int32_t n_env, int32_t n_r, int32_t n_z,
 int prt_env_destroy(prt_env_t* env)
 {
     if (!env) return PRT_SUCCESS;
-    cudaSetDevice(env->device);
+    prt_device_guard guard(env->device);
     cudaFree(env->dev_blob);
     delete env;
     return PRT_SUCCESS;
@@ -901,11 +991,11 @@ static int shoot_fan_impl(const prt_env_t* env, int64_t n_rays, int64_t rays_per
     if (!out_final_dev || !out_n_bottom_dev || !out_n_surface_dev || !out_status_dev)
         return fail(PRT_ERR_ARG, "prt_shoot_fan: null output pointer");
     const bool save = (n_save > 0);
-    if (save && (n_save < 2 || !range_save_dev || !out_traj_dev))
-        return fail(PRT_ERR_ARG, "prt_shoot_fan: n_save >= 2, range_save_dev and out_traj_dev required to save");
+    if (save && (!range_save_dev || !out_traj_dev))
+        return fail(PRT_ERR_ARG, "prt_shoot_fan: range_save_dev and out_traj_dev required to save");
     if (!(source_range < receiver_range))
         return fail(PRT_ERR_ARG, "prt_shoot_fan: source_range must be < receiver_range (mirror backwards shots)");
-    PRT_CUDA(cudaSetDevice(env->device));
+    PRT_ON_DEVICE(env->device);
     prt_fan_params P;
     P.n_rays = n_rays; P.angles = angles_dev; P.y0 = y0_dev;
     P.source_depth = source_depth; P.source_range = source_range; P.receiver_range = receiver_range;
@@ -993,7 +1083,7 @@ int prt_shoot_fan_host(const prt_env_t* env, int64_t n_rays, const double* angle
 {
     if (!env) return fail(PRT_ERR_ARG, "prt_shoot_fan_host: null environment");
     if (n_rays <= 0) return n_rays == 0 ? PRT_SUCCESS : fail(PRT_ERR_ARG, "prt_shoot_fan_host: n_rays < 0");
-    PRT_CUDA(cudaSetDevice(env->device));
+    PRT_ON_DEVICE(env->device);
     const bool save = n_save > 0 && out_traj && range_save;
     const size_t n = (size_t)n_rays;
     // one scratch allocation: inputs | outputs
@@ -1104,6 +1194,40 @@ int prt_pack_arrivals(int64_t n_rays, const double* final_dev, const int32_t* n_
     return PRT_SUCCESS;
 }
 
+int prt_received_angles(int64_t n, double x, const double* z_dev, const double* p_dev, int32_t n_r, int32_t n_z,
+                        const double* rin_dev, const double* zin_dev, const double* cin_dev, double* out_theta_dev,
+                        void* stream)
+{
+    if (n <= 0) return n == 0 ? PRT_SUCCESS : fail(PRT_ERR_ARG, "prt_received_angles: n < 0");
+    if (!z_dev || !p_dev || !rin_dev || !zin_dev || !cin_dev || !out_theta_dev)
+        return fail(PRT_ERR_ARG, "prt_received_angles: null pointer");
+    if (n_r < 2 || n_z < 2) return fail(PRT_ERR_ARG, "prt_received_angles: the sound-speed grid needs 2 x 2 nodes");
+    prt_received_angles_kernel<<<(unsigned)((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        n, x, z_dev, p_dev, n_r, n_z, rin_dev, zin_dev, cin_dev, out_theta_dev);
+    g_launches.fetch_add(1);
+    PRT_CUDA(cudaGetLastError());
+    return PRT_SUCCESS;
+}
+
+int prt_eigen_table(int64_t n, int64_t n_br, const int64_t* idx_dev, const int32_t* rcv_dev, const double* theta_dev,
+                    const double* final_dev, const int32_t* n_bottom_dev, const int32_t* n_surface_dev,
+                    const int32_t* p_sign_changes_dev, double receiver_range, int32_t n_r, int32_t n_z,
+                    const double* rin_dev, const double* zin_dev, const double* cin_dev, double* out_table_dev,
+                    void* stream)
+{
+    if (n <= 0) return n == 0 ? PRT_SUCCESS : fail(PRT_ERR_ARG, "prt_eigen_table: n < 0");
+    if (!idx_dev || !rcv_dev || !theta_dev || !final_dev || !n_bottom_dev || !n_surface_dev || !rin_dev || !zin_dev ||
+        !cin_dev || !out_table_dev)
+        return fail(PRT_ERR_ARG, "prt_eigen_table: null pointer");
+    if (n_r < 2 || n_z < 2) return fail(PRT_ERR_ARG, "prt_eigen_table: the sound-speed grid needs 2 x 2 nodes");
+    prt_eigen_table_kernel<<<(unsigned)((n + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        n, n_br, idx_dev, rcv_dev, theta_dev, final_dev, n_bottom_dev, n_surface_dev, p_sign_changes_dev, receiver_range,
+        n_r, n_z, rin_dev, zin_dev, cin_dev, out_table_dev);
+    g_launches.fetch_add(1);
+    PRT_CUDA(cudaGetLastError());
+    return PRT_SUCCESS;
+}
+
 int64_t prt_refine_workspace_bytes(int64_t n_br)
 {
     if (n_br < 0) return 0;
@@ -1128,7 +1252,7 @@ int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev
     if (!(source_range < receiver_range))
         return fail(PRT_ERR_ARG, "prt_refine_brackets: source_range must be < receiver_range");
     if (max_iter < 0) return fail(PRT_ERR_ARG, "prt_refine_brackets: max_iter < 0");
-    PRT_CUDA(cudaSetDevice(env->device));
+    PRT_ON_DEVICE(env->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t n = (size_t)n_br;
     unsigned char* w = static_cast<unsigned char*>(work_dev);
@@ -1187,7 +1311,8 @@ int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev
 double prt_measure_fp64_peak(int device, int32_t iters)
 {
     if (prt_device_count() <= device || device < 0) return -1.0;
-    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    prt_device_guard guard(device);
+    if (guard.err != cudaSuccess) return -1.0;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     double* out = nullptr;

@@ -10,7 +10,7 @@ memory (:133-198) have no equivalent here.  There is no CPU path: without libprt
 device every call raises.
 """
 import ctypes as C
-import zlib
+import hashlib
 
 import numpy as np
 from scipy.interpolate import CubicSpline
@@ -266,19 +266,22 @@ def shoot_ensemble_arrays(dens, source_depth, source_range, receiver_range, angl
 
 
 def _fingerprint(*arrays):
-    crc = 0
+    """128-bit content digest of the environment arrays (shape-aware): the key of the device-side cache."""
+    h = hashlib.blake2b(digest_size=16)
     for a in arrays:
         a = np.ascontiguousarray(a)
-        crc = zlib.crc32(a.view(np.uint8).reshape(-1), crc)
-        crc = zlib.crc32(repr(a.shape).encode(), crc)
-    return crc
+        h.update(repr((a.shape, a.dtype.str)).encode())
+        h.update(a.view(np.uint8).reshape(-1))
+    return h.digest()
 
 
 def _device_environment(environment, flatearth, backwards, device=None):
     """Unpack (+ mirror) the environment and stage it once per (content, orientation, device).
 
-    The cache key is a checksum of the arrays the environment holds (so in-place edits are seen); the depth
-    derivative (``np.gradient``, the expensive part of ``_unpack_envi``) is only formed on a miss."""
+    The cache key is a 128-bit digest of the arrays the environment holds (so in-place edits are seen; about 1 ms per
+    MB of grid per call); the depth derivative (``np.gradient``, the expensive part of ``_unpack_envi``) is only
+    formed on a miss.  Hot loops over one environment should stage it once (:class:`DeviceEnvironment`) and call
+    :func:`shoot_fan_arrays`."""
     import torch  # noqa: PLC0415
 
     if flatearth and not hasattr(environment, "sound_speed_fe"):
@@ -302,7 +305,7 @@ def _device_environment(environment, flatearth, backwards, device=None):
             )
         denv = DeviceEnvironment(cin, cpin, rin, zin, depths, depth_ranges, bottom_angles, device=device)
         if len(cache) >= 4:
-            cache.pop(next(iter(cache))).close()
+            cache.pop(next(iter(cache)))  # freed by DeviceEnvironment.__del__ once no launch holds it any more
         cache[key] = denv
     return denv
 
@@ -333,12 +336,16 @@ def shoot_fan_arrays(denv, source_depth, source_range, receiver_range, angles=No
         if y0s is not None:
             y0_h = torch.from_numpy(_as_f64(y0s).reshape(-1, 3))
             n = y0_h.shape[0]
-            y0_d = y0_h.pin_memory().to(dev, non_blocking=True) if n else y0_h.to(dev)
+            y0_d = y0_h.to(dev)
             ang_d = None
+        elif isinstance(angles, torch.Tensor):  # launch angles that already live on the device
+            ang_d = angles.to(device=dev, dtype=torch.float64).reshape(-1).contiguous()
+            n = ang_d.shape[0]
+            y0_d = None
         else:
             ang_h = torch.from_numpy(_as_f64(np.atleast_1d(angles)).reshape(-1))
             n = ang_h.shape[0]
-            ang_d = ang_h.pin_memory().to(dev, non_blocking=True) if n else ang_h.to(dev)
+            ang_d = ang_h.to(dev)
             y0_d = None
         n_save = int(num_range_save) if num_range_save else 0
         out = {}
@@ -511,6 +518,7 @@ _RAISING = {
     5: (ValueError, "A value in x_new is outside the interpolation range of the bottom-angle spline."),
     6: (ValueError, "f(a) and f(b) must have different signs"),
     7: (RuntimeError, "Failed to converge after 100 iterations."),
+    9: (RuntimeError, "ray exceeded the max_bounces safety cap (no reference equivalent: the reference would loop on)"),
 }
 
 
@@ -533,7 +541,9 @@ def _fan_from_device(res, stored_thetas, source_depth, backwards):
     m = traj.shape[1]
     fan = RayFan.__new__(RayFan)
     fan.thetas = np.asarray(stored_thetas, dtype=np.float64)[kept]
-    fan.rs = np.broadcast_to(rs, (m, rs.shape[0]))  # every ray shares the save grid (read-only view)
+    # every ray shares the save grid: a read-only broadcast view (the reference materialises M writable copies;
+    # use np.array(fan.rs) to edit)
+    fan.rs = np.broadcast_to(rs, (m, rs.shape[0]))
     fan.ts, fan.zs, fan.ps = traj[0], traj[1], traj[2]
     fan.n_botts = res["n_bottom"].astype(np.int64)
     fan.n_surfs = res["n_surface"].astype(np.int64)

@@ -5,18 +5,12 @@ Output contract of the reference (/root/reference/src/pygenray/ray_objects.py:7-
 ``p = -y[2]``), ray-id strings and the indexing/concatenation quirks are
 kept so downstream code written against pygenray keeps working.  Containers are host-side numpy;
 they are filled from device arrival tables / trajectories by :mod:`pygenray_b200.launch_rays`.
-Plot methods import matplotlib lazily (not installed in this image; cosmetic, out of scope).
+The reference's plot methods are out of scope and not provided.
 """
 import numpy as np
 from scipy import io
 
 __all__ = ["Ray", "RayFan", "EigenRays"]
-
-
-def _plt():
-    from matplotlib import pyplot as plt  # noqa: PLC0415 - optional dependency
-
-    return plt
 
 
 class Ray:
@@ -33,13 +27,6 @@ class Ray:
             self.launch_angle = launch_angle
         if source_depth is not None:
             self.source_depth = source_depth
-
-    def plot(self, **kwargs):
-        plt = _plt()
-        plt.plot(self.r, self.z, **kwargs)
-        plt.xlabel("time [s]")
-        plt.ylabel("depth [m]")
-        plt.ylim([self.z.min(), self.z.max()])
 
 
 def _ray_id_numbers(ps, thetas):
@@ -80,8 +67,7 @@ class RayFan:
         numbers = getattr(self, "_ray_id_numbers", None)  # counted on the device when the fan came from there
         if numbers is None:
             numbers = _ray_id_numbers(self.ps, self.thetas)
-        free = (self.n_botts == 0) & (self.n_surfs == 0)
-        self.ray_ids = np.array([str(n) if f else f"{n}b" for n, f in zip(numbers, free)])
+        self.ray_ids = _ray_id_strings(numbers, (self.n_botts == 0) & (self.n_surfs == 0))
 
     @property
     def ray_ids(self):
@@ -169,72 +155,72 @@ class RayFan:
             },
         )
 
-    # ---- plots (optional matplotlib) ------------------------------------------------------
-    def plot_time_front(self, include_lines=False, range_idx=-1, add_colorbar=True, ray_id=False, **kwargs):
-        plt = _plt()
-        if include_lines:
-            plt.plot(self.ts[:, range_idx], self.zs[:, range_idx], c="#aaaaaa", lw=0.5, zorder=5)
-        style = {"c": self.thetas, "cmap": "managua", "s": 2, "lw": 0, "zorder": 6}
-        style.update(kwargs)
-        if ray_id:
-            cats = np.unique(self.ray_ids)
-            colors = plt.cm.tab20(np.linspace(0, 1, len(cats)))
-            lut = dict(zip(cats, colors))
-            style["c"] = [lut[c] for c in self.ray_ids]
-            add_colorbar = False
-            for i, cat in enumerate(cats):
-                plt.scatter([], [], c=[colors[i]], label=cat)
-            plt.legend(ncols=3, loc="lower left")
-        plt.scatter(x=self.ts[:, range_idx], y=self.zs[:, range_idx], **style)
-        plt.ylim([self.zs.min(), self.zs.max()])
-        if add_colorbar:
-            plt.colorbar(label="launch angle [degrees]")
-            plt.xlabel("time [s]")
-            plt.ylabel("depth [m]")
-            plt.title("Time Front")
 
-    def plot_ray_fan(self, **kwargs):
-        plt = _plt()
-        alpha = min(1.0, 10.0 / max(len(self.thetas), 1))
-        style = {"c": "k", "lw": 1, "alpha": alpha}
-        style.update(kwargs)
-        plt.plot(self.rs.T, self.zs.T, **style)
-        plt.xlabel("range [m]")
-        plt.ylabel("depth [m]")
-        plt.ylim([self.zs.min(), self.zs.max()])
-        plt.title("Ray Fan")
-
-    def plot_depth_v_angle(self, include_line=False, **kwargs):
-        plt = _plt()
-        if include_line:
-            plt.plot(self.thetas, self.zs[:, -1], c="#aaaaaa", lw=0.5, zorder=5)
-        plt.scatter(x=self.thetas, y=self.zs[:, -1], **kwargs)
+def _ray_id_strings(numbers, free):
+    """'-3.0', '4.0b', ...: the number, then 'b' when the ray touched a boundary (ray_objects.py:145-155, 536-541)."""
+    numbers = np.ascontiguousarray(numbers, dtype=np.float64)
+    if numbers.shape[0] == 0:
+        return np.array([], dtype=str)
+    # few distinct values: format each once (by bit pattern, so that 0.0 and -0.0 keep their own spelling)
+    bits, inverse = np.unique(numbers.view(np.int64), return_inverse=True)
+    text = np.array([str(v) for v in bits.view(np.float64)])
+    return np.char.add(text[inverse], np.where(free, "", "b"))
 
 
-def _ray_angle_host(x, y, cin, rin, zin):
-    """Host evaluation of ray_angle (integration_processes.py:306-334) for EigenRays.received_angles.
+def _received_angles_device(x, zs_end, ps_end, environment):
+    """EigenRays.received_angles (ray_objects.py:519-531) for all rays of a receiver at once: ``prt_received_angles``
+    on the stored end states and the un-flattened sound speed (reference quirk Q10), staged once per environment."""
+    import ctypes as C  # noqa: PLC0415
 
-    Same cell rule and weight expression as the reference's bilinear_interp, in numpy scalars.
-    """
-    i = int(np.searchsorted(rin, x)) - 1
-    j = int(np.searchsorted(zin, y[1])) - 1
-    i = max(0, min(i, len(rin) - 2))
-    j = max(0, min(j, len(zin) - 2))
-    wx = (x - rin[i]) / (rin[i + 1] - rin[i])
-    wy = (y[1] - zin[j]) / (zin[j + 1] - zin[j])
-    c = (
-        (1 - wx) * (1 - wy) * cin[i, j]
-        + wx * (1 - wy) * cin[i + 1, j]
-        + (1 - wx) * wy * cin[i, j + 1]
-        + wx * wy * cin[i + 1, j + 1]
-    )
-    with np.errstate(invalid="ignore"):
-        theta = np.degrees(np.arcsin(y[2] * c))
-    return theta, c
+    import torch  # noqa: PLC0415
+
+    from . import _lib  # noqa: PLC0415
+
+    L = _lib.require_gpu()
+    n = int(np.shape(zs_end)[0])
+    if n == 0:
+        return np.zeros(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    grid = unflattened_grid_on_device(environment, dev)
+    with torch.cuda.device(dev):
+        z_d = torch.from_numpy(np.ascontiguousarray(zs_end, dtype=np.float64)).to(dev)
+        p_d = torch.from_numpy(np.ascontiguousarray(ps_end, dtype=np.float64)).to(dev)
+        out = torch.empty(n, dtype=torch.float64, device=dev)
+        rc = L.prt_received_angles(n, float(x), C.c_void_p(z_d.data_ptr()), C.c_void_p(p_d.data_ptr()), grid["n_r"],
+                                   grid["n_z"], C.c_void_p(grid["rin"].data_ptr()), C.c_void_p(grid["zin"].data_ptr()),
+                                   C.c_void_p(grid["cin"].data_ptr()), C.c_void_p(out.data_ptr()),
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "prt_received_angles")
+        return out.cpu().numpy()
+
+
+def unflattened_grid_on_device(environment, dev):
+    """``environment.sound_speed`` (values + coordinates, NOT flat-earth transformed) as CUDA tensors, cached on the
+    environment object per device: the grid ``ray_angle`` is evaluated on for received angles."""
+    import torch  # noqa: PLC0415
+
+    cache = environment.__dict__.setdefault("_prt_unflattened_cache", {})
+    ss = environment.sound_speed
+    cin = np.ascontiguousarray(np.asarray(ss.values), dtype=np.float64)
+    key = (dev.index, cin.shape, float(cin[0, 0]), float(cin[-1, -1]), float(cin.sum()))
+    hit = cache.get("grid")
+    if hit is None or hit["key"] != key:
+        rin = np.ascontiguousarray(np.asarray(ss.coords["range"].values), dtype=np.float64)
+        zin = np.ascontiguousarray(np.asarray(ss.coords["depth"].values), dtype=np.float64)
+        hit = dict(key=key, n_r=int(rin.shape[0]), n_z=int(zin.shape[0]), cin=torch.from_numpy(cin).to(dev),
+                   rin=torch.from_numpy(rin).to(dev), zin=torch.from_numpy(zin).to(dev))
+        cache["grid"] = hit
+    return hit
 
 
 class EigenRays:
-    """Eigenrays per receiver depth (dicts keyed by receiver index), ray_objects.py:433-548."""
+    """Eigenrays per receiver depth (dicts keyed by receiver index), ray_objects.py:433-548.
+
+    ``eigenray_dict[ridx]`` is a ``RayFan`` or a list of ``Ray`` (as in the reference).  No per-ray host loop: received
+    angles come from ``prt_received_angles`` (or, when the fan was assembled by :func:`pygenray_b200.find_eigenrays`,
+    from the device-built eigenray table it carries), ray ids from vectorised numpy.  A receiver without eigenrays
+    yields empty arrays (the reference raises an AxisError there: ``RayFan([])``, ray_objects.py:135-144).
+    """
 
     def __init__(
         self, receiver_depths, eigenray_dict, environment, num_eigenrays, num_eigenrays_found,
@@ -249,33 +235,28 @@ class EigenRays:
         self.num_eigenrays_found = num_eigenrays_found
         self.failed_eray_theta_brackets = failed_eray_theta_brackets
 
-        ss = environment.sound_speed
-        cin = np.asarray(ss.values)
-        rin = np.asarray(ss.coords["range"].values)
-        zin = np.asarray(ss.coords["depth"].values)
-
         for ridx in range(len(receiver_depths)):
             fan = eigenray_dict[ridx]
             if not isinstance(fan, RayFan):
                 fan = RayFan(fan)
             self.rs[ridx], self.ts[ridx], self.zs[ridx], self.ps[ridx] = fan.rs, fan.ts, fan.zs, fan.ps
             self.n_botts[ridx], self.n_surfs[ridx] = fan.n_botts, fan.n_surfs
-            angles, ids, ids_int = [], [], []
             n_rays = fan.rs.shape[0] if fan.rs.ndim == 2 else 0
-            for k in range(n_rays):
-                # received angle from the STORED (negative-z) state and the un-flattened sound
-                # speed -- numerically odd but it is the reference's output
-                y_last = np.stack((fan.ts[k, -1], fan.zs[k, -1], fan.ps[k, -1]))
-                theta, _ = _ray_angle_host(fan.rs[k, -1], y_last, cin, rin, zin)
-                angles.append(theta)
-                number = np.sum(np.diff(np.sign(fan.ps[k, :])) != 0) * np.sign(fan.thetas[k])
-                free = fan.n_botts[k] == 0 and fan.n_surfs[k] == 0
-                ids.append(f"{number}{'' if free else 'b'}")
-                ids_int.append(int(number))
-            self.received_angles[ridx] = np.array(angles)
+            table = getattr(fan, "_eigen_table", None)  # (received angles, ray id numbers) built on the device
+            if n_rays == 0:
+                recv, numbers = np.zeros(0), np.zeros(0)
+            elif table is not None:
+                recv, numbers = table
+            else:
+                # received angle from the STORED (negative-z) state and the un-flattened sound speed --
+                # numerically odd but it is the reference's output
+                recv = _received_angles_device(fan.rs[0, -1], fan.zs[:, -1], fan.ps[:, -1], environment)
+                numbers = _ray_id_numbers(fan.ps, fan.thetas)
+            free = (np.asarray(fan.n_botts) == 0) & (np.asarray(fan.n_surfs) == 0) if n_rays else np.zeros(0, bool)
+            self.received_angles[ridx] = np.asarray(recv, dtype=np.float64)
             self.launch_angles[ridx] = fan.thetas
-            self.ray_id[ridx] = np.array(ids)
-            self.ray_id_int[ridx] = np.array(ids_int)
+            self.ray_id[ridx] = _ray_id_strings(numbers, free)
+            self.ray_id_int[ridx] = np.asarray(numbers).astype(np.int64)
 
     def save_mat(self, filename):
         data = {}
@@ -297,34 +278,3 @@ class EigenRays:
                 "num_eigenrays_found": self.num_eigenrays_found,
             }
         io.savemat(filename, {"eigenrays": data})
-
-    def plot_angle_time(self, ridxs=None, **kwargs):
-        plt = _plt()
-        for ridx in ridxs if ridxs is not None else list(self.received_angles.keys()):
-            plt.scatter(self.ts[ridx][:, -1], self.received_angles[ridx], **kwargs)
-        plt.xlabel("time [s]")
-        plt.ylabel("received angle [deg]")
-        plt.title("Received Angle vs Time")
-
-    def plot(self, ridxs=(0,), **kwargs):
-        plt = _plt()
-        if isinstance(ridxs, int):
-            ridxs = [ridxs]
-        style = {"c": "k"}
-        style.update(kwargs)
-        for ridx in ridxs:
-            plt.plot(self.rs[ridx].T, self.zs[ridx].T, **style)
-        plt.xlabel("range [m]")
-        plt.ylabel("depth [m]")
-        plt.title("Eigen Rays")
-
-    def plot_ducted(self, **kwargs):
-        plt = _plt()
-        style = {"c": "k"}
-        style.update(kwargs)
-        for ridx in self.ray_id:
-            free = (self.n_botts[ridx] == 0) & (self.n_surfs[ridx] == 0)
-            plt.plot(self.rs[ridx][free].T, -self.zs[ridx][free].T, **style)
-        plt.xlabel("range [m]")
-        plt.ylabel("depth [m]")
-        plt.title("Ducted Eigen Rays")

@@ -140,3 +140,19 @@ def oracle_shoot_ray(env, source_depth, source_range, launch_angle, receiver_ran
     tr = o["traj"][0]
     return dict(r=-rs if backwards else rs, t=tr[0], z=-tr[1], p=-tr[2], n_bottom=int(o["n_bottom"][0]),
                 n_surface=int(o["n_surface"][0]), launch_angle=internal)
+
+
+def ray_angle_numpy(x, y, cin, rin, zin):
+    """Checker for prt_received_angles: ray_angle + bilinear_interp of the reference restated in numpy scalars
+    (/root/reference/src/pygenray/integration_processes.py:101-174, 306-334): cell = searchsorted - 1 clamped to
+    [0, n - 2], unclamped weights, four-term sum, degrees(arcsin(p c))."""
+    i = int(np.searchsorted(rin, x)) - 1
+    j = int(np.searchsorted(zin, y[1])) - 1
+    i = max(0, min(i, len(rin) - 2))
+    j = max(0, min(j, len(zin) - 2))
+    wx = (x - rin[i]) / (rin[i + 1] - rin[i])
+    wy = (y[1] - zin[j]) / (zin[j + 1] - zin[j])
+    c = ((1 - wx) * (1 - wy) * cin[i, j] + wx * (1 - wy) * cin[i + 1, j] + (1 - wx) * wy * cin[i, j + 1]
+         + wx * wy * cin[i + 1, j + 1])
+    with np.errstate(invalid="ignore"):
+        return np.degrees(np.arcsin(y[2] * c)), c

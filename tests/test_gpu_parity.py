@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from conftest import assert_same_fan, golden, make_env, oracle_env_from
+from conftest import assert_same_fan, golden, make_env, oracle_env_from, ray_angle_numpy
 import workloads as cases
 from oracle import oracle as orc
 
@@ -389,7 +389,7 @@ def test_config3_full_size_subsample_bit_identical(pr, cfg3_fan):
     assert ok.mean() > 0.97 and np.isnan(final[:, ~ok]).all() and not np.isnan(final[:, ok]).any()
     assert (final[0, ok] > 1000e3 / 1560.0).all() and (final[0, ok] < 1000e3 / 1400.0).all()  # travel times
     free = ok & (nb + ns == 0)
-    assert free.mean() > 0.8 and (np.abs(ang[free]) < 13.5).all()
+    assert free.mean() > 0.8 and (np.abs(ang[free]) < 14.0).all()
     # a second launch of a shuffled slice of the fan returns the same bits (rays are independent; lane/warp
     # placement must not matter)
     rng = np.random.default_rng(7)
@@ -461,3 +461,84 @@ def test_bracket_fill_edge_cases(pr):
         assert np.array_equal(counts, [len(k) for k in exp]), n
         assert np.array_equal(br["k"].cpu().numpy(), np.concatenate(exp)), n
         assert np.array_equal(br["rcv"].cpu().numpy(), np.repeat(np.arange(5), counts)), n
+
+
+# ---- device-side eigenray post-processing (EigenRays.__init__, ray_objects.py:505-548) ------------------------------
+def test_eigenrays_container_from_ray_lists(pr, tmp_path):
+    """EigenRays built the reference's way (lists of Ray): received angles from prt_received_angles == the numpy
+    restatement of ray_angle on the stored end state and the un-flattened sound speed (quirk Q10)."""
+    from pygenray_b200 import EigenRays, Ray, RayFan
+
+    def make_ray(launch_angle, source_depth, n_bottom=0, n_surface=0, N=10, R=10000.0):
+        r = np.linspace(0.0, R, N)
+        y = np.vstack([r / 1500.0, np.linspace(source_depth, source_depth + R * 0.01, N),
+                       np.cos(np.linspace(0, 7, N)) * np.sin(np.radians(abs(launch_angle) + 1e-3)) / 1500.0])
+        return Ray(r=r, y=y, n_bottom=n_bottom, n_surface=n_surface, launch_angle=launch_angle, source_depth=source_depth)
+
+    env = pr.OceanEnvironment2D(flat_earth_transform=False)
+    fans = {0: [make_ray(-5.0, 100.0), make_ray(5.0, 100.0, n_surface=1)],
+            1: RayFan([make_ray(-5.0, 100.0), make_ray(5.0, 150.0, n_bottom=1), make_ray(-10.0, 200.0)]), 2: []}
+    er = EigenRays([1000.0, 2000.0, 3000.0], fans, env, {1000.0: 2, 2000.0: 3, 3000.0: 0}, {0: 2, 1: 3, 2: 0},
+                   {0: [], 1: [], 2: []})
+    assert er.ts[0].shape == (2, 10) and er.zs[1].shape == (3, 10) and er.received_angles[2].shape == (0,)
+    assert list(er.ray_id[0]) == ["-2.0", "2.0b"] and list(er.ray_id_int[0]) == [-2, 2]
+    assert np.array_equal(er.launch_angles[1], [-5.0, 5.0, -10.0])
+    ss = env.sound_speed
+    for ridx in (0, 1):
+        exp = [ray_angle_numpy(er.rs[ridx][k, -1], (er.ts[ridx][k, -1], er.zs[ridx][k, -1], er.ps[ridx][k, -1]),
+                               np.asarray(ss.values), np.asarray(ss.coords["range"].values),
+                               np.asarray(ss.coords["depth"].values))[0] for k in range(er.rs[ridx].shape[0])]
+        assert np.abs(er.received_angles[ridx] - np.array(exp)).max() < 1e-11  # degrees; asin differs by ulps
+    er.save_mat(str(tmp_path / "e.mat"))
+
+
+def test_eigenray_table_matches_host_restatement(pr):
+    """prt_eigen_table on a config-2 refinement: rows == (receiver, T, -z, -p, theta, received angle, ray id number,
+    bounces, bracket) assembled on the host from the same refinement + re-shot; find_eigenrays serves the same
+    numbers through the reference's EigenRays object."""
+    env = make_env(cases.config2_arrays())
+    fan = pr.shoot_rays(1000.0, 0.0, np.linspace(-14, 14, 400), 300e3, 31, env, rtol=1e-9, debug=False, flatearth=False)
+    rds = [float(v) for v in np.linspace(300.0, 4000.0, 6)]
+    denv = pr.DeviceEnvironment(*pr._unpack_envi(env, flatearth=False))
+    br, counts = pr.find_brackets(fan.zs[:, -1], fan.thetas, rds)
+    ref = pr.refine_brackets(denv, br, 1000.0, 0.0, 300e3, ztol=1.0, max_iter=20)
+    tab = pr.eigenray_table(denv, br, ref, env, 1000.0, 0.0, 300e3, num_range_save=31)
+    st = ref["status"].cpu().numpy()
+    conv = np.flatnonzero(st == 0)
+    t = tab["table"]
+    assert t.shape == (len(conv), 10) and len(conv) > 20 and tab["n_converged"] == len(conv)
+    fin = ref["final"].cpu().numpy()
+    assert np.array_equal(t[:, 9], conv) and np.array_equal(t[:, 0], br["rcv"].cpu().numpy()[conv])
+    assert np.array_equal(t[:, 1], fin[0, conv]) and np.array_equal(t[:, 2], -fin[1, conv]) and np.array_equal(t[:, 3], -fin[2, conv])
+    assert np.array_equal(t[:, 4], ref["theta"].cpu().numpy()[conv])
+    assert np.array_equal(t[:, 7], ref["n_bottom"].cpu().numpy()[conv]) and np.array_equal(t[:, 8], ref["n_surface"].cpu().numpy()[conv])
+    ss = env.sound_speed
+    cin, rin, zin = np.asarray(ss.values), np.asarray(ss.coords["range"].values), np.asarray(ss.coords["depth"].values)
+    exp = np.array([ray_angle_numpy(300e3, (t[k, 1], t[k, 2], t[k, 3]), cin, rin, zin)[0] for k in range(len(conv))])
+    assert np.abs(t[:, 5] - exp).max() < 1e-11
+    traj = tab["fan"]["traj"]  # re-shot of the converged angles, stored convention
+    assert np.array_equal(traj[:, :, -1], np.stack((t[:, 1], t[:, 2], t[:, 3])))  # same ray as the converged trial
+    ids = np.sum(np.diff(np.sign(traj[2]), axis=1) != 0, axis=1) * np.sign(t[:, 4])
+    assert np.array_equal(t[:, 6], ids)
+    assert np.array_equal(tab["offsets"], np.searchsorted(t[:, 0], np.arange(7)))
+    er = pr.find_eigenrays(fan, rds, 1000.0, 0.0, 300e3, 31, env, ztol=1.0, max_iter=20, flatearth=False, debug=False)
+    for i in range(6):
+        a, b = tab["offsets"][i], tab["offsets"][i + 1]
+        assert er.num_eigenrays_found[i] == b - a and er.num_eigenrays[rds[i]] == counts[i]
+        assert np.array_equal(er.received_angles[i], t[a:b, 5]) and np.array_equal(er.launch_angles[i], t[a:b, 4])
+        assert np.array_equal(er.ray_id_int[i], t[a:b, 6].astype(np.int64))
+        assert np.array_equal(er.ts[i][:, -1], t[a:b, 1]) and np.array_equal(er.zs[i][:, -1], t[a:b, 2])
+        free = (t[a:b, 7] == 0) & (t[a:b, 8] == 0)
+        assert list(er.ray_id[i]) == [f"{v}{'' if f else 'b'}" for v, f in zip(t[a:b, 6], free)]
+        assert len(er.failed_eray_theta_brackets[i]) == counts[i] - (b - a)
+
+
+def test_find_eigenrays_when_nothing_converges(pr):
+    """ztol far below the step-sequence noise: no bracket converges; the product returns empty per-receiver arrays
+    (the reference raises an AxisError on RayFan([]), recorded in tests/golden/ref_cfg4_sub_*.npz)."""
+    env = make_env(cases.config2_arrays())
+    fan = pr.shoot_rays(1000.0, 0.0, np.linspace(-14, 14, 100), 300e3, 11, env, rtol=1e-9, debug=False, flatearth=False)
+    er = pr.find_eigenrays(fan, [1500.0], 1000.0, 0.0, 300e3, 11, env, ztol=1e-12, max_iter=3, flatearth=False, debug=False)
+    assert er.num_eigenrays_found[0] == 0 and er.num_eigenrays[1500.0] > 0
+    assert er.ts[0].shape == (0, 11) and er.received_angles[0].shape == (0,)
+    assert len(er.failed_eray_theta_brackets[0]) == er.num_eigenrays[1500.0]
