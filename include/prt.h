@@ -223,6 +223,10 @@ PRT_API int prt_fill_brackets(int64_t n_rays, const double *z_end_dev, const dou
  * one trial shot per round; each trial is a full ray (no trajectory).  theta are USER angles: the
  * trial ray is launched with internal angle -theta (launch_rays.py:251).
  *   work_dev: caller-provided scratch of prt_refine_workspace_bytes(n_br) bytes
+ *   order_dev [n_br] int32 or NULL: a permutation of 0..n_br-1, the order in which the brackets are laid out over
+ *             warps (results do not depend on it).  Brackets sorted by launch angle put 32 nearly identical trial
+ *             rays in a warp -- same steps, same grid cells, same reflections -- which the (receiver, ray) order of
+ *             prt_fill_brackets does not (neighbours there are ~80 fan rays apart): 1.9x faster trial shots on config 4
  *   out_theta_dev [n_br]  converged user launch angle (NaN otherwise)
  *   out_final_dev [3][n_br], out_n_bottom_dev, out_n_surface_dev, out_status_dev (PRT_EIG_*),
  *   out_shots_dev [n_br], out_ray_status_dev [n_br] (PRT_RAY_* of the dropped trial)
@@ -236,7 +240,36 @@ PRT_API int prt_refine_brackets(const prt_env_t *env, int64_t n_br, const double
                         double atol, int32_t terminate_backwards, double ztol, int32_t max_iter,
                         double *out_theta_dev, double *out_final_dev, int32_t *out_n_bottom_dev,
                         int32_t *out_n_surface_dev, int32_t *out_status_dev, int32_t *out_shots_dev,
-                        int32_t *out_ray_status_dev, void *work_dev, int32_t max_bounces, void *stream);
+                        int32_t *out_ray_status_dev, void *work_dev, const int32_t *order_dev, int32_t max_bounces,
+                        void *stream);
+
+/*
+ * Earth flattening of sound-speed grids in device memory (environment.py:121-151, 239-401) -- the step right before
+ * the path, per realisation in ensemble mode.  c_dev / out_dev: [n_env][n_r][n_z]; depth_dev [n_z] the UN-flattened
+ * depth coordinate; re_dev [n_r] the local earth radius of every range column (WGS-84, eflat :382-395; one value
+ * repeated for the single-latitude transform).
+ *   resample = 0: out = c (1 + E (1 + E)), E = depth / re  (the values of flat_earth_transform; the caller also
+ *                 stretches the depth coordinate: z_f = z (1 + E (1/2 + E / 3)))
+ *   resample = 1: flat_earth_c: the flattened column on its stretched grid interpolated back onto depth_dev
+ *                 (linear, NaN outside), i.e. sound_speed_fe of flat_earth_transform_rd.  Not in place.
+ */
+PRT_API int prt_flat_earth(int32_t n_env, int32_t n_r, int32_t n_z, const double *depth_dev, const double *re_dev,
+                           const double *c_dev, int32_t resample, double *out_dev, void *stream);
+
+/*
+ * Perturbed sound-speed realisations generated in device memory for tomography ensembles (BASELINE config 5; the
+ * reference has no generator -- SURVEY.md section 8f rank 3).  Separable internal-wave-like field
+ *   out_e(r, z) = c_base(r, z) + s_e * sum_j vert[j][z] * sum_k cos(kappa[k] * r + phases[e][j][k])
+ * with s_e chosen so that the rms of the perturbation over range at depth index iax equals rms_axis.
+ *   r_dev [n_r], vert_dev [J][n_z] (amplitude-weighted vertical modes), kappa_dev [K], phases_dev [n_env][J][K],
+ *   c_base_dev [n_r][n_z], work_dev: prt_iw_workspace_bytes(n_env, n_r, J) bytes, out_dev [n_env][n_r][n_z]
+ * The result feeds prt_ensemble_create_dev directly (nothing crosses PCIe but the phase table).
+ */
+PRT_API int64_t prt_iw_workspace_bytes(int32_t n_env, int32_t n_r, int32_t J);
+PRT_API int prt_iw_perturb(int32_t n_env, int32_t n_r, int32_t n_z, int32_t J, int32_t K, const double *r_dev,
+                           const double *vert_dev, const double *kappa_dev, const double *phases_dev,
+                           const double *c_base_dev, int32_t iax, double rms_axis, void *work_dev, double *out_dev,
+                           void *stream);
 
 /*
  * Eigenray post-processing on the device (EigenRays.__init__, ray_objects.py:505-548).

@@ -273,9 +273,23 @@ def case_cfg4_sub():
     save("ref_cfg4_sub", **out)
 
 
+def case_flatearth():
+    """eflat / eflatinv of the reference (environment.py:371-466) on a spread of depths and latitudes.
+    (flat_earth_c needs xarray's DataArray.interp, which the import stub does not provide: unpinned.)"""
+    from pygenray.environment import eflat, eflatinv
+
+    dep = np.concatenate(([1.0], np.linspace(10.0, 6000.0, 41)))
+    out = {"dep": dep, "lats": np.array([-60.0, 0.0, 35.0, 80.0])}
+    for lat in out["lats"]:
+        depf, csf = eflat(dep, lat, 1480.0 + 0.017 * dep)
+        d_inv, c_inv = eflatinv(depf, lat, csf)
+        out[f"depf_{lat}"] = depf; out[f"csf_{lat}"] = csf; out[f"dinv_{lat}"] = d_inv; out[f"cinv_{lat}"] = c_inv
+    save("ref_flatearth", **out)
+
+
 CASES = dict(cfg1=case_cfg1, fixture=case_fixture, cfg2_sub=case_cfg2_sub, bounce_fine=case_bounce_fine,
              physics=case_physics, eigen=case_eigen, cfg3_sub=case_cfg3_sub,
-             cfg4_sub=case_cfg4_sub)
+             cfg4_sub=case_cfg4_sub, flatearth=case_flatearth)
 # cases re-run without the JIT to measure the reference's own self-consistency envelope
 NOJIT_CASES = ("cfg1", "cfg2_sub", "bounce_fine", "cfg3_sub", "cfg4_sub")
 

@@ -8,7 +8,7 @@
 Everything numerical runs in libprt.so (hand-written sm_100a CUDA, C ABI in include/prt.h).
 There is no CPU fallback: without the built library and a CUDA device the compute calls raise.
 """
-from . import _lib, dist
+from . import _lib, dist, ensemble
 from .eigenrays import eigenray_table, find_brackets, find_eigenrays, refine_brackets
 from .environment import DataArray, OceanEnvironment2D, eflat, munk_ssp
 from .launch_rays import (DeviceEnsemble, DeviceEnvironment, _mirror_envi_arrays, _unpack_envi,
@@ -19,7 +19,7 @@ __all__ = [
     "OceanEnvironment2D", "DataArray", "munk_ssp", "eflat", "shoot_rays", "shoot_ray", "find_eigenrays",
     "Ray", "RayFan", "EigenRays", "shoot_fan_arrays", "shoot_ensemble_arrays", "find_brackets", "refine_brackets", "eigenray_table",
     "DeviceEnvironment",
-    "DeviceEnsemble", "dist",
+    "DeviceEnsemble", "dist", "ensemble",
     "bottom_angle_ppoly", "_unpack_envi", "_mirror_envi_arrays",
 ]
 __version__ = "0.1.0"

@@ -27,7 +27,7 @@ EXPORTS = (
     "prt_ensemble_create_dev",
     "prt_shoot_ensemble", "prt_env_destroy",
     "prt_env_device_bytes", "prt_shoot_fan", "prt_shoot_fan_host", "prt_pack_arrivals", "prt_bracket_workspace_bytes", "prt_count_brackets", "prt_fill_brackets",
-    "prt_refine_workspace_bytes", "prt_refine_brackets", "prt_received_angles", "prt_eigen_table", "prt_launch_count", "prt_measure_fp64_peak",
+    "prt_refine_workspace_bytes", "prt_refine_brackets", "prt_received_angles", "prt_eigen_table", "prt_flat_earth", "prt_iw_workspace_bytes", "prt_iw_perturb", "prt_launch_count", "prt_measure_fp64_peak",
 )
 
 
@@ -86,11 +86,17 @@ def load():
     L.prt_refine_workspace_bytes.argtypes = [i64]
     L.prt_refine_brackets.restype = C.c_int
     L.prt_refine_brackets.argtypes = [vp, i64, vp, vp, vp, vp, vp, d, d, d, d, d, i32, d, i32,
-                                      vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
+                                      vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]
     L.prt_received_angles.restype = C.c_int
     L.prt_received_angles.argtypes = [i64, d, vp, vp, i32, i32, vp, vp, vp, vp, vp]
     L.prt_eigen_table.restype = C.c_int
     L.prt_eigen_table.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp, d, i32, i32, vp, vp, vp, vp, vp]
+    L.prt_flat_earth.restype = C.c_int
+    L.prt_flat_earth.argtypes = [i32, i32, i32, vp, vp, vp, i32, vp, vp]
+    L.prt_iw_workspace_bytes.restype = i64
+    L.prt_iw_workspace_bytes.argtypes = [i32, i32, i32]
+    L.prt_iw_perturb.restype = C.c_int
+    L.prt_iw_perturb.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, d, vp, vp, vp]
     L.prt_launch_count.restype = i64
     L.prt_measure_fp64_peak.restype = d
     L.prt_measure_fp64_peak.argtypes = [C.c_int, i32]

@@ -51,6 +51,16 @@ PRT_HD prt_d2 prt_ld2(const prt_d2* p)
     return r;
 }
 PRT_HD double prt_ld(const double* p) { return __ldg(p); }
+#if defined(PRT_TEX_ROW1)
+__device__ __forceinline__ prt_d2 prt_tex2(unsigned long long tex, unsigned texel)
+{
+    const int4 t = tex1Dfetch<int4>((cudaTextureObject_t)tex, (int)texel);
+    prt_d2 r;
+    r.x = __hiloint2double(t.y, t.x);
+    r.y = __hiloint2double(t.w, t.z);
+    return r;
+}
+#endif
 #define PRT_FMA(a, b, c) __fma_rn((a), (b), (c))
 PRT_HD double prt_bits_to_double(uint64_t b) { return __longlong_as_double((long long)b); }
 PRT_HD uint64_t prt_double_to_bits(double d) { return (uint64_t)__double_as_longlong(d); }
@@ -121,6 +131,15 @@ struct prt_env_view {
     // least-squares quadratic q fitted at staging time (prt_env_layout.h); z_cubic == 0 for uniform grids
     double z_b1, z_b2, z_b3, z_un;
     int32_t z_cubic;
+    // exactly uniform depth grids (np.arange / np.linspace with a representable step): zin[j] == fma(j, z_dz, z0) and
+    // 1/(zin[j+1]-zin[j]) == z_r0 bit for bit for every cell (checked at staging time) -- the stage lookups then
+    // COMPUTE the lower edge and take the reciprocal as a constant instead of loading {zin[j], 1/dz_j} from a table:
+    // one scattered load less per lookup, and the kernel is bound by the L1 data pipe (profiles/r02_ncu_fan.md)
+    int32_t z_uniform;
+    double z_dz, z_r0;
+    // the sound-speed grid(s) once more as a linear texture of 16-byte texels (0 when not created): an experiment that
+    // routes the loads of range row i + 1 through the texture pipe of L1TEX (PRT_TEX_ROW1, profiles/r02_variants.md)
+    unsigned long long grid_tex;
     int32_t spec_off;       // 1: guesses too poor on this environment (irregular grids) -> every trial step uses the exact lookup
     const prt_d2* rxr;      // [n_r-1] {rin[i], 1/(rin[i+1]-rin[i])}: all the speculative stage lookup needs per axis
     const prt_d2* zxr;      // [n_z-1] {zin[j], 1/(zin[j+1]-zin[j])}
@@ -128,13 +147,16 @@ struct prt_env_view {
     double bb_zmax, bb_zmin, bb_rmin, bb_rmax;  // zin[-1]+1e-6, zin[0]-1e-6, rin[0]-1e-6, rin[-1]+1e-6
 };
 
+PRT_HD int prt_z_mode(const prt_env_view& v) { return v.z_uniform ? 2 : (v.z_cubic ? 1 : 0); }
+
 // One ray's environment: the shared tables plus this ray's sound-speed grid (ensembles: one grid per
 // realisation behind one set of tables).  The tables are referenced, never copied, so that on the device
 // every field is read straight from the kernel's __grid_constant__ parameter.
 struct prt_envp {
     const prt_env_view& v;
     const prt_d2* grid;
-    bool zc;  // == (v.z_cubic != 0); a compile-time constant in each kernel instantiation, so uniform grids pay nothing
+    int zm;   // depth-axis mode, a compile-time constant in each kernel instantiation: 0 linear cell guess, 1 guess refined
+              // by the fitted quadratic (v.z_cubic), 2 exactly uniform grid, cell edges computed (v.z_uniform)
 };
 
 // np.nextafter(t, +inf) (scipy rk.py:119) by integer increment of the bit pattern (select-only: it opens
@@ -436,7 +458,7 @@ PRT_HD unsigned prt_guess(double v, double inv, double off, int m)
 PRT_HD unsigned prt_guess_z_from(const prt_envp& E, double s)
 {
     const prt_env_view& V = E.v;
-    if (E.zc) {
+    if (E.zm == 1) {
         const double u = s * V.z_un;
         s = PRT_FMA(s, PRT_FMA(PRT_FMA(V.z_b3, u, V.z_b2), u, V.z_b1), s);
     }
@@ -528,8 +550,19 @@ PRT_HD void prt_field_spec(const prt_envp& E, const prt_xcell& xc, double z, dou
     const unsigned j = prt_guess_z_from(E, sg);
     const unsigned e0 = xc.row + j, e1 = e0 + (unsigned)V.n_z;
     const prt_d2 *g0 = E.grid + e0, *g1 = E.grid + e1;
-    const prt_d2 za = prt_ld2(V.zxr + j);
+    prt_d2 za;
+    if (E.zm == 2) {
+        za.x = PRT_FMA((double)j, V.z_dz, V.z0);
+        za.y = V.z_r0;
+    } else {
+        za = prt_ld2(V.zxr + j);
+    }
+#if defined(__CUDA_ARCH__) && defined(PRT_TEX_ROW1)
+    const unsigned t1 = (unsigned)(E.grid - V.grid) + e1;  // texel index of node (i + 1, j) (ensembles: this ray's grid)
+    const prt_d2 v00 = prt_ld2(g0), v01 = prt_ld2(g0 + 1), v10 = prt_tex2(V.grid_tex, t1), v11 = prt_tex2(V.grid_tex, t1 + 1u);
+#else
     const prt_d2 v00 = prt_ld2(g0), v01 = prt_ld2(g0 + 1), v10 = prt_ld2(g1), v11 = prt_ld2(g1 + 1);
+#endif
     const double wy = (z - za.x) * za.y;
     ok = ok & (prt_w_proven(wy) | ((j == 0u) & prt_w_negative_finite(wy)));  // waiver: above the surface (overshoot before a reflection)
     prt_bilerp(v00, v01, v10, v11, xc.wx, wy, c, cz);
@@ -920,7 +953,7 @@ PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, do
     // sum, stage input, guess): the guess differs from the literal one by rounding only, and any guess is a correct
     // guess (the weight proves it), so results do not change; the FP64 chain of every stage gets 2 operations shorter.
 #ifndef PRT_FOLD_GUESS
-#define PRT_FOLD_GUESS 1
+#define PRT_FOLD_GUESS 0
 #endif
     const double hz = hh * E.v.z_inv, zz = PRT_FMA(z, E.v.z_inv, E.v.z_off);
 #define PRT_GUESS(zs, a_last, k_last, a_part) \
@@ -1042,7 +1075,7 @@ PRT_HD_NOINLINE void prt_rk_try_exact(const prt_env_view* V, const prt_d2* grid,
                                       double hh, double T, double z, double p, double f0, double f1, double f2,
                                       prt_try* out)
 {
-    const prt_envp E{*V, grid, V->z_cubic != 0};
+    const prt_envp E{*V, grid, prt_z_mode(*V)};
     bool ok = true;
 #if defined(PRT_COUNT_COLD) && !defined(__CUDACC__)
     extern long long prt_cold_count;

@@ -252,6 +252,17 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
         }
     }
     if (err_r > tol_ok || err_b > tol_ok || err_z > tol_ok) v.spec_off = 1;
+    // exactly uniform depth grid?  (every lower edge reproduced by one fma, every reciprocal width identical)
+    v.grid_tex = 0;
+    v.z_uniform = 0;
+    v.z_dz = zin[1] - zin[0];
+    v.z_r0 = 1.0 / (zin[1] - zin[0]);
+    if (!v.z_cubic && !v.spec_off) {
+        bool uniform = true;
+        for (int j = 0; j < n_z - 1 && uniform; ++j)
+            uniform = (fma((double)j, v.z_dz, v.z0) == zin[j]) && (1.0 / (zin[j + 1] - zin[j]) == v.z_r0);
+        v.z_uniform = uniform ? 1 : 0;
+    }
     // ray_bounding_box_event tolerances (integration_processes.py:280-303)
     const double tol = 1e-6;
     v.bb_zmax = zin[n_z - 1] + tol;

@@ -1,6 +1,6 @@
 // prt_kernels.cu -- sm_100a kernels + the C ABI of libprt.so (include/prt.h).
 //
-// K1  prt_fan_kernel<SAVE, ZC>  one FP64 thread per launch angle: the whole ray (all solve_ivp
+// K1  prt_fan_kernel<SAVE, ZM, COUNT>  one FP64 thread per launch angle: the whole ray (all solve_ivp
 //                               segments, events, reflections, save-grid resampling) in registers.
 // K2  prt_refine_round_kernel   one regula-falsi trial shot per active eigenray bracket.
 // K3  prt_count/fill_brackets   sign-change bracketing of the arrival table.
@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 #include <mutex>
@@ -56,6 +57,29 @@ struct prt_device_guard {
     prt_device_guard guard__(dev);                                                                  \
     if (guard__.err != cudaSuccess)                                                                 \
         return fail(PRT_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(guard__.err))
+
+#if defined(PRT_TEX_ROW1)
+// the grid region of an environment as a linear texture of int4 texels (one {c, dc/dz} node each)
+static cudaError_t prt_make_grid_texture(prt_env_view& v)
+{
+    cudaResourceDesc res;
+    memset(&res, 0, sizeof res);
+    res.resType = cudaResourceTypeLinear;
+    res.res.linear.devPtr = const_cast<prt_d2*>(v.grid);
+    res.res.linear.desc = cudaCreateChannelDesc<int4>();
+    res.res.linear.sizeInBytes = sizeof(prt_d2) * (size_t)v.n_r * (size_t)v.n_z * (size_t)(v.n_env > 0 ? v.n_env : 1);
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof td);
+    td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t tex = 0;
+    cudaError_t e = cudaCreateTextureObject(&tex, &res, &td, nullptr);
+    v.grid_tex = (unsigned long long)tex;
+    return e;
+}
+#define PRT_MAKE_TEX(env) do { cudaError_t te__ = prt_make_grid_texture((env)->view); if (te__ != cudaSuccess) return fail(PRT_ERR_CUDA, std::string("texture: ") + cudaGetErrorString(te__)); } while (0)
+#else
+#define PRT_MAKE_TEX(env) do { } while (0)
+#endif
 
 struct prt_env {
     int device;
@@ -198,7 +222,7 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SA
 #define PRT_BLOCK_ARR 128  // threads per block, arrival-table kernels (fan without save grid, eigenray trial shots)
 #endif
 #define PRT_BLOCK_MAX (PRT_BLOCK > PRT_BLOCK_ARR ? PRT_BLOCK : PRT_BLOCK_ARR)
-template <bool SAVE, bool ZC, bool COUNT>
+template <bool SAVE, int ZM, bool COUNT>
 __global__ void __launch_bounds__(SAVE ? PRT_BLOCK : PRT_BLOCK_ARR, SAVE ? PRT_MIN_BLOCKS : PRT_MIN_BLOCKS_ARR) prt_fan_kernel(const __grid_constant__ prt_env_view E0,
                                                       const __grid_constant__ prt_fan_params P)
 {
@@ -221,7 +245,7 @@ __global__ void __launch_bounds__(SAVE ? PRT_BLOCK : PRT_BLOCK_ARR, SAVE ? PRT_M
         angle_index = ray - env * P.rays_per_env;
         grid = E0.grid + env * E0.grid_stride;
     }
-    const prt_envp E{E0, grid, ZC};
+    const prt_envp E{E0, grid, ZM};
     prt_shot S;
     S.x_end = P.receiver_range; S.rtol = P.rtol; S.atol = P.atol;
     S.terminate_backwards = P.terminate_backwards; S.n_save = P.n_save; S.max_bounces = P.max_bounces;
@@ -510,7 +534,7 @@ struct prt_refine_params {
 __global__ void prt_refine_init_kernel(prt_refine_state S, int64_t n_br, const double* __restrict__ z1,
                                        const double* __restrict__ z2, const double* __restrict__ th1,
                                        const double* __restrict__ th2, const double* __restrict__ rd,
-                                       prt_refine_params P)
+                                       const int32_t* __restrict__ order, prt_refine_params P)
 {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b == 0) {
@@ -526,7 +550,7 @@ __global__ void prt_refine_init_kernel(prt_refine_state S, int64_t n_br, const d
     S.th[b] = th1[b] - (z1[b] + rd[b]) * (th2[b] - th1[b]) / (z2[b] - z1[b]);
     S.iter[b] = 0;
     S.shots[b] = 0;
-    S.list_a[b] = (int32_t)b;
+    S.list_a[b] = order ? order[b] : (int32_t)b;  // processing order: slot b of the first round
     P.out_theta[b] = NAN;
     P.out_final[b] = NAN;
     P.out_final[n_br + b] = NAN;
@@ -538,13 +562,13 @@ __global__ void prt_refine_init_kernel(prt_refine_state S, int64_t n_br, const d
     P.out_ray_status[b] = 0;
 }
 
-template <bool ZC>
+template <int ZM>
 __global__ void __launch_bounds__(PRT_BLOCK_ARR, PRT_MIN_BLOCKS_ARR) prt_refine_round_kernel(const __grid_constant__ prt_env_view E0,
                                                                const __grid_constant__ prt_refine_params P,
                                                                prt_refine_state S, const int32_t* __restrict__ list_in,
                                                                const int32_t* n_in)
 {
-    const prt_envp E{E0, E0.grid, ZC};
+    const prt_envp E{E0, E0.grid, ZM};
     const int n_active = *n_in;
     // rays per warp: the rule of pick_lanes() on the number of brackets still active, which only the device knows
     // (the host never waits for a round): few survivors are spread over more, partly filled warps
@@ -807,6 +831,104 @@ __global__ void prt_stage_grid_kernel(int64_t n_nodes, int32_t n_z, const double
 }
 
 // ---------------------------------------------------------------------------------------------
+// Earth flattening of sound-speed grids that live in HBM (the preprocessing step right before the path; per
+// realisation in ensemble mode).  eflat (environment.py:371-401): E = z / R_e(lat), z_f = z (1 + E (1/2 + E / 3)),
+// c_f = c (1 + E (1 + E)).
+//   resample = 0: single-latitude transform (flat_earth_transform, :121-151): out = c_f on the stretched grid z_f
+//                 (the caller stretches the depth coordinate once).
+//   resample = 1: range-dependent transform (flat_earth_c, :239-368): every range column has its own earth radius
+//                 re[r]; c_f on z_f is interpolated back onto the ORIGINAL depth grid, linearly, as
+//                 xarray.DataArray.interp does through scipy interp1d (slope = (y_hi - y_lo) / (x_hi - x_lo),
+//                 y = slope (x - x_lo) + y_lo, interval by searchsorted clipped to [1, n - 1], NaN outside).
+__global__ void prt_flat_earth_kernel(int64_t n_nodes, int32_t n_r, int32_t n_z, const double* __restrict__ depth,
+                                      const double* __restrict__ re, const double* __restrict__ c, int resample,
+                                      double* __restrict__ out)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_nodes) return;
+    const int j = (int)(k % n_z);
+    const int r = (int)((k / n_z) % n_r);
+    const double R = re[r];
+    const double* col = c + (k - j);
+    auto zf = [&](int i) { const double E = depth[i] / R; return depth[i] * (1.0 + E * (0.50 + E / 3.0)); };
+    auto cf = [&](int i) { const double E = depth[i] / R; return col[i] * (1.0 + E * (1.0 + E)); };
+    if (!resample) {
+        out[k] = cf(j);
+        return;
+    }
+    const double x = depth[j];
+    // hi = searchsorted(z_f, x) clipped to [1, n_z - 1]; z_f[j] >= depth[j] for depth >= 0, so scan down from j
+    // (general input: scan up first)
+    int hi = j;
+    while (hi < n_z - 1 && zf(hi) < x) ++hi;
+    while (hi > 1 && !(zf(hi - 1) < x)) --hi;
+    hi = hi < 1 ? 1 : hi;
+    const int lo = hi - 1;
+    const double x_lo = zf(lo), x_hi = zf(hi), y_lo = cf(lo), y_hi = cf(hi);
+    const double slope = (y_hi - y_lo) / (x_hi - x_lo);
+    double y = slope * (x - x_lo) + y_lo;
+    if (!(x >= zf(0)) || !(x <= zf(n_z - 1))) y = NAN;  // bounds_error=False, fill_value=nan
+    out[k] = y;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tomography ensembles: perturbed sound-speed realisations generated in HBM (the
+// reference has no generator).  Separable internal-wave-like field
+//   dc_e(r, z) = s_e * sum_j V[j][z] * H_e[j][r],   H_e[j][r] = sum_k cos(kappa_k r + phi_e[j][k]),
+// V = amplitude-weighted vertical modes (host, [J][n_z]); s_e normalises the rms over range at depth index iax to
+// rms_axis.  out_e = c_base + dc_e.  (Plain CUDA libm cos: this defines inputs, it is not on the parity path.)
+__global__ void prt_iw_horizontal_kernel(int64_t n, int32_t n_r, int32_t K, const double* __restrict__ r,
+                                         const double* __restrict__ kappa, const double* __restrict__ phases,
+                                         double* __restrict__ H)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (e * J + j) * n_r + ir
+    if (i >= n) return;
+    const int ir = (int)(i % n_r);
+    const double* ph = phases + (i / n_r) * K;
+    const double x = r[ir];
+    double acc = 0.0;
+    for (int k = 0; k < K; ++k) acc += cos(kappa[k] * x + ph[k]);
+    H[i] = acc;
+}
+
+__global__ void prt_iw_scale_kernel(int32_t n_r, int32_t n_z, int32_t J, int32_t iax, double rms_axis,
+                                    const double* __restrict__ V, const double* __restrict__ H, double* __restrict__ scale)
+{
+    const int e = blockIdx.x;
+    const double* He = H + (size_t)e * J * n_r;
+    double acc = 0.0;
+    for (int ir = threadIdx.x; ir < n_r; ir += blockDim.x) {
+        double v = 0.0;
+        for (int j = 0; j < J; ++j) v += V[(size_t)j * n_z + iax] * He[(size_t)j * n_r + ir];
+        acc += v * v;
+    }
+    __shared__ double part[256];
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) scale[e] = rms_axis / sqrt(part[0] / (double)n_r);
+}
+
+__global__ void prt_iw_compose_kernel(int64_t n_nodes, int32_t n_r, int32_t n_z, int32_t J, const double* __restrict__ V,
+                                      const double* __restrict__ H, const double* __restrict__ scale,
+                                      const double* __restrict__ c_base, double* __restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (e * n_r + ir) * n_z + iz
+    if (i >= n_nodes) return;
+    const int iz = (int)(i % n_z);
+    const int64_t er = i / n_z;
+    const int ir = (int)(er % n_r);
+    const int64_t e = er / n_r;
+    const double* He = H + (size_t)e * J * n_r + ir;
+    double acc = 0.0;
+    for (int j = 0; j < J; ++j) acc += V[(size_t)j * n_z + iz] * He[(size_t)j * n_r];
+    out[i] = c_base[(size_t)ir * n_z + iz] + scale[e] * acc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP64 FMA-pipe peak: 8 independent DFMA chains per thread
 __global__ void prt_fp64_peak_kernel(double* out, int iters, double a, double b)
 {
@@ -883,6 +1005,7 @@ int prt_env_create(int device, int32_t n_r, int32_t n_z, const double* rin, cons
     env->dev_blob = dev;
     env->bytes = blob.bytes.size();
     env->view = prt_env_rebase(blob.view, dev);
+    PRT_MAKE_TEX(env);
     *out = env;
     return PRT_SUCCESS;
 }
@@ -911,6 +1034,7 @@ int prt_ensemble_create(int device, int32_t n_env, int32_t n_r, int32_t n_z, con
     env->dev_blob = dev;
     env->bytes = blob.bytes.size();
     env->view = prt_env_rebase(blob.view, dev);
+    PRT_MAKE_TEX(env);
     *out = env;
     return PRT_SUCCESS;
 }
@@ -957,6 +1081,7 @@ int prt_ensemble_create_dev(int device, int32_t n_env, int32_t n_r, int32_t n_z,
     env->dev_blob = dev;
     env->bytes = blob.total_bytes;
     env->view = prt_env_rebase(blob.view, dev);
+    PRT_MAKE_TEX(env);
     *out = env;
     return PRT_SUCCESS;
 }
@@ -965,6 +1090,7 @@ int prt_env_destroy(prt_env_t* env)
 {
     if (!env) return PRT_SUCCESS;
     prt_device_guard guard(env->device);
+    if (env->view.grid_tex) cudaDestroyTextureObject((cudaTextureObject_t)env->view.grid_tex);
     cudaFree(env->dev_blob);
     delete env;
     return PRT_SUCCESS;
@@ -1020,11 +1146,11 @@ static int shoot_fan_impl(const prt_env_t* env, int64_t n_rays, int64_t rays_per
     const int64_t n_warps = (n_rays + P.lanes - 1) / P.lanes;
     const unsigned grid = (unsigned)((n_warps * 32 + block - 1) / block);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const bool zc = env->view.z_cubic != 0;  // refined depth guess compiled in only for stretched depth grids
+    const int zm = prt_z_mode(env->view);  // depth-axis variant compiled in: plain / refined guess / exactly uniform grid
     const bool cnt = out_counters_dev != nullptr;
 #define PRT_FAN_LAUNCH(SV, Z, CN) prt_fan_kernel<SV, Z, CN><<<grid, block, 0, s>>>(env->view, P)
 #define PRT_FAN_PICK_CN(SV, Z) do { if (cnt) PRT_FAN_LAUNCH(SV, Z, true); else PRT_FAN_LAUNCH(SV, Z, false); } while (0)
-#define PRT_FAN_PICK_Z(SV) do { if (zc) PRT_FAN_PICK_CN(SV, true); else PRT_FAN_PICK_CN(SV, false); } while (0)
+#define PRT_FAN_PICK_Z(SV) do { if (zm == 2) PRT_FAN_PICK_CN(SV, 2); else if (zm == 1) PRT_FAN_PICK_CN(SV, 1); else PRT_FAN_PICK_CN(SV, 0); } while (0)
     if (save) PRT_FAN_PICK_Z(true);
     else PRT_FAN_PICK_Z(false);
 #undef PRT_FAN_PICK_Z
@@ -1074,6 +1200,41 @@ int prt_shoot_ensemble(const prt_env_t* env, int32_t n_env, int64_t rays_per_env
                           out_counters_dev, stored_convention, out_p_sign_changes_dev, max_bounces, stream);
 }
 
+// Scratch of prt_shoot_fan_host, kept between calls (grow-only, one per device): device memory for inputs and
+// outputs plus a page-locked staging block for everything but the trajectories, so that a call costs no
+// cudaMalloc / cudaFree, ONE staged host-to-device copy and TWO device-to-host copies (small outputs; trajectories).
+struct prt_host_scratch {
+    std::mutex lock;
+    unsigned char* dev = nullptr;
+    size_t dev_bytes = 0;
+    unsigned char* pin = nullptr;
+    size_t pin_bytes = 0;
+};
+static prt_host_scratch g_host_scratch[64];
+
+static cudaError_t host_scratch_reserve(prt_host_scratch& S, size_t dev_bytes, size_t pin_bytes)
+{
+    if (dev_bytes > S.dev_bytes) {
+        if (S.dev) cudaFree(S.dev);
+        S.dev = nullptr;
+        S.dev_bytes = 0;
+        const size_t want = dev_bytes + dev_bytes / 4;
+        cudaError_t e = cudaMalloc(&S.dev, want);
+        if (e != cudaSuccess) return e;
+        S.dev_bytes = want;
+    }
+    if (pin_bytes > S.pin_bytes) {
+        if (S.pin) cudaFreeHost(S.pin);
+        S.pin = nullptr;
+        S.pin_bytes = 0;
+        const size_t want = pin_bytes + pin_bytes / 4;
+        cudaError_t e = cudaMallocHost(&S.pin, want);
+        if (e != cudaSuccess) return e;
+        S.pin_bytes = want;
+    }
+    return cudaSuccess;
+}
+
 int prt_shoot_fan_host(const prt_env_t* env, int64_t n_rays, const double* angles, const double* y0,
                        double source_depth, double source_range, double receiver_range, double rtol, double atol,
                        int32_t terminate_backwards, int32_t n_save, const double* range_save, double* out_traj,
@@ -1083,49 +1244,53 @@ int prt_shoot_fan_host(const prt_env_t* env, int64_t n_rays, const double* angle
 {
     if (!env) return fail(PRT_ERR_ARG, "prt_shoot_fan_host: null environment");
     if (n_rays <= 0) return n_rays == 0 ? PRT_SUCCESS : fail(PRT_ERR_ARG, "prt_shoot_fan_host: n_rays < 0");
+    if (!angles && !y0) return fail(PRT_ERR_ARG, "prt_shoot_fan_host: need angles or y0");
+    if (!out_final || !out_n_bottom || !out_n_surface || !out_status)
+        return fail(PRT_ERR_ARG, "prt_shoot_fan_host: null output pointer");
+    if (env->device < 0 || env->device >= 64) return fail(PRT_ERR_ARG, "prt_shoot_fan_host: device index out of range");
     PRT_ON_DEVICE(env->device);
     const bool save = n_save > 0 && out_traj && range_save;
+    const bool flips = save && out_p_sign_changes;
     const size_t n = (size_t)n_rays;
-    // one scratch allocation: inputs | outputs
-    size_t o_in = 0, in_bytes = (y0 ? 3 * n : n) * sizeof(double);
-    size_t o_rs = prt_align256(o_in + in_bytes);
-    size_t o_final = prt_align256(o_rs + (save ? (size_t)n_save * sizeof(double) : 0));
-    size_t o_nb = prt_align256(o_final + 3 * n * sizeof(double));
-    size_t o_ns = prt_align256(o_nb + n * sizeof(int32_t));
-    size_t o_st = prt_align256(o_ns + n * sizeof(int32_t));
-    size_t o_cnt = prt_align256(o_st + n * sizeof(int32_t));
-    size_t o_flip = prt_align256(o_cnt + (out_counters ? PRT_CNT_N * n * sizeof(uint32_t) : 0));
-    size_t o_traj = prt_align256(o_flip + n * sizeof(int32_t));
-    size_t total = o_traj + (save ? 3 * n * (size_t)n_save * sizeof(double) : 0);
-    unsigned char* d = nullptr;
-    PRT_CUDA(cudaMalloc(&d, total));
-    int rc = PRT_SUCCESS;
-    cudaError_t e = cudaMemcpy(d + o_in, y0 ? y0 : angles, in_bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && save) e = cudaMemcpy(d + o_rs, range_save, (size_t)n_save * sizeof(double), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        rc = prt_shoot_fan(env, n_rays, y0 ? nullptr : (const double*)(d + o_in), y0 ? (const double*)(d + o_in) : nullptr,
-                           source_depth, source_range, receiver_range, rtol, atol, terminate_backwards,
-                           save ? n_save : 0, save ? (const double*)(d + o_rs) : nullptr,
-                           save ? (double*)(d + o_traj) : nullptr, (double*)(d + o_final), (int32_t*)(d + o_nb),
-                           (int32_t*)(d + o_ns), (int32_t*)(d + o_st), out_counters ? (uint32_t*)(d + o_cnt) : nullptr,
-                           stored_convention, (save && out_p_sign_changes) ? (int32_t*)(d + o_flip) : nullptr,
-                           max_bounces, nullptr);
-        if (rc == PRT_SUCCESS) {
-            e = cudaMemcpy(out_final, d + o_final, 3 * n * sizeof(double), cudaMemcpyDeviceToHost);
-            if (e == cudaSuccess) e = cudaMemcpy(out_n_bottom, d + o_nb, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
-            if (e == cudaSuccess) e = cudaMemcpy(out_n_surface, d + o_ns, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
-            if (e == cudaSuccess) e = cudaMemcpy(out_status, d + o_st, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
-            if (e == cudaSuccess && out_counters)
-                e = cudaMemcpy(out_counters, d + o_cnt, PRT_CNT_N * n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
-            if (e == cudaSuccess && save && out_p_sign_changes)
-                e = cudaMemcpy(out_p_sign_changes, d + o_flip, n * sizeof(int32_t), cudaMemcpyDeviceToHost);
-            if (e == cudaSuccess && save)
-                e = cudaMemcpy(out_traj, d + o_traj, 3 * n * (size_t)n_save * sizeof(double), cudaMemcpyDeviceToHost);
-        }
-    }
-    cudaFree(d);
+    // staged block (identical layout on the device and in page-locked host memory): inputs | small outputs
+    const size_t in_bytes = (y0 ? 3 * n : n) * sizeof(double);
+    const size_t o_rs = prt_align256(in_bytes);
+    const size_t o_final = prt_align256(o_rs + (save ? (size_t)n_save * sizeof(double) : 0));
+    const size_t o_nb = prt_align256(o_final + 3 * n * sizeof(double));
+    const size_t o_ns = prt_align256(o_nb + n * sizeof(int32_t));
+    const size_t o_st = prt_align256(o_ns + n * sizeof(int32_t));
+    const size_t o_cnt = prt_align256(o_st + n * sizeof(int32_t));
+    const size_t o_flip = prt_align256(o_cnt + (out_counters ? PRT_CNT_N * n * sizeof(uint32_t) : 0));
+    const size_t staged = prt_align256(o_flip + (flips ? n * sizeof(int32_t) : 0));
+    const size_t total = staged + (save ? 3 * n * (size_t)n_save * sizeof(double) : 0);
+    prt_host_scratch& S = g_host_scratch[env->device];
+    std::lock_guard<std::mutex> hold(S.lock);
+    cudaError_t e = host_scratch_reserve(S, total, staged);
+    if (e != cudaSuccess) return fail(PRT_ERR_CUDA, std::string("prt_shoot_fan_host: scratch: ") + cudaGetErrorString(e));
+    unsigned char *d = S.dev, *h = S.pin;
+    memcpy(h, y0 ? y0 : angles, in_bytes);
+    if (save) memcpy(h + o_rs, range_save, (size_t)n_save * sizeof(double));
+    cudaStream_t s = nullptr;  // legacy default stream
+    e = cudaMemcpyAsync(d, h, o_final, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return fail(PRT_ERR_CUDA, std::string("prt_shoot_fan_host: H2D: ") + cudaGetErrorString(e));
+    int rc = prt_shoot_fan(env, n_rays, y0 ? nullptr : (const double*)d, y0 ? (const double*)d : nullptr, source_depth,
+                           source_range, receiver_range, rtol, atol, terminate_backwards, save ? n_save : 0,
+                           save ? (const double*)(d + o_rs) : nullptr, save ? (double*)(d + staged) : nullptr,
+                           (double*)(d + o_final), (int32_t*)(d + o_nb), (int32_t*)(d + o_ns), (int32_t*)(d + o_st),
+                           out_counters ? (uint32_t*)(d + o_cnt) : nullptr, stored_convention,
+                           flips ? (int32_t*)(d + o_flip) : nullptr, max_bounces, s);
     if (rc != PRT_SUCCESS) return rc;
+    e = cudaMemcpyAsync(h + o_final, d + o_final, staged - o_final, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && save)  // the big one goes straight to the caller's (pageable) array
+        e = cudaMemcpy(out_traj, d + staged, 3 * n * (size_t)n_save * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return fail(PRT_ERR_CUDA, std::string("prt_shoot_fan_host: ") + cudaGetErrorString(e));
+    memcpy(out_final, h + o_final, 3 * n * sizeof(double));
+    memcpy(out_n_bottom, h + o_nb, n * sizeof(int32_t));
+    memcpy(out_n_surface, h + o_ns, n * sizeof(int32_t));
+    memcpy(out_status, h + o_st, n * sizeof(int32_t));
+    if (out_counters) memcpy(out_counters, h + o_cnt, PRT_CNT_N * n * sizeof(uint32_t));
+    if (flips) memcpy(out_p_sign_changes, h + o_flip, n * sizeof(int32_t));
     return PRT_SUCCESS;
 }
 
@@ -1144,14 +1309,14 @@ int prt_count_brackets(int64_t n_rays, const double* z_end_dev, int32_t n_rcv, c
                        int32_t* counts_dev, void* work_dev, void* stream)
 {
     if (n_rcv <= 0) return PRT_SUCCESS;
-    if (!z_end_dev || !receiver_depths_dev || !counts_dev || !work_dev)
-        return fail(PRT_ERR_ARG, "prt_count_brackets: null pointer");
+    if (!counts_dev) return fail(PRT_ERR_ARG, "prt_count_brackets: null pointer");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int32_t n_tiles = bracket_tiles(n_rays);
-    if (n_tiles == 0) {
+    if (n_tiles == 0) {  // fewer than two rays: no pair, no bracket (the table pointers may be null)
         PRT_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(int32_t) * (size_t)n_rcv, s));
         return PRT_SUCCESS;
     }
+    if (!z_end_dev || !receiver_depths_dev || !work_dev) return fail(PRT_ERR_ARG, "prt_count_brackets: null pointer");
     if (n_tiles > 65535) return fail(PRT_ERR_ARG, "prt_count_brackets: more than 134 million rays in one table");
     int64_t* tile_cnt = static_cast<int64_t*>(work_dev);
     prt_count_brackets_kernel<<<dim3((unsigned)n_rcv, (unsigned)n_tiles), 256, 0, s>>>(n_rays, z_end_dev,
@@ -1228,6 +1393,48 @@ int prt_eigen_table(int64_t n, int64_t n_br, const int64_t* idx_dev, const int32
     return PRT_SUCCESS;
 }
 
+int prt_flat_earth(int32_t n_env, int32_t n_r, int32_t n_z, const double* depth_dev, const double* re_dev,
+                   const double* c_dev, int32_t resample, double* out_dev, void* stream)
+{
+    if (n_env < 1 || n_r < 1 || n_z < 2) return fail(PRT_ERR_ARG, "prt_flat_earth: need n_env, n_r >= 1 and n_z >= 2");
+    if (!depth_dev || !re_dev || !c_dev || !out_dev) return fail(PRT_ERR_ARG, "prt_flat_earth: null pointer");
+    if (c_dev == out_dev && resample) return fail(PRT_ERR_ARG, "prt_flat_earth: resampling cannot run in place");
+    const int64_t n_nodes = (int64_t)n_env * n_r * n_z;
+    prt_flat_earth_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        n_nodes, n_r, n_z, depth_dev, re_dev, c_dev, resample, out_dev);
+    g_launches.fetch_add(1);
+    PRT_CUDA(cudaGetLastError());
+    return PRT_SUCCESS;
+}
+
+int64_t prt_iw_workspace_bytes(int32_t n_env, int32_t n_r, int32_t J)
+{
+    if (n_env < 0 || n_r < 0 || J < 0) return 0;
+    return (int64_t)(prt_align256(sizeof(double) * (size_t)n_env * (size_t)J * (size_t)n_r) + prt_align256(sizeof(double) * (size_t)n_env));
+}
+
+int prt_iw_perturb(int32_t n_env, int32_t n_r, int32_t n_z, int32_t J, int32_t K, const double* r_dev,
+                   const double* vert_dev, const double* kappa_dev, const double* phases_dev, const double* c_base_dev,
+                   int32_t iax, double rms_axis, void* work_dev, double* out_dev, void* stream)
+{
+    if (n_env < 1 || n_r < 1 || n_z < 1 || J < 1 || K < 1 || iax < 0 || iax >= n_z)
+        return fail(PRT_ERR_ARG, "prt_iw_perturb: bad sizes");
+    if (!r_dev || !vert_dev || !kappa_dev || !phases_dev || !c_base_dev || !work_dev || !out_dev)
+        return fail(PRT_ERR_ARG, "prt_iw_perturb: null pointer");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    double* H = static_cast<double*>(work_dev);
+    double* scale = reinterpret_cast<double*>(static_cast<unsigned char*>(work_dev) +
+                                              prt_align256(sizeof(double) * (size_t)n_env * (size_t)J * (size_t)n_r));
+    const int64_t nH = (int64_t)n_env * J * n_r, n_nodes = (int64_t)n_env * n_r * n_z;
+    prt_iw_horizontal_kernel<<<(unsigned)((nH + 255) / 256), 256, 0, s>>>(nH, n_r, K, r_dev, kappa_dev, phases_dev, H);
+    prt_iw_scale_kernel<<<(unsigned)n_env, 256, 0, s>>>(n_r, n_z, J, iax, rms_axis, vert_dev, H, scale);
+    prt_iw_compose_kernel<<<(unsigned)((n_nodes + 255) / 256), 256, 0, s>>>(n_nodes, n_r, n_z, J, vert_dev, H, scale,
+                                                                            c_base_dev, out_dev);
+    g_launches.fetch_add(3);
+    PRT_CUDA(cudaGetLastError());
+    return PRT_SUCCESS;
+}
+
 int64_t prt_refine_workspace_bytes(int64_t n_br)
 {
     if (n_br < 0) return 0;
@@ -1241,7 +1448,7 @@ int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev
                         int32_t terminate_backwards, double ztol, int32_t max_iter, double* out_theta_dev,
                         double* out_final_dev, int32_t* out_n_bottom_dev, int32_t* out_n_surface_dev,
                         int32_t* out_status_dev, int32_t* out_shots_dev, int32_t* out_ray_status_dev, void* work_dev,
-                        int32_t max_bounces, void* stream)
+                        const int32_t* order_dev, int32_t max_bounces, void* stream)
 {
     if (!env) return fail(PRT_ERR_ARG, "prt_refine_brackets: null environment");
     if (n_br < 0 || n_br > 0x7fffffff) return fail(PRT_ERR_ARG, "prt_refine_brackets: bad n_br");
@@ -1274,7 +1481,7 @@ int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev
     P.out_theta = out_theta_dev; P.out_final = out_final_dev; P.out_nb = out_n_bottom_dev; P.out_ns = out_n_surface_dev;
     P.out_status = out_status_dev; P.out_shots = out_shots_dev; P.out_ray_status = out_ray_status_dev;
     prt_refine_init_kernel<<<(unsigned)((n_br + 255) / 256), 256, 0, s>>>(S, n_br, z1_dev, z2_dev, th1_dev, th2_dev,
-                                                                          rd_dev, P);
+                                                                          rd_dev, order_dev, P);
     g_launches.fetch_add(1);
     PRT_CUDA(cudaGetLastError());
     // Every round is launched for the first round's size: the number of brackets still active lives on the device
@@ -1296,8 +1503,10 @@ int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev
         int32_t* list_out = flip ? S.list_a : S.list_b;
         int32_t* n_in = S.counters + flip;
         int32_t* n_out = S.counters + (1 - flip);
-        if (env->view.z_cubic) prt_refine_round_kernel<true><<<grid, block, 0, s>>>(env->view, P, S, list_in, n_in);
-        else prt_refine_round_kernel<false><<<grid, block, 0, s>>>(env->view, P, S, list_in, n_in);
+        const int zm = prt_z_mode(env->view);
+        if (zm == 2) prt_refine_round_kernel<2><<<grid, block, 0, s>>>(env->view, P, S, list_in, n_in);
+        else if (zm == 1) prt_refine_round_kernel<1><<<grid, block, 0, s>>>(env->view, P, S, list_in, n_in);
+        else prt_refine_round_kernel<0><<<grid, block, 0, s>>>(env->view, P, S, list_in, n_in);
         prt_compact_count_kernel<<<n_blk, 256, 0, s>>>(S.keep, n_in, S.blk);
         prt_compact_scan_kernel<<<1, 1024, 0, s>>>(n_blk, S.blk, n_out);
         prt_compact_scatter_kernel<<<n_blk, 256, 0, s>>>(S.keep, n_in, S.blk, list_in, list_out);

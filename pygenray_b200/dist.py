@@ -214,8 +214,8 @@ def find_eigenrays_sharded(denv, table, user_thetas, receiver_depths, source_dep
     (user) convention, one per table row.
 
     Every rank compacts the table to surviving rays (``RayFan`` only holds those, eigenrays.py:62 works on them),
-    brackets it for all receivers, refines its cyclic blocks of 32 brackets and contributes their records to one
-    all-gather.  Returns ``(records, counts)``: ``records`` [n_brackets, EIGEN_WIDTH] float64 on the device, in
+    brackets it for all receivers, refines its cyclic blocks of 32 brackets (dealt in launch-angle order) and
+    contributes their records to one all-gather.  Returns ``(records, counts)``: ``records`` [n_brackets, EIGEN_WIDTH] float64 on the device, in
     (receiver, ray) order and identical on every rank, columns ``EIGEN_FIELDS`` (``k`` indexes the COMPACTED
     fan, ``status`` is PRT_EIG_*; theta, T, z, p are NaN unless converged); ``counts`` [n_rcv] brackets per
     receiver.  ``_bracket`` / ``_refine`` are test hooks (gloo runs have no GPU).
@@ -227,7 +227,9 @@ def find_eigenrays_sharded(denv, table, user_thetas, receiver_depths, source_dep
     th = torch.as_tensor(np.ascontiguousarray(user_thetas, dtype=np.float64)).to(table.device).index_select(0, keep)
     br, counts = _bracket(z_end, th, receiver_depths)
     n_br = int(br["z1"].shape[0])
-    mine = torch.from_numpy(shard_indices(n_br, rank, world).copy()).to(table.device)
+    # deal in launch-angle order: a block of 32 then holds 32 nearly identical trial rays (one warp of the refinement)
+    perm = torch.argsort(br["th1"], stable=True)
+    mine = perm.index_select(0, torch.from_numpy(shard_indices(n_br, rank, world).copy()).to(table.device))
     local = {k: v.index_select(0, mine).contiguous() for k, v in br.items()}
     ref = _refine(denv, local, source_depth, source_range, receiver_range, rtol=rtol,
                   terminate_backwards=terminate_backwards, ztol=ztol, max_iter=max_iter)
@@ -240,7 +242,10 @@ def find_eigenrays_sharded(denv, table, user_thetas, receiver_depths, source_dep
     rec[:, 7] = ref["n_surface"]
     rec[:, 8] = ref["status"]
     rec[:, 9] = ref["shots"]
-    return all_gather_rows(rec, n_br, rank, world, group=group), counts
+    gathered = all_gather_rows(rec, n_br, rank, world, group=group)  # rows in launch-angle order
+    out = torch.empty_like(gathered)
+    out[perm] = gathered
+    return out, counts
 
 
 # ---------------------------------------------------------------------------------------------

@@ -71,8 +71,11 @@ def find_brackets(z_end, thetas, receiver_depths, device=None):
 
 
 def refine_brackets(denv, br, source_depth, source_range, receiver_range, rtol=1e-9, terminate_backwards=True,
-                    ztol=1.0, max_iter=20, max_bounces=_lib.DEFAULT_MAX_BOUNCES):
-    """Regula-falsi refinement of the brackets ``br`` (CUDA tensors from :func:`find_brackets`)."""
+                    ztol=1.0, max_iter=20, max_bounces=_lib.DEFAULT_MAX_BOUNCES, angle_order=True):
+    """Regula-falsi refinement of the brackets ``br`` (CUDA tensors from :func:`find_brackets`).
+
+    ``angle_order``: lay the brackets out over warps sorted by launch angle (an argsort of ``th1``: plumbing) so
+    that a warp holds 32 nearly identical trial rays; results are per bracket and do not depend on it."""
     L = _lib.require_gpu()
     import torch  # noqa: PLC0415
 
@@ -86,12 +89,13 @@ def refine_brackets(denv, br, source_depth, source_range, receiver_range, rtol=1
                    ray_status=torch.empty(n, **i32))
         if n:
             work = torch.empty(int(L.prt_refine_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+            order = torch.argsort(br["th1"], stable=True).to(torch.int32) if angle_order else None
             rc = L.prt_refine_brackets(
                 denv.handle, n, _ptr(br["z1"]), _ptr(br["z2"]), _ptr(br["th1"]), _ptr(br["th2"]), _ptr(br["rd"]),
                 float(source_depth), float(source_range), float(receiver_range), float(rtol), ATOL,
                 int(bool(terminate_backwards)), float(ztol), int(max_iter), _ptr(out["theta"]), _ptr(out["final"]),
                 _ptr(out["n_bottom"]), _ptr(out["n_surface"]), _ptr(out["status"]), _ptr(out["shots"]),
-                _ptr(out["ray_status"]), _ptr(work), int(max_bounces),
+                _ptr(out["ray_status"]), _ptr(work), _ptr(order), int(max_bounces),
                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
             _lib.check(rc, "prt_refine_brackets")
     return out

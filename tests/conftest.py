@@ -71,9 +71,10 @@ class HostHarness:
         h = self.lib.hh_env_create(len(e.rin), len(e.zin), e.rin.ctypes.data, e.zin.ctypes.data, e.cin.ctypes.data,
                                    e.cpin.ctypes.data, len(e.depths), e.depth_ranges.ctypes.data,
                                    e.depths.ctypes.data, len(e.ba_x), e.ba_x.ctypes.data, e.ba_c.ctypes.data)
-        out = (C.c_int * 2)()
+        out = (C.c_int * 3)()
         self.lib.hh_env_flags(h, out)
         self.lib.hh_env_destroy(h)
+        self.last_z_uniform = int(out[2])  # exactly uniform depth grid: cell edges computed instead of loaded
         return int(out[0]), int(out[1])
 
     def shoot_fan(self, oenv, source_depth, source_range, receiver_range, angles, range_save=None, rtol=1e-9,

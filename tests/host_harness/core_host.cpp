@@ -41,12 +41,13 @@ __attribute__((visibility("default"))) void hh_gradient(const double* z, int n, 
     }
 }
 
-// staging-time decisions about the cell guess: out = {z_cubic, spec_off}
+// staging-time decisions about the cell guess: out = {z_cubic, spec_off, z_uniform}
 __attribute__((visibility("default"))) void hh_env_flags(void* e, int* out)
 {
     const prt_env_view& V = static_cast<hh_env*>(e)->view;
     out[0] = V.z_cubic;
     out[1] = V.spec_off;
+    out[2] = V.z_uniform;
 }
 
 // same output layout as prt_shoot_fan: traj [3][n_rays][n_save], final [3][n_rays], counters [6][n_rays]
@@ -59,7 +60,7 @@ __attribute__((visibility("default"))) int hh_shoot_fan(void* env, int64_t n_ray
                                                          int max_bounces)
 {
     const prt_env_view& V = static_cast<hh_env*>(env)->view;
-    const prt_envp E{V, V.grid, V.z_cubic != 0};
+    const prt_envp E{V, V.grid, prt_z_mode(V)};
     for (int64_t i = 0; i < n_rays; ++i) {
         double T, z, p;
         if (y0s) {

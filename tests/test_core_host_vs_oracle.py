@@ -100,6 +100,26 @@ def test_cell_guess_rating(harness):
     assert harness.env_flags(oracle_env_from(make_env(a), False))[1] == 1
 
 
+def test_exactly_uniform_depth_grid_computes_its_cell_edges(harness):
+    """np.arange / np.linspace grids with a representable step (config 3: 5 m; the reference's default 1 m grid before
+    flat-earth) are detected at staging time: the trial step computes {zin[j], 1/dz} instead of loading them -- same
+    bits as the table, hence the same results as the oracle; a linspace with an inexact step keeps the table."""
+    a3 = cases.config2_arrays(n_r=41, n_z=1201, R=2e5)
+    a3["z"] = np.linspace(0, 6000, 1201)
+    a3["c"] = np.array([cases.munk_ssp(a3["z"], 1300.0 - 1e-3 * r) for r in a3["r"]])
+    oenv = oracle_env_from(make_env(a3), False)
+    assert harness.env_flags(oenv) == (0, 0) and harness.last_z_uniform == 1
+    o, h = _both(harness, oenv, 1000.0, 0.0, 2e5, np.linspace(-16, 16, 65), 80)
+    assert_same_fan(o, h, "exactly uniform depth grid")
+    assert (o["n_bottom"] + o["n_surface"]).sum() > 0
+    harness.env_flags(oracle_env_from(make_env(cases.config2_arrays()), False))
+    assert harness.last_z_uniform == 0  # linspace(0, 5500, 500): the reciprocals of the cell widths differ by rounding
+    harness.env_flags(oracle_env_from(make_env(cases.config1_arrays(), flat=False), False))
+    assert harness.last_z_uniform == 1  # np.arange(0, 6000, 1)
+    harness.env_flags(oracle_env_from(make_env(cases.config1_arrays(), flat=True), True))
+    assert harness.last_z_uniform == 0  # flat-earth stretching: refined guess + table
+
+
 def test_depth_derivative_tables_equal_numpy_gradient(harness):
     """The device-side staging of GPU-resident sound-speed grids (prt_ensemble_create_dev) forms dc/dz from
     coefficient tables; they must reproduce np.gradient(c, z, edge_order=1) -- what _unpack_envi hands to the

@@ -439,10 +439,12 @@ def test_config4_brackets_and_refinement_on_the_full_fan(pr, cfg3_fan):
         assert np.array_equal(ref["n_bottom"].cpu().numpy(), o["n_bottom"]), ztol
         conv = o["status"] == 0
         assert (np.abs(-o["final"][conv, 1] + host["rd"][conv]) < ztol).all()
+        # through 1000 km of internal waves the arrival depth is a chaotic function of the launch angle: regula
+        # falsi converges on a few per cent of the brackets at 1 m and on almost none at 1 mm (oracle and GPU alike)
         if ztol == 1.0:
-            assert conv.mean() > 0.5
+            assert 0.02 < conv.mean() < 0.5
         else:
-            assert (o["status"] == 2).mean() > 0.5  # most brackets cannot reach a millimetre through 1000 km
+            assert (o["status"] == 2).mean() > 0.9 and (o["shots"][o["status"] == 2] == 22).all()
 
 
 def test_bracket_fill_edge_cases(pr):
@@ -542,3 +544,109 @@ def test_find_eigenrays_when_nothing_converges(pr):
     assert er.num_eigenrays_found[0] == 0 and er.num_eigenrays[1500.0] > 0
     assert er.ts[0].shape == (0, 11) and er.received_angles[0].shape == (0,)
     assert len(er.failed_eray_theta_brackets[0]) == er.num_eigenrays[1500.0]
+
+
+# ---- earth flattening on the device (environment.py:121-173, 239-401) -----------------------------------------------
+def _flat_earth_c_numpy(c, depth, lat):
+    """flat_earth_c restated: per range column eflat with its own latitude, then xarray's linear interp back onto the
+    original depth grid (scipy interp1d, bounds_error=False -> NaN outside)."""
+    from scipy.interpolate import interp1d
+
+    out = np.empty_like(c)
+    for r in range(c.shape[0]):
+        depf, cf = __import__("pygenray_b200").eflat(depth, lat[r], c[r])
+        out[r] = interp1d(depf, cf, kind="linear", bounds_error=False)(depth)
+    return out
+
+
+def test_flat_earth_c_and_transform_rd(pr):
+    import torch
+    from pygenray_b200.environment import flat_earth_c, flat_earth_device
+
+    a = cases.config2_arrays(n_r=37, n_z=301)
+    lat = np.linspace(20.0, 47.0, 37)
+    c = pr.DataArray(a["c"].T, dims=["depth", "range"], coords={"depth": a["z"], "range": a["r"], "lat": lat})
+    out = flat_earth_c(c, verbose=False, n_cpus=3)
+    assert out.dims == ("range", "depth") and np.array_equal(out.coords["lat"].values, lat)
+    exp = _flat_earth_c_numpy(a["c"], a["z"], lat)
+    assert np.array_equal(np.isnan(out.values), np.isnan(exp))
+    np.testing.assert_allclose(out.values, exp, rtol=1e-13, atol=0, equal_nan=True)
+    assert np.abs(out.values - a["c"]).max() > 0.1  # the transform does something (c_f - c ~ c z / R_e)
+    # irregular, non-zero-based depth grid: generic interval search, NaN above the first flattened node
+    z = np.sort(np.concatenate(([5.0, 5400.0], np.random.default_rng(2).uniform(5.0, 5400.0, 120))))
+    c2 = np.array([cases.munk_ssp(z, 1300.0 + 10 * i) for i in range(9)])
+    o2 = flat_earth_device(torch.from_numpy(c2).cuda(), z, np.linspace(-70, 70, 9), resample=True).cpu().numpy()
+    e2 = _flat_earth_c_numpy(c2, z, np.linspace(-70, 70, 9))
+    assert np.isnan(e2[:, 0]).all() and np.array_equal(np.isnan(o2), np.isnan(e2))
+    np.testing.assert_allclose(o2, e2, rtol=1e-13, atol=0, equal_nan=True)
+    # environment method: attributes as the reference sets them (bathymetry copied, dcdz on the flattened field)
+    ssp = pr.DataArray(a["c"], dims=["range", "depth"], coords={"range": a["r"], "depth": a["z"], "lat": lat})
+    bathy = pr.DataArray(a["bathy"], dims=["range"], coords={"range": a["bathy_r"]})
+    env = pr.OceanEnvironment2D(sound_speed=ssp, bathymetry=bathy, flat_earth_transform=False)
+    env.flat_earth_transform_rd()
+    np.testing.assert_allclose(env.sound_speed_fe.values, exp, rtol=1e-13, equal_nan=True)
+    assert np.array_equal(env.bathymetry_fe.values, a["bathy"])
+    assert np.array_equal(env.dcdz.values, np.gradient(env.sound_speed_fe.values, a["z"], axis=1))
+    fan = pr.shoot_rays(1000.0, 0.0, np.linspace(-8, 8, 9), 100e3, 21, env, debug=False, flatearth=True)
+    assert len(fan) == 9
+    # single-latitude transform of an ensemble on the device == OceanEnvironment2D.flat_earth_transform per member
+    stack = np.stack([cases.config5_realisation(i)["c"] for i in range(3)])
+    dev = flat_earth_device(torch.from_numpy(stack).cuda(), cases.config2_arrays()["z"], 35.0, resample=False).cpu().numpy()
+    for i in range(3):
+        e = make_env(dict(cases.config2_arrays(), c=stack[i]), flat=True, lat=35)
+        assert np.array_equal(dev[i], e.sound_speed_fe.values)
+
+
+# ---- tomography-ensemble driver (SURVEY.md section 8f rank 3) --------------------------------------------------------
+def test_iw_realisations_generated_on_device(pr):
+    """prt_iw_perturb == the numpy definition of the config-5 realisations (workloads.config5_realisation) to rounding
+    (device cos and a different summation order: not bit-identical, 1e-11 m/s), and the ensemble staged from it shoots
+    the same fans as the host-generated one to well below the integration tolerance."""
+    from pygenray_b200 import ensemble as ens
+
+    a = cases.config2_arrays()
+    seeds = [1000 + i for i in range(5)]
+    dev = ens.iw_realisations_device(a["c"], a["r"], a["z"], ens.iw_phases(seeds, J=8, K=8))
+    host = np.stack([cases.config5_realisation(i)["c"] for i in range(5)])
+    assert dev.shape == host.shape and np.abs(dev.cpu().numpy() - host).max() < 1e-11
+    iax = np.argmin(np.abs(a["z"] - 1300.0))
+    rms = np.sqrt(np.mean((dev.cpu().numpy()[:, :, iax] - a["c"][None, :, iax]) ** 2, axis=1))
+    assert np.abs(rms - 0.5).max() < 1e-12
+    env = make_env(a)
+    arrs = pr._unpack_envi(env, flatearth=False)
+    dens = pr.DeviceEnsemble.from_device(dev, *arrs[2:])
+    ang = np.linspace(-8, 8, 33)
+    g = pr.shoot_ensemble_arrays(dens, 1000.0, 0.0, 100e3, ang)
+    for i in range(5):
+        o = _oracle_fan(make_env(cases.config5_realisation(i)), False, 1000.0, 0.0, 100e3, ang, 0)
+        assert np.array_equal(g["status"][i], o["status"])
+        assert np.abs(g["final"][0, i] - o["final"][:, 0]).max() < 1e-9 and np.abs(g["final"][1, i] - o["final"][:, 1]).max() < 1e-4
+
+
+def test_travel_time_sensitivity_central_differences(pr):
+    from pygenray_b200 import ensemble as ens
+
+    a = cases.config2_arrays()
+    env = make_env(a)
+    arrs = pr._unpack_envi(env, flatearth=False)
+    r, z = a["r"], a["z"]
+    modes = np.stack([np.exp(-((z[None, :] - 1000.0) / 400.0) ** 2) * np.cos(2 * np.pi * r[:, None] / 2e5),
+                      np.exp(-z[None, :] / 1500.0) * np.ones_like(r)[:, None]])
+    ang = np.linspace(-9, 9, 41)
+    s1 = ens.travel_time_sensitivity(a["c"], modes, 1e-2, *arrs[2:], 1000.0, 0.0, 200e3, ang)
+    assert s1["dT"].shape == (2, 41) and s1["valid"].all()
+    # == explicit host-staged runs of the two perturbed environments, bit for bit
+    for m in range(2):
+        fin = []
+        for sgn in (1.0, -1.0):
+            e = make_env(dict(a, c=a["c"] + sgn * 1e-2 * modes[m]))
+            d = pr.DeviceEnvironment(*pr._unpack_envi(e, flatearth=False))
+            fin.append(pr.shoot_fan_arrays(d, 1000.0, 0.0, 200e3, angles=ang)["final"])
+        assert np.array_equal(s1["dT"][m], (fin[0][0] - fin[1][0]) / 2e-2)
+        assert np.array_equal(s1["dz"][m], (fin[0][1] - fin[1][1]) / 2e-2)
+    # a uniform speed-up shortens every travel time: dT/dalpha ~ -integral(mode / c^2) ds < 0, of the expected size
+    assert (s1["dT"][1] < 0).all() and np.abs(s1["dT"][1] / (200e3 / 1500.0 ** 2) + np.exp(-1000.0 / 1500.0)).max() < 0.25
+    # second-order accuracy: halving eps changes the estimate by O(eps^2)
+    s2 = ens.travel_time_sensitivity(a["c"], modes, 5e-3, *arrs[2:], 1000.0, 0.0, 200e3, ang)
+    assert np.abs(s1["dT"] - s2["dT"]).max() < 2e-3 * np.abs(s2["dT"]).max()
+    assert np.array_equal(s1["T0"], s2["T0"])

@@ -18,6 +18,8 @@ from pygenray_b200 import _lib
 from pygenray_b200.environment import OceanEnvironment2D, eflat, munk_ssp
 from pygenray_b200.ray_objects import EigenRays, Ray, RayFan
 
+from conftest import golden
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DA = pr.DataArray
 
@@ -228,3 +230,20 @@ def test_numa_binding_is_best_effort():
     assert dist._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
     assert dist._parse_cpulist("") == set()
     assert dist.bind_to_gpu_numa(0) is None or isinstance(dist.bind_to_gpu_numa(0), int)
+
+
+def test_eflat_and_eflatinv_against_reference_values():
+    """eflat bit-identical to the reference; eflatinv (Newton on the cubic instead of the reference's Ridder search
+    to 1 mm, environment.py:404-535) within the reference's own accuracy of its output and exact against the truth."""
+    from pygenray_b200.environment import eflatinv
+
+    g = golden("ref_flatearth_jit.npz")
+    dep = g["dep"]
+    for lat in g["lats"]:
+        depf, csf = eflat(dep, lat, 1480.0 + 0.017 * dep)
+        assert np.array_equal(depf, g[f"depf_{lat}"]) and np.array_equal(csf, g[f"csf_{lat}"])
+        d, c = eflatinv(depf, lat, csf)
+        assert np.abs(d - g[f"dinv_{lat}"]).max() < 2e-3 and np.abs(c - g[f"cinv_{lat}"]).max() < 1e-6
+        assert np.abs(d - dep).max() < 1e-9 and np.abs(c - (1480.0 + 0.017 * dep)).max() < 1e-9
+    d, c = eflatinv(np.array([100.0, 2000.0]), np.array([10.0, 50.0]))
+    assert d.shape == (2,) and (c == 0).all()
