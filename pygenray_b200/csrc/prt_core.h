@@ -41,6 +41,18 @@ struct alignas(16) prt_d2 {
     double x, y;
 };
 
+// -DPRT_BOUNDS_CHECK: every table index of the lookup functions is compared with the table size and violations are
+// counted (prt_debug_oob(); compute-sanitizer is closed on the measurement pool, so the memcheck pass over the parity
+// cases is done with this build: profiles/r02_bounds_check.md).  Compiled out otherwise.
+#if defined(PRT_BOUNDS_CHECK) && defined(__CUDACC__)
+__device__ unsigned long long prt_dbg_oob_count;
+#endif
+#if defined(PRT_BOUNDS_CHECK) && defined(__CUDA_ARCH__)
+#define PRT_CHECK_IDX(idx, n) do { if (!((long long)(idx) >= 0 && (long long)(idx) < (long long)(n))) atomicAdd(&prt_dbg_oob_count, 1ULL); } while (0)
+#else
+#define PRT_CHECK_IDX(idx, n) do { } while (0)
+#endif
+
 #if defined(__CUDA_ARCH__)
 PRT_HD prt_d2 prt_ld2(const prt_d2* p)
 {
@@ -420,6 +432,7 @@ PRT_HD int prt_locate(const prt_d2* pair, int n, double x0, double inv, double v
     int g = PRT_D2I((v - x0) * inv);
     g = g < 0 ? 0 : g;
     g = g > m ? m : g;
+    PRT_CHECK_IDX(g, n - 1);
     edges = prt_ld2(pair + g);
     if ((g == 0 || edges.x < v) && (g == m || v <= edges.y)) return g;
     g += (edges.x < v) ? 1 : -1;  // failed on the upper edge -> one cell up, else one cell down
@@ -478,6 +491,8 @@ PRT_HD void prt_field(const prt_envp& E, double x, double z, double& c, double& 
     const prt_env_view& V = E.v;
     unsigned i = prt_guess(x, V.r_inv, V.r_off, V.n_r - 2);
     unsigned j = prt_guess_z(E, z);
+    PRT_CHECK_IDX(i, V.n_r - 1);
+    PRT_CHECK_IDX(j, V.n_z - 1);
     const prt_d2* rc = V.rcell + 2 * i;
     const prt_d2* zc = V.zcell + 2 * j;
     const prt_d2 rv = prt_ld2(rc), ra = prt_ld2(rc + 1);
@@ -495,6 +510,8 @@ PRT_HD void prt_field(const prt_envp& E, double x, double z, double& c, double& 
         prt_d2 re, ze;
         i = (unsigned)prt_locate(V.rpair, V.n_r, V.r0, V.r_inv, x, re);
         j = (unsigned)prt_locate(V.zpair, V.n_z, V.z0, V.z_inv, z, ze);
+        PRT_CHECK_IDX(i, V.n_r - 1);
+        PRT_CHECK_IDX(j, V.n_z - 1);
         g = E.grid + (i * (unsigned)V.n_z + j);
         v00 = prt_ld2(g);
         v01 = prt_ld2(g + 1);
@@ -535,6 +552,7 @@ PRT_HD prt_xcell prt_xlook(const prt_envp& E, double x, bool& ok)
 {
     const prt_env_view& V = E.v;
     const unsigned i = prt_guess(x, V.r_inv, V.r_off, V.n_r - 2);
+    PRT_CHECK_IDX(i, V.n_r - 1);
     const prt_d2 ra = prt_ld2(V.rxr + i);
     prt_xcell xc;
     xc.row = i * (unsigned)V.n_z;
@@ -549,6 +567,8 @@ PRT_HD void prt_field_spec(const prt_envp& E, const prt_xcell& xc, double z, dou
     const prt_env_view& V = E.v;
     const unsigned j = prt_guess_z_from(E, sg);
     const unsigned e0 = xc.row + j, e1 = e0 + (unsigned)V.n_z;
+    PRT_CHECK_IDX(j, V.n_z - 1);
+    PRT_CHECK_IDX(e1 + 1u, (long long)V.n_r * V.n_z);
     const prt_d2 *g0 = E.grid + e0, *g1 = E.grid + e1;
     prt_d2 za;
     if (E.zm == 2) {
@@ -574,6 +594,7 @@ PRT_HD double prt_bathy(const prt_envp& E, double x)
 {
     const prt_env_view& V = E.v;
     const unsigned g = prt_guess(x, V.b_inv, V.b_off, V.n_b - 2);
+    PRT_CHECK_IDX(g, V.n_b - 1);
     const prt_d2* bc = V.bcell + 3 * g;
     const prt_d2 e = prt_ld2(bc), a = prt_ld2(bc + 1);
     prt_d2 v = prt_ld2(bc + 2);
@@ -592,6 +613,7 @@ PRT_HD double prt_bathy_spec(const prt_envp& E, double x, bool& ok)
 {
     const prt_env_view& V = E.v;
     const unsigned g = prt_guess(x, V.b_inv, V.b_off, V.n_b - 2);
+    PRT_CHECK_IDX(g, V.n_b - 1);
     const prt_d2* bc = V.bcell + 3 * g;
     const prt_d2 a = prt_ld2(bc + 1), v = prt_ld2(bc + 2);
     const double w = (x - a.x) * a.y;
@@ -848,6 +870,7 @@ PRT_HD double prt_bottom_angle(const prt_env_view& E, double x, bool& oob)
     int i = lo - 1;
     i = i < 0 ? 0 : i;
     i = i > n - 2 ? n - 2 : i;
+    PRT_CHECK_IDX(i, n - 1);
     double s = x - prt_ld(E.ba_x + i);
     const int m = n - 1;
     double v = prt_ld(E.ba_c + i);
@@ -892,9 +915,13 @@ struct prt_traj_sink {
     double* z;
     double* p;
     int64_t stride;  // element stride between consecutive save points of one ray
+#if defined(PRT_BOUNDS_CHECK)
+    int n_save;      // bounds-check builds only
+#endif
     double sgn;      // +1: ODE convention; -1: stored convention (-z, -p) of ray_objects.py:49-52
     PRT_HD void put(int i, double vT, double vz, double vp) const
     {
+        PRT_CHECK_IDX(i, n_save);
         T[(int64_t)i * stride] = vT;
         z[(int64_t)i * stride] = vz * sgn;
         p[(int64_t)i * stride] = vp * sgn;

