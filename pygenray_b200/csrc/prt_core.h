@@ -63,16 +63,6 @@ PRT_HD prt_d2 prt_ld2(const prt_d2* p)
     return r;
 }
 PRT_HD double prt_ld(const double* p) { return __ldg(p); }
-#if defined(PRT_TEX_ROW1)
-__device__ __forceinline__ prt_d2 prt_tex2(unsigned long long tex, unsigned texel)
-{
-    const int4 t = tex1Dfetch<int4>((cudaTextureObject_t)tex, (int)texel);
-    prt_d2 r;
-    r.x = __hiloint2double(t.y, t.x);
-    r.y = __hiloint2double(t.w, t.z);
-    return r;
-}
-#endif
 #define PRT_FMA(a, b, c) __fma_rn((a), (b), (c))
 PRT_HD double prt_bits_to_double(uint64_t b) { return __longlong_as_double((long long)b); }
 PRT_HD uint64_t prt_double_to_bits(double d) { return (uint64_t)__double_as_longlong(d); }
@@ -149,9 +139,6 @@ struct prt_env_view {
     // one scattered load less per lookup, and the kernel is bound by the L1 data pipe (profiles/r02_ncu_fan.md)
     int32_t z_uniform;
     double z_dz, z_r0;
-    // the sound-speed grid(s) once more as a linear texture of 16-byte texels (0 when not created): an experiment that
-    // routes the loads of range row i + 1 through the texture pipe of L1TEX (PRT_TEX_ROW1, profiles/r02_variants.md)
-    unsigned long long grid_tex;
     int32_t spec_off;       // 1: guesses too poor on this environment (irregular grids) -> every trial step uses the exact lookup
     const prt_d2* rxr;      // [n_r-1] {rin[i], 1/(rin[i+1]-rin[i])}: all the speculative stage lookup needs per axis
     const prt_d2* zxr;      // [n_z-1] {zin[j], 1/(zin[j+1]-zin[j])}
@@ -577,12 +564,7 @@ PRT_HD void prt_field_spec(const prt_envp& E, const prt_xcell& xc, double z, dou
     } else {
         za = prt_ld2(V.zxr + j);
     }
-#if defined(__CUDA_ARCH__) && defined(PRT_TEX_ROW1)
-    const unsigned t1 = (unsigned)(E.grid - V.grid) + e1;  // texel index of node (i + 1, j) (ensembles: this ray's grid)
-    const prt_d2 v00 = prt_ld2(g0), v01 = prt_ld2(g0 + 1), v10 = prt_tex2(V.grid_tex, t1), v11 = prt_tex2(V.grid_tex, t1 + 1u);
-#else
     const prt_d2 v00 = prt_ld2(g0), v01 = prt_ld2(g0 + 1), v10 = prt_ld2(g1), v11 = prt_ld2(g1 + 1);
-#endif
     const double wy = (z - za.x) * za.y;
     ok = ok & (prt_w_proven(wy) | ((j == 0u) & prt_w_negative_finite(wy)));  // waiver: above the surface (overshoot before a reflection)
     prt_bilerp(v00, v01, v10, v11, xc.wx, wy, c, cz);

@@ -253,7 +253,6 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
     }
     if (err_r > tol_ok || err_b > tol_ok || err_z > tol_ok) v.spec_off = 1;
     // exactly uniform depth grid?  (every lower edge reproduced by one fma, every reciprocal width identical)
-    v.grid_tex = 0;
     v.z_uniform = 0;
     v.z_dz = zin[1] - zin[0];
     v.z_r0 = 1.0 / (zin[1] - zin[0]);

@@ -58,29 +58,6 @@ struct prt_device_guard {
     if (guard__.err != cudaSuccess)                                                                 \
         return fail(PRT_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(guard__.err))
 
-#if defined(PRT_TEX_ROW1)
-// the grid region of an environment as a linear texture of int4 texels (one {c, dc/dz} node each)
-static cudaError_t prt_make_grid_texture(prt_env_view& v)
-{
-    cudaResourceDesc res;
-    memset(&res, 0, sizeof res);
-    res.resType = cudaResourceTypeLinear;
-    res.res.linear.devPtr = const_cast<prt_d2*>(v.grid);
-    res.res.linear.desc = cudaCreateChannelDesc<int4>();
-    res.res.linear.sizeInBytes = sizeof(prt_d2) * (size_t)v.n_r * (size_t)v.n_z * (size_t)(v.n_env > 0 ? v.n_env : 1);
-    cudaTextureDesc td;
-    memset(&td, 0, sizeof td);
-    td.readMode = cudaReadModeElementType;
-    cudaTextureObject_t tex = 0;
-    cudaError_t e = cudaCreateTextureObject(&tex, &res, &td, nullptr);
-    v.grid_tex = (unsigned long long)tex;
-    return e;
-}
-#define PRT_MAKE_TEX(env) do { cudaError_t te__ = prt_make_grid_texture((env)->view); if (te__ != cudaSuccess) return fail(PRT_ERR_CUDA, std::string("texture: ") + cudaGetErrorString(te__)); } while (0)
-#else
-#define PRT_MAKE_TEX(env) do { } while (0)
-#endif
-
 struct prt_env {
     int device;
     void* dev_blob;
@@ -1021,7 +998,6 @@ int prt_env_create(int device, int32_t n_r, int32_t n_z, const double* rin, cons
     env->dev_blob = dev;
     env->bytes = blob.bytes.size();
     env->view = prt_env_rebase(blob.view, dev);
-    PRT_MAKE_TEX(env);
     *out = env;
     return PRT_SUCCESS;
 }
@@ -1050,7 +1026,6 @@ int prt_ensemble_create(int device, int32_t n_env, int32_t n_r, int32_t n_z, con
     env->dev_blob = dev;
     env->bytes = blob.bytes.size();
     env->view = prt_env_rebase(blob.view, dev);
-    PRT_MAKE_TEX(env);
     *out = env;
     return PRT_SUCCESS;
 }
@@ -1097,7 +1072,6 @@ int prt_ensemble_create_dev(int device, int32_t n_env, int32_t n_r, int32_t n_z,
     env->dev_blob = dev;
     env->bytes = blob.total_bytes;
     env->view = prt_env_rebase(blob.view, dev);
-    PRT_MAKE_TEX(env);
     *out = env;
     return PRT_SUCCESS;
 }
@@ -1106,7 +1080,6 @@ int prt_env_destroy(prt_env_t* env)
 {
     if (!env) return PRT_SUCCESS;
     prt_device_guard guard(env->device);
-    if (env->view.grid_tex) cudaDestroyTextureObject((cudaTextureObject_t)env->view.grid_tex);
     cudaFree(env->dev_blob);
     delete env;
     return PRT_SUCCESS;
