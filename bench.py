@@ -400,9 +400,9 @@ def run_b200(args):
                 tab, _ = pdist.shoot_fan_sharded(denv, zs, r0, r1, all_angles, rank, world)
             n_ok = 0
             if rank == 0:
+                ok_d = (tab[..., 5] == 0).sum()  # counted on the device, read back with the table
                 host_table.copy_(tab, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                n_ok = int((host_table[..., 5] == 0).sum())
+                n_ok = int(ok_d.item())          # (synchronises the stream: the table copy has landed too)
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         cnt_ok = torch.tensor([float(n_ok)], dtype=torch.float64, device=dev)
