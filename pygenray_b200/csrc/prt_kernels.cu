@@ -58,22 +58,12 @@ struct prt_device_guard {
     if (guard__.err != cudaSuccess)                                                                 \
         return fail(PRT_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(guard__.err))
 
-#define PRT_N_CURSORS 256
 struct prt_env {
     int device;
     void* dev_blob;
     size_t bytes;
     prt_env_view view;  // device pointers
-    // work-queue cursors of the fan launches on this environment (device memory, one per launch in flight, used
-    // round-robin: up to PRT_N_CURSORS launches may overlap on different streams)
-    unsigned long long* cursors = nullptr;
-    mutable std::atomic<unsigned> next_cursor{0};
 };
-
-static cudaError_t prt_env_alloc_cursors(prt_env* env)
-{
-    return cudaMalloc(&env->cursors, sizeof(unsigned long long) * PRT_N_CURSORS);
-}
 
 // ---------------------------------------------------------------------------------------------
 // K1: the fan
@@ -95,8 +85,7 @@ struct prt_fan_params {
     int32_t park_wait;
     int32_t lanes;  // rays per warp (32, 16, 8, 4, 2 or 1): small fans use partly filled warps, see pick_lanes()
     int64_t rays_per_env;  // ensembles: ray r belongs to realisation r / rays_per_env and uses angles[r % rays_per_env]
-    int32_t reorder;       // 1: chunks are handed out from both ends of the fan inwards (see prt_fan_kernel)
-    unsigned long long* cursor;  // work queue of the launch: next chunk of P.lanes rays to hand to a warp (zeroed before)
+    int32_t reorder;       // 1: second half of the blocks takes its chunks in reverse order (see prt_fan_kernel)
 };
 
 // Lanes that hit a boundary wait (at most this many step attempts of the other lanes) so that the
@@ -214,88 +203,77 @@ template <bool SAVE, int ZM, bool COUNT>
 __global__ void __launch_bounds__(SAVE ? PRT_BLOCK : PRT_BLOCK_ARR, SAVE ? PRT_MIN_BLOCKS : PRT_MIN_BLOCKS_ARR) prt_fan_kernel(const __grid_constant__ prt_env_view E0,
                                                       const __grid_constant__ prt_fan_params P)
 {
-    // Persistent warps over a work queue: the grid is at most the resident capacity of the chip, and every WARP pulls the
-    // next chunk of P.lanes rays (lanes >= P.lanes idle; the driver is warp-synchronous) from an atomic cursor as soon
-    // as its previous chunk is done.  A warp slot is never held hostage by the slowest warp of its block, an SM never
-    // idles while chunks are queued, and the end of a launch is one chunk long instead of one block long -- what
-    // matters when one fan is strong-scaled over 8 GPUs and a rank has fewer than two chunks per warp slot.
-    // Chunks are handed out from both ends of the fan inwards: the cost of a ray grows with |launch angle|
-    // (reflections), so a fan sorted by angle starts its most expensive chunks first and ends on the cheapest.  (Any
-    // order is correct -- rays are independent and results do not depend on it; unsorted fans are no worse off.)
+    // P.lanes rays per warp (lanes >= P.lanes idle); whole warps stay in the kernel: the driver is warp-synchronous
     const int lane = threadIdx.x & 31;
-    const unsigned full = 0xffffffffu;
-    const int64_t n_chunks = (P.n_rays + P.lanes - 1) / P.lanes;
-    __shared__ double park_mem[PRT_PARK_FIELDS * (SAVE ? PRT_BLOCK : PRT_BLOCK_ARR)];
-    prt_park_slot park;
-    park.base = park_mem + threadIdx.x;
+    // Blocks start roughly in index order and the cost of a ray grows with |launch angle| (reflections), so a fan
+    // sorted by angle would start its most expensive chunks LAST and end on a long, poorly filled tail.  The second
+    // half of the blocks therefore walks the fan backwards: both halves go from steep to shallow and the launch
+    // ends on the cheapest rays.  (Any order is correct; unsorted fans are no worse off than before.)
+    const unsigned nb = gridDim.x, half = nb >> 1;
+    const unsigned blk = (blockIdx.x < half || P.reorder == 0) ? blockIdx.x : nb - 1u - (blockIdx.x - half);
+    const int64_t warp = ((int64_t)blk * blockDim.x + threadIdx.x) >> 5;
+    const int64_t ray = warp * P.lanes + lane;
+    const bool live = (lane < P.lanes) && (ray < P.n_rays);
+    // ensembles: same tables, this ray's realisation of the sound-speed grid
+    const prt_d2* grid = E0.grid;
+    int64_t angle_index = ray;
+    if (P.rays_per_env > 0 && live) {
+        const int64_t env = ray / P.rays_per_env;
+        angle_index = ray - env * P.rays_per_env;
+        grid = E0.grid + env * E0.grid_stride;
+    }
+    const prt_envp E{E0, grid, ZM};
     prt_shot S;
     S.x_end = P.receiver_range; S.rtol = P.rtol; S.atol = P.atol;
     S.terminate_backwards = P.terminate_backwards; S.n_save = P.n_save; S.max_bounces = P.max_bounces;
     S.range_save = P.range_save;
-    for (;;) {
-        unsigned long long q = 0;
-        if (lane == 0) q = atomicAdd(P.cursor, 1ULL);
-        q = __shfl_sync(full, q, 0);
-        if ((int64_t)q >= n_chunks) break;
-        const int64_t chunk = P.reorder ? ((q & 1ULL) ? n_chunks - 1 - (int64_t)(q >> 1) : (int64_t)(q >> 1)) : (int64_t)q;
-        const int64_t ray = chunk * P.lanes + lane;
-        const bool live = (lane < P.lanes) && (ray < P.n_rays);
-        // ensembles: same tables, this ray's realisation of the sound-speed grid
-        const prt_d2* grid = E0.grid;
-        int64_t angle_index = ray;
-        if (P.rays_per_env > 0 && live) {
-            const int64_t env = ray / P.rays_per_env;
-            angle_index = ray - env * P.rays_per_env;
-            grid = E0.grid + env * E0.grid_stride;
+    double T = 0.0, z = 0.0, p = 0.0;
+    if (live) {
+        if (P.y0) {
+            T = P.y0[3 * ray];
+            z = P.y0[3 * ray + 1];
+            p = P.y0[3 * ray + 2];
+        } else {
+            prt_initial_state(E, P.source_depth, P.source_range, P.angles[angle_index], T, z, p);
         }
-        const prt_envp E{E0, grid, ZM};
-        double T = 0.0, z = 0.0, p = 0.0;
-        if (live) {
-            if (P.y0) {
-                T = P.y0[3 * ray];
-                z = P.y0[3 * ray + 1];
-                p = P.y0[3 * ray + 2];
-            } else {
-                prt_initial_state(E, P.source_depth, P.source_range, P.angles[angle_index], T, z, p);
-            }
-        }
-        prt_traj_sink sink;
-        sink.stride = 1;
+    }
+    prt_traj_sink sink;
+    sink.stride = 1;
 #if defined(PRT_BOUNDS_CHECK)
-        sink.n_save = P.n_save;
+    sink.n_save = P.n_save;
 #endif
-        sink.sgn = P.stored_convention ? -1.0 : 1.0;
-        sink.T = sink.z = sink.p = nullptr;
-        if (SAVE && live) {
-            const size_t plane = (size_t)P.n_rays * (size_t)P.n_save;
-            sink.T = P.out_traj + (size_t)ray * (size_t)P.n_save;
-            sink.z = sink.T + plane;
-            sink.p = sink.z + plane;
-        }
-        prt_ray<SAVE, COUNT> r;
-        r.start(T, z, p, P.source_range, S);
-        if (!live) r.phase = PRT_PH_DONE;
-        prt_integrate_warp(E, r, S, sink, P.park_wait, park);
-        if (live) {
-            prt_ray_result res;
-            uint32_t cnt[PRT_CNT_N];
-            r.result(S, sink, res, cnt);
-            if (SAVE && res.status != PRT_RAY_OK) {
-                // the reference returns None for a dropped ray; leave no half-written trajectory behind
-                for (int i = 0; i < P.n_save; ++i) sink.put(i, NAN, NAN, NAN);
-            }
-            P.out_final[ray] = res.T;
-            P.out_final[P.n_rays + ray] = res.z;
-            P.out_final[2 * P.n_rays + ray] = res.p;
-            P.out_nb[ray] = res.n_bottom;
-            P.out_ns[ray] = res.n_surface;
-            P.out_status[ray] = res.status;
-            if (COUNT) {
+    sink.sgn = P.stored_convention ? -1.0 : 1.0;
+    sink.T = sink.z = sink.p = nullptr;
+    if (SAVE && live) {
+        const size_t plane = (size_t)P.n_rays * (size_t)P.n_save;
+        sink.T = P.out_traj + (size_t)ray * (size_t)P.n_save;
+        sink.z = sink.T + plane;
+        sink.p = sink.z + plane;
+    }
+    __shared__ double park_mem[PRT_PARK_FIELDS * (SAVE ? PRT_BLOCK : PRT_BLOCK_ARR)];
+    prt_park_slot park;
+    park.base = park_mem + threadIdx.x;
+    prt_ray<SAVE, COUNT> r;
+    r.start(T, z, p, P.source_range, S);
+    if (!live) r.phase = PRT_PH_DONE;
+    prt_integrate_warp(E, r, S, sink, P.park_wait, park);
+    if (!live) return;
+    prt_ray_result res;
+    uint32_t cnt[PRT_CNT_N];
+    r.result(S, sink, res, cnt);
+    if (SAVE && res.status != PRT_RAY_OK) {
+        // the reference returns None for a dropped ray; leave no half-written trajectory behind
+        for (int i = 0; i < P.n_save; ++i) sink.put(i, NAN, NAN, NAN);
+    }
+    P.out_final[ray] = res.T;
+    P.out_final[P.n_rays + ray] = res.z;
+    P.out_final[2 * P.n_rays + ray] = res.p;
+    P.out_nb[ray] = res.n_bottom;
+    P.out_ns[ray] = res.n_surface;
+    P.out_status[ray] = res.status;
+    if (COUNT) {
 #pragma unroll
-                for (int k = 0; k < PRT_CNT_N; ++k) P.out_counters[(size_t)k * P.n_rays + ray] = cnt[k];
-            }
-        }
-        __syncwarp(full);
+        for (int k = 0; k < PRT_CNT_N; ++k) P.out_counters[(size_t)k * P.n_rays + ray] = cnt[k];
     }
 }
 
@@ -1020,11 +998,6 @@ int prt_env_create(int device, int32_t n_r, int32_t n_z, const double* rin, cons
     env->dev_blob = dev;
     env->bytes = blob.bytes.size();
     env->view = prt_env_rebase(blob.view, dev);
-    if (prt_env_alloc_cursors(env) != cudaSuccess) {
-        cudaFree(dev);
-        delete env;
-        return fail(PRT_ERR_CUDA, "cudaMalloc(work-queue cursors)");
-    }
     *out = env;
     return PRT_SUCCESS;
 }
@@ -1053,11 +1026,6 @@ int prt_ensemble_create(int device, int32_t n_env, int32_t n_r, int32_t n_z, con
     env->dev_blob = dev;
     env->bytes = blob.bytes.size();
     env->view = prt_env_rebase(blob.view, dev);
-    if (prt_env_alloc_cursors(env) != cudaSuccess) {
-        cudaFree(dev);
-        delete env;
-        return fail(PRT_ERR_CUDA, "cudaMalloc(work-queue cursors)");
-    }
     *out = env;
     return PRT_SUCCESS;
 }
@@ -1104,11 +1072,6 @@ int prt_ensemble_create_dev(int device, int32_t n_env, int32_t n_r, int32_t n_z,
     env->dev_blob = dev;
     env->bytes = blob.total_bytes;
     env->view = prt_env_rebase(blob.view, dev);
-    if (prt_env_alloc_cursors(env) != cudaSuccess) {
-        cudaFree(dev);
-        delete env;
-        return fail(PRT_ERR_CUDA, "cudaMalloc(work-queue cursors)");
-    }
     *out = env;
     return PRT_SUCCESS;
 }
@@ -1117,7 +1080,6 @@ int prt_env_destroy(prt_env_t* env)
 {
     if (!env) return PRT_SUCCESS;
     prt_device_guard guard(env->device);
-    cudaFree(env->cursors);
     cudaFree(env->dev_blob);
     delete env;
     return PRT_SUCCESS;
@@ -1170,17 +1132,9 @@ static int shoot_fan_impl(const prt_env_t* env, int64_t n_rays, int64_t rays_per
     if (P.rtol < 100.0 * PRT_EPS) P.rtol = 100.0 * PRT_EPS;  // validate_tol (scipy common.py:44-60)
     const int block = save ? PRT_BLOCK : PRT_BLOCK_ARR;
     P.lanes = pick_lanes(n_rays, env->device, (save ? PRT_MIN_BLOCKS : PRT_MIN_BLOCKS_ARR) * (block / 32));
-    const int64_t n_warps = (n_rays + P.lanes - 1) / P.lanes;  // chunks of the work queue
+    const int64_t n_warps = (n_rays + P.lanes - 1) / P.lanes;
+    const unsigned grid = (unsigned)((n_warps * 32 + block - 1) / block);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    // persistent warps: no more blocks than can be resident (every warp pulls chunks until the queue is empty)
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, env->device);
-    const int64_t resident = (int64_t)sms * (save ? PRT_MIN_BLOCKS : PRT_MIN_BLOCKS_ARR);
-    int64_t blocks = (n_warps * 32 + block - 1) / block;
-    if (blocks > resident) blocks = resident;
-    const unsigned grid = (unsigned)blocks;
-    P.cursor = env->cursors + (env->next_cursor.fetch_add(1) % PRT_N_CURSORS);
-    PRT_CUDA(cudaMemsetAsync(P.cursor, 0, sizeof(unsigned long long), s));
     const int zm = prt_z_mode(env->view);  // depth-axis variant compiled in: plain / refined guess / exactly uniform grid
     const bool cnt = out_counters_dev != nullptr;
 #define PRT_FAN_LAUNCH(SV, Z, CN) prt_fan_kernel<SV, Z, CN><<<grid, block, 0, s>>>(env->view, P)
