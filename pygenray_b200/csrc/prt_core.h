@@ -139,6 +139,8 @@ struct prt_env_view {
     // one scattered load less per lookup, and the kernel is bound by the L1 data pipe (profiles/r02_ncu_fan.md)
     int32_t z_uniform;
     double z_dz, z_r0;
+    int32_t r_uniform;  // the same for the range axis of the sound-speed grid: rin[i] == fma(i, r_dx, r0), 1/dr == r_r0
+    double r_dx, r_r0;
     int32_t spec_off;       // 1: guesses too poor on this environment (irregular grids) -> every trial step uses the exact lookup
     const prt_d2* rxr;      // [n_r-1] {rin[i], 1/(rin[i+1]-rin[i])}: all the speculative stage lookup needs per axis
     const prt_d2* zxr;      // [n_z-1] {zin[j], 1/(zin[j+1]-zin[j])}
@@ -146,7 +148,9 @@ struct prt_env_view {
     double bb_zmax, bb_zmin, bb_rmin, bb_rmax;  // zin[-1]+1e-6, zin[0]-1e-6, rin[0]-1e-6, rin[-1]+1e-6
 };
 
-PRT_HD int prt_z_mode(const prt_env_view& v) { return v.z_uniform ? 2 : (v.z_cubic ? 1 : 0); }
+// grid mode of an environment: 0 linear cell guesses + edge tables, 1 depth guess refined by the fitted quadratic,
+// 2 exactly uniform depth grid (depth-cell edges computed), 3 exactly uniform depth AND range grids (both computed)
+PRT_HD int prt_z_mode(const prt_env_view& v) { return v.z_uniform ? (v.r_uniform ? 3 : 2) : (v.z_cubic ? 1 : 0); }
 
 // One ray's environment: the shared tables plus this ray's sound-speed grid (ensembles: one grid per
 // realisation behind one set of tables).  The tables are referenced, never copied, so that on the device
@@ -154,8 +158,7 @@ PRT_HD int prt_z_mode(const prt_env_view& v) { return v.z_uniform ? 2 : (v.z_cub
 struct prt_envp {
     const prt_env_view& v;
     const prt_d2* grid;
-    int zm;   // depth-axis mode, a compile-time constant in each kernel instantiation: 0 linear cell guess, 1 guess refined
-              // by the fitted quadratic (v.z_cubic), 2 exactly uniform grid, cell edges computed (v.z_uniform)
+    int zm;   // grid mode (prt_z_mode), a compile-time constant in each kernel instantiation
 };
 
 // np.nextafter(t, +inf) (scipy rk.py:119) by integer increment of the bit pattern (select-only: it opens
@@ -540,7 +543,13 @@ PRT_HD prt_xcell prt_xlook(const prt_envp& E, double x, bool& ok)
     const prt_env_view& V = E.v;
     const unsigned i = prt_guess(x, V.r_inv, V.r_off, V.n_r - 2);
     PRT_CHECK_IDX(i, V.n_r - 1);
-    const prt_d2 ra = prt_ld2(V.rxr + i);
+    prt_d2 ra;
+    if (E.zm == 3) {
+        ra.x = PRT_FMA((double)i, V.r_dx, V.r0);
+        ra.y = V.r_r0;
+    } else {
+        ra = prt_ld2(V.rxr + i);
+    }
     prt_xcell xc;
     xc.row = i * (unsigned)V.n_z;
     xc.wx = (x - ra.x) * ra.y;
@@ -558,7 +567,7 @@ PRT_HD void prt_field_spec(const prt_envp& E, const prt_xcell& xc, double z, dou
     PRT_CHECK_IDX(e1 + 1u, (long long)V.n_r * V.n_z);
     const prt_d2 *g0 = E.grid + e0, *g1 = E.grid + e1;
     prt_d2 za;
-    if (E.zm == 2) {
+    if (E.zm >= 2) {
         za.x = PRT_FMA((double)j, V.z_dz, V.z0);
         za.y = V.z_r0;
     } else {

@@ -262,6 +262,15 @@ static inline int prt_env_pack(int n_r, int n_z, const double* rin, const double
             uniform = (fma((double)j, v.z_dz, v.z0) == zin[j]) && (1.0 / (zin[j + 1] - zin[j]) == v.z_r0);
         v.z_uniform = uniform ? 1 : 0;
     }
+    v.r_uniform = 0;
+    v.r_dx = rin[1] - rin[0];
+    v.r_r0 = 1.0 / (rin[1] - rin[0]);
+    if (v.z_uniform) {
+        bool uniform = true;
+        for (int i = 0; i < n_r - 1 && uniform; ++i)
+            uniform = (fma((double)i, v.r_dx, v.r0) == rin[i]) && (1.0 / (rin[i + 1] - rin[i]) == v.r_r0);
+        v.r_uniform = uniform ? 1 : 0;
+    }
     // ray_bounding_box_event tolerances (integration_processes.py:280-303)
     const double tol = 1e-6;
     v.bb_zmax = zin[n_z - 1] + tol;

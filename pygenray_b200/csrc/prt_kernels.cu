@@ -1139,7 +1139,7 @@ static int shoot_fan_impl(const prt_env_t* env, int64_t n_rays, int64_t rays_per
     const bool cnt = out_counters_dev != nullptr;
 #define PRT_FAN_LAUNCH(SV, Z, CN) prt_fan_kernel<SV, Z, CN><<<grid, block, 0, s>>>(env->view, P)
 #define PRT_FAN_PICK_CN(SV, Z) do { if (cnt) PRT_FAN_LAUNCH(SV, Z, true); else PRT_FAN_LAUNCH(SV, Z, false); } while (0)
-#define PRT_FAN_PICK_Z(SV) do { if (zm == 2) PRT_FAN_PICK_CN(SV, 2); else if (zm == 1) PRT_FAN_PICK_CN(SV, 1); else PRT_FAN_PICK_CN(SV, 0); } while (0)
+#define PRT_FAN_PICK_Z(SV) do { if (zm == 3) PRT_FAN_PICK_CN(SV, 3); else if (zm == 2) PRT_FAN_PICK_CN(SV, 2); else if (zm == 1) PRT_FAN_PICK_CN(SV, 1); else PRT_FAN_PICK_CN(SV, 0); } while (0)
     if (save) PRT_FAN_PICK_Z(true);
     else PRT_FAN_PICK_Z(false);
 #undef PRT_FAN_PICK_Z
@@ -1493,7 +1493,8 @@ int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev
         int32_t* n_in = S.counters + flip;
         int32_t* n_out = S.counters + (1 - flip);
         const int zm = prt_z_mode(env->view);
-        if (zm == 2) prt_refine_round_kernel<2><<<grid, block, 0, s>>>(env->view, P, S, list_in, n_in);
+        if (zm == 3) prt_refine_round_kernel<3><<<grid, block, 0, s>>>(env->view, P, S, list_in, n_in);
+        else if (zm == 2) prt_refine_round_kernel<2><<<grid, block, 0, s>>>(env->view, P, S, list_in, n_in);
         else if (zm == 1) prt_refine_round_kernel<1><<<grid, block, 0, s>>>(env->view, P, S, list_in, n_in);
         else prt_refine_round_kernel<0><<<grid, block, 0, s>>>(env->view, P, S, list_in, n_in);
         prt_compact_count_kernel<<<n_blk, 256, 0, s>>>(S.keep, n_in, S.blk);

@@ -23,6 +23,12 @@ __all__ = ["shoot_rays", "shoot_ray", "shoot_fan_arrays", "shoot_ensemble_arrays
 
 ATOL = 1e-6  # scipy.integrate.solve_ivp default, never overridden by the reference (launch_rays.py:670-679)
 
+# Host arrays returned by shoot_fan_arrays / shoot_rays are views of PAGE-LOCKED buffers (the D2H copies land in them
+# directly: an extra host pass over 240 MB of trajectories would cost more than the kernel).  A caller that keeps many
+# fans alive, or very large ones, can switch this off: the results are then copied once more into ordinary numpy
+# arrays and the pinned buffers are released with the call.
+PINNED_RESULTS = True
+
 # shoot_rays() with fewer than 70 angles negates the launch angles and then calls shoot_ray(), which
 # negates them again (launch_rays.py:64-67, 94-117, 251): user angle a is integrated with internal
 # angle +a, whereas the >= 70 branch integrates -a.  The reference's own golden fixture pins this
@@ -393,7 +399,7 @@ def shoot_fan_arrays(denv, source_depth, source_range, receiver_range, angles=No
         for k, v in dev_out.items():
             host[k].copy_(v, non_blocking=True)
         stream.synchronize()
-        out.update({k: v.numpy() for k, v in host.items()})
+        out.update({k: (v.numpy() if PINNED_RESULTS else v.numpy().copy()) for k, v in host.items()})
     return out
 
 
@@ -509,9 +515,10 @@ def _shoot_fan_pipelined(denv, source_depth, source_range, receiver_range, angle
     idx_np = idx_h.numpy()
     parts = [idx_np[lo:lo + kc] + a for (lo, kc, a) in (kept_slices[k] for k in range(n_chunks))]
     kept = np.concatenate(parts) if parts else np.zeros(0, np.int64)
-    return dict(range_save=rs_np, traj=traj_h[:, left:right].numpy(), final=final_h[:, left:right].numpy(),
-                n_bottom=i32_h[0, left:right].numpy(), n_surface=i32_h[1, left:right].numpy(),
-                status=np.zeros(right - left, dtype=np.int32), p_sign_changes=i32_h[2, left:right].numpy(), kept=kept)
+    take = (lambda t: t.numpy()) if PINNED_RESULTS else (lambda t: t.numpy().copy())
+    return dict(range_save=rs_np, traj=take(traj_h[:, left:right]), final=take(final_h[:, left:right]),
+                n_bottom=take(i32_h[0, left:right]), n_surface=take(i32_h[1, left:right]),
+                status=np.zeros(right - left, dtype=np.int32), p_sign_changes=take(i32_h[2, left:right]), kept=kept)
 
 
 _RAISING = {

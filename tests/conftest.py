@@ -94,7 +94,8 @@ class HostHarness:
         out = (C.c_int * 3)()
         self.lib.hh_env_flags(h, out)
         self.lib.hh_env_destroy(h)
-        self.last_z_uniform = int(out[2])  # exactly uniform depth grid: cell edges computed instead of loaded
+        self.last_z_uniform = int(out[2]) & 1   # exactly uniform depth grid: cell edges computed instead of loaded
+        self.last_r_uniform = int(out[2]) >> 1  # ... and exactly uniform range grid
         return int(out[0]), int(out[1])
 
     def shoot_fan(self, oenv, source_depth, source_range, receiver_range, angles, range_save=None, rtol=1e-9,

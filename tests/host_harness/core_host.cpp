@@ -47,7 +47,7 @@ __attribute__((visibility("default"))) void hh_env_flags(void* e, int* out)
     const prt_env_view& V = static_cast<hh_env*>(e)->view;
     out[0] = V.z_cubic;
     out[1] = V.spec_off;
-    out[2] = V.z_uniform;
+    out[2] = V.z_uniform + 2 * V.r_uniform;
 }
 
 // same output layout as prt_shoot_fan: traj [3][n_rays][n_save], final [3][n_rays], counters [6][n_rays]

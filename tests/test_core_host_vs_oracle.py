@@ -108,10 +108,17 @@ def test_exactly_uniform_depth_grid_computes_its_cell_edges(harness):
     a3["z"] = np.linspace(0, 6000, 1201)
     a3["c"] = np.array([cases.munk_ssp(a3["z"], 1300.0 - 1e-3 * r) for r in a3["r"]])
     oenv = oracle_env_from(make_env(a3), False)
-    assert harness.env_flags(oenv) == (0, 0) and harness.last_z_uniform == 1
+    assert harness.env_flags(oenv) == (0, 0) and harness.last_z_uniform == 1 and harness.last_r_uniform == 1  # 5 km x 5 m
     o, h = _both(harness, oenv, 1000.0, 0.0, 2e5, np.linspace(-16, 16, 65), 80)
-    assert_same_fan(o, h, "exactly uniform depth grid")
+    assert_same_fan(o, h, "exactly uniform depth and range grids")
     assert (o["n_bottom"] + o["n_surface"]).sum() > 0
+    a4 = dict(a3, r=np.linspace(0, 2e5, 44))  # range step 4651.16...: not representable -> range edges stay in the table
+    a4["c"] = np.array([cases.munk_ssp(a3["z"], 1300.0 - 1e-3 * r) for r in a4["r"]])
+    a4["bathy_r"], a4["bathy"] = a4["r"], np.interp(a4["r"], a3["bathy_r"], a3["bathy"])
+    oenv4 = oracle_env_from(make_env(a4), False)
+    assert harness.env_flags(oenv4) == (0, 0) and harness.last_z_uniform == 1 and harness.last_r_uniform == 0
+    o, h = _both(harness, oenv4, 1000.0, 0.0, 2e5, np.linspace(-16, 16, 33), 0)
+    assert_same_fan(o, h, "exactly uniform depth grid, inexact range step")
     harness.env_flags(oracle_env_from(make_env(cases.config2_arrays()), False))
     assert harness.last_z_uniform == 0  # linspace(0, 5500, 500): the reciprocals of the cell widths differ by rounding
     harness.env_flags(oracle_env_from(make_env(cases.config1_arrays(), flat=False), False))
