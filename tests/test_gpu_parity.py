@@ -684,3 +684,16 @@ def test_sharded_eigenray_search_single_rank(pr):
     assert np.array_equal(r[:, 3:6], ref["final"].cpu().numpy().T, equal_nan=True)
     assert np.array_equal(r[:, 8], ref["status"].cpu().numpy()) and np.array_equal(r[:, 9], ref["shots"].cpu().numpy())
     assert (r[:, 8] == 0).sum() > 20
+
+
+def test_single_save_point_like_the_reference(pr):
+    """num_range_save = 1: np.linspace(source, receiver, 1) = [source] and the only column holds the exact final state
+    (launch_rays.py:772-775 overwrites the last column) -- accepted like the reference, == the oracle."""
+    env = make_env(cases.config2_arrays())
+    ang = np.linspace(-12, 12, 9)
+    g = _gpu_fan(pr, env, False, 1000.0, 0.0, 80e3, ang, 1)
+    o = _oracle_fan(env, False, 1000.0, 0.0, 80e3, ang, 1)
+    assert_same_fan(o, g, "n_save = 1")
+    assert np.array_equal(g["traj"][:, :, 0], g["final"])
+    ray = pr.shoot_ray(1000.0, 0.0, -5.0, 80e3, 1, env, flatearth=False, debug=False)
+    assert ray.r.shape == (1,) and ray.r[0] == 0.0 and ray.t.shape == (1,) and ray.t[0] > 50.0

@@ -144,20 +144,22 @@ def _envelope_check(o, g, gn, k_env, what):
     # bounce counts: exact wherever the reference agrees with itself
     assert np.array_equal(o["n_bottom"][agree], g["al_n_bottom"][agree]), what
     assert np.array_equal(o["n_surface"][agree], g["al_n_surface"][agree]), what
-    env = np.abs(g["al_final"] - gn["al_final"])[agree]
-    dev = np.minimum(np.abs(o["final"] - g["al_final"]), np.abs(o["final"] - gn["al_final"]))[agree]
-    # arrival depth / time deviation of the oracle from the nearer reference variant, against the
-    # spread between the two variants (medians: single rays are chaotic)
+    # Three-way test: the oracle is a third run of a system that does not reproduce itself.  Its distance to EITHER
+    # reference variant (arrival depth and time) must be within k_env x the distance between the two variants, in
+    # the median, the 90th percentile and the maximum over the rays (k_env = 2: measured ratios 0.7-1.4)
     for comp, name in ((1, "depth"), (0, "time")):
-        assert np.median(dev[:, comp]) <= k_env * max(np.median(env[:, comp]), 1e-12), (what, name)
-        assert dev[:, comp].max() <= k_env * env[:, comp].max(), (what, name)
+        d_oj = np.abs(o["final"] - g["al_final"])[agree, comp]
+        d_on = np.abs(o["final"] - gn["al_final"])[agree, comp]
+        d_jn = np.abs(g["al_final"] - gn["al_final"])[agree, comp]
+        for stat in (np.median, lambda v: np.percentile(v, 90), np.max):
+            assert max(stat(d_oj), stat(d_on)) <= k_env * max(stat(d_jn), 1e-12), (what, name, stat(d_oj), stat(d_on), stat(d_jn))
 
 
 def test_config2_chaotic_regime_within_reference_envelope():
     g, gn = golden("ref_cfg2_sub_jit.npz"), golden("ref_cfg2_sub_nojit.npz")
     oenv = oracle_env_from(make_env(cases.config2_arrays()), False)
     o = orc.shoot_fan(oenv, 1000.0, 0.0, 500e3, angles_deg=g["al_internal_angles"], range_save=g["al_range_save"])
-    _envelope_check(o, g, gn, 5.0, "config 2 sub-sample")
+    _envelope_check(o, g, gn, 2.0, "config 2 sub-sample")
     # work per ray-km is the reference's: RHS evaluations within 2 % in total
     assert abs(o["counters"][:, 0].sum() / g["al_nfev"].sum() - 1) < 0.02
 
@@ -169,7 +171,7 @@ def test_reflections_on_fine_grid_within_reference_envelope():
     oenv = oracle_env_from(pr.OceanEnvironment2D(), True)
     o = orc.shoot_fan(oenv, 1000.0, 0.0, 100e3, angles_deg=g["al_internal_angles"], range_save=g["al_range_save"])
     assert np.array_equal(o["n_bottom"], g["al_n_bottom"]) and np.array_equal(o["n_surface"], g["al_n_surface"])
-    _envelope_check(o, g, gn, 5.0, "steep rays, 1 m grid")
+    _envelope_check(o, g, gn, 2.0, "steep rays, 1 m grid")
     free = (g["al_n_bottom"] + g["al_n_surface"]) == 0
     assert np.abs(o["traj"][free] - g["al_traj"][free])[:, 1].max() < 1e-6
 
