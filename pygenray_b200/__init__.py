@@ -13,11 +13,11 @@ from .eigenrays import eigenray_table, find_brackets, find_eigenrays, refine_bra
 from .environment import DataArray, OceanEnvironment2D, eflat, munk_ssp
 from .launch_rays import (DeviceEnsemble, DeviceEnvironment, _mirror_envi_arrays, _unpack_envi,
                           bottom_angle_ppoly, shoot_ensemble_arrays, shoot_fan_arrays, shoot_ray, shoot_rays)
-from .ray_objects import EigenRays, Ray, RayFan
+from .ray_objects import DeviceRows, EigenRays, Ray, RayFan
 
 __all__ = [
     "OceanEnvironment2D", "DataArray", "munk_ssp", "eflat", "shoot_rays", "shoot_ray", "find_eigenrays",
-    "Ray", "RayFan", "EigenRays", "shoot_fan_arrays", "shoot_ensemble_arrays", "find_brackets", "refine_brackets", "eigenray_table",
+    "Ray", "RayFan", "EigenRays", "DeviceRows", "shoot_fan_arrays", "shoot_ensemble_arrays", "find_brackets", "refine_brackets", "eigenray_table",
     "DeviceEnvironment",
     "DeviceEnsemble", "dist", "ensemble",
     "bottom_angle_ppoly", "_unpack_envi", "_mirror_envi_arrays",

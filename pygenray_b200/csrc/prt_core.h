@@ -654,6 +654,17 @@ PRT_HD void prt_rhs(const prt_envp& E, double x, double z, double p, double& dT,
     c_out = c;
 }
 
+// The same as ONE out-of-line function for the seven stages of the exact trial step (the cold path of an attempt and
+// the rebuild of a parked step): 14 inlined copies of the general lookup were a third of the kernels' 132 KB of
+// code, and the kernels stall on instruction fetch when their warps are in different phases (35 % of the stall
+// samples of the eigenray refinement, profiles/r02_ncu_final.md).  Same arithmetic, same bits.
+PRT_HD_NOINLINE void prt_rhs_cold(const prt_env_view* V, const prt_d2* grid, int zm, double x, double z, double p,
+                                  double* out4)
+{
+    const prt_envp E{*V, grid, zm};
+    prt_rhs(E, x, z, p, out4[0], out4[1], out4[2], out4[3]);
+}
+
 PRT_HD void prt_rhs_spec(const prt_envp& E, const prt_xcell& xc, double z, double p, double sg, double& dT, double& dz,
                          double& dp, double& c_out, bool& ok)
 {
@@ -979,7 +990,9 @@ PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, do
 #define PRT_STAGE(xs, zs, ps, sg, cout)                                          \
     do {                                                                         \
         if (EXACT) {                                                             \
-            prt_rhs(E, (xs), (zs), (ps), kT, kz, kp, cout);                      \
+            double o4_[4];                                                       \
+            prt_rhs_cold(&E.v, E.grid, E.zm, (xs), (zs), (ps), o4_);             \
+            kT = o4_[0]; kz = o4_[1]; kp = o4_[2]; cout = o4_[3];                \
         } else {                                                                 \
             const prt_xcell xc_ = prt_xlook(E, (xs), ok);                        \
             prt_rhs_spec(E, xc_, (zs), (ps), (sg), kT, kz, kp, cout, ok);        \
@@ -1030,8 +1043,11 @@ PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, do
     const double x6 = t + hh;
     prt_xcell xc6;
     if (!EXACT) xc6 = prt_xlook(E, x6, ok);
-    if (EXACT) prt_rhs(E, x6, PRT_FMA(hh, a6z, z), PRT_FMA(hh, a6p, p), kT, kz, kp, cc);
-    else prt_rhs_spec(E, xc6, PRT_FMA(hh, a6z, z), PRT_FMA(hh, a6p, p), sg6, kT, kz, kp, cc, ok);
+    if (EXACT) {
+        double o4[4];
+        prt_rhs_cold(&E.v, E.grid, E.zm, x6, PRT_FMA(hh, a6z, z), PRT_FMA(hh, a6p, p), o4);
+        kT = o4[0]; kz = o4[1]; kp = o4[2]; cc = o4[3];
+    } else prt_rhs_spec(E, xc6, PRT_FMA(hh, a6z, z), PRT_FMA(hh, a6p, p), sg6, kT, kz, kp, cc, ok);
     const double sg7 = PRT_GUESS(PRT_FMA(hh, PRT_FMA(B6, kz, sz), z), B6, kz, sz);
     sT = PRT_FMA(B6, kT, sT); sz = PRT_FMA(B6, kz, sz); sp = PRT_FMA(B6, kp, sp);
     eT = PRT_FMA(E6, kT, eT); ez = PRT_FMA(E6, kz, ez); ep = PRT_FMA(E6, kp, ep);
@@ -1049,8 +1065,11 @@ PRT_HD void prt_rk_try(const prt_envp& E, double rtol, double atol, double t, do
     const double sTz = scT * scz, szp = scz * scp, sTp = scT * scp;
     const double inv3 = prt_rcp(sTz * scp);
     const double iT = inv3 * szp, iz = inv3 * sTp, ip = inv3 * sTz;
-    if (EXACT) prt_rhs(E, x6, v.nz, v.np_, v.k7T, v.k7z, v.k7p, v.c_new);  // f_new (FSAL)
-    else prt_rhs_spec(E, xc6, v.nz, v.np_, sg7, v.k7T, v.k7z, v.k7p, v.c_new, ok);
+    if (EXACT) {  // f_new (FSAL)
+        double o4[4];
+        prt_rhs_cold(&E.v, E.grid, E.zm, x6, v.nz, v.np_, o4);
+        v.k7T = o4[0]; v.k7z = o4[1]; v.k7p = o4[2]; v.c_new = o4[3];
+    } else prt_rhs_spec(E, xc6, v.nz, v.np_, sg7, v.k7T, v.k7z, v.k7p, v.c_new, ok);
 #undef PRT_STAGE
 #undef PRT_GUESS
     // the event functions at the step end (ivp.py:678-699) only need y_new and c_new: formed here, they overlap
@@ -1150,8 +1169,10 @@ struct prt_ray {
     PRT_HD void seg_init(const prt_envp& E, const prt_shot& S)
     {
         if (COUNT) ++c_seg;
-        double c_here;
-        prt_rhs(E, t, z, p, f0, f1, f2, c_here);
+        double o4[4];  // out-of-line lookups: a segment starts once per reflection
+        prt_rhs_cold(&E.v, E.grid, E.zm, t, z, p, o4);
+        f0 = o4[0]; f1 = o4[1]; f2 = o4[2];
+        const double c_here = o4[3];
         g = prt_events(E, t, z, p, c_here);
         double interval = fabs(S.x_end - t);
         double s0 = PRT_FMA(fabs(T), S.rtol, S.atol), s1 = PRT_FMA(fabs(z), S.rtol, S.atol),
@@ -1160,8 +1181,8 @@ struct prt_ray {
         double d1 = prt_rms3(f0 / s0, f1 / s1, f2 / s2);
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (0.01 * d0) / d1;
         h0 = prt_py_min(h0, interval);
-        double g0, g1, g2, cc;
-        prt_rhs(E, t + h0, PRT_FMA(h0, f1, z), PRT_FMA(h0, f2, p), g0, g1, g2, cc);
+        prt_rhs_cold(&E.v, E.grid, E.zm, t + h0, PRT_FMA(h0, f1, z), PRT_FMA(h0, f2, p), o4);
+        const double g0 = o4[0], g1 = o4[1], g2 = o4[2];
         double d2 = prt_rms3((g0 - f0) / s0, (g1 - f1) / s1, (g2 - f2) / s2) / h0;
         double h1;
         if (d1 <= 1e-15 && d2 <= 1e-15) h1 = prt_py_max(1e-6, h0 * 1e-3);
@@ -1203,9 +1224,9 @@ struct prt_ray {
         prt_try v;
         bool ok = (E.v.spec_off == 0);  // irregular grids: straight to the exact lookup
         if (ok) prt_rk_try<false, SAVE>(E, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, v, ok);
-        if (!ok) {
+        if (!ok) {  // (always the DENSE instantiation: one copy of the exact trial step per kernel, the rows are cheap)
             prt_try cold;
-            prt_rk_try_exact<SAVE>(&E.v, E.grid, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, &cold);
+            prt_rk_try_exact<true>(&E.v, E.grid, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, &cold);
             v = cold;
         }
         // controller (rk.py:153-165); one power serves accepting and rejecting lanes.  ms == 0 needs no special

@@ -16,7 +16,7 @@ import numpy as np
 from scipy.interpolate import CubicSpline
 
 from . import _lib, _xr
-from .ray_objects import Ray, RayFan
+from .ray_objects import DeviceRows, Ray, RayFan
 
 __all__ = ["shoot_rays", "shoot_ray", "shoot_fan_arrays", "shoot_ensemble_arrays", "DeviceEnvironment",
            "DeviceEnsemble", "_unpack_envi", "_mirror_envi_arrays", "bottom_angle_ppoly"]
@@ -547,6 +547,8 @@ def _fan_from_device(res, stored_thetas, source_depth, backwards):
     rs = -res["range_save"] if backwards else res["range_save"]
     kept = res["kept"]
     m = traj.shape[1]
+    if not isinstance(traj, np.ndarray):  # trajectories left on the device (device_trajectories=True)
+        traj = [DeviceRows(traj[q]) for q in range(3)]
     fan = RayFan.__new__(RayFan)
     fan.thetas = np.asarray(stored_thetas, dtype=np.float64)[kept]
     # every ray shares the save grid: a read-only broadcast view (the reference materialises M writable copies;
@@ -563,11 +565,15 @@ def _fan_from_device(res, stored_thetas, source_depth, backwards):
 
 
 def shoot_rays(source_depth, source_range, launch_angles, receiver_range, num_range_save, environment,
-               rtol=1e-9, terminate_backwards=True, n_processes=None, debug=True, flatearth=True):
+               rtol=1e-9, terminate_backwards=True, n_processes=None, debug=True, flatearth=True,
+               device_trajectories=False):
     """Integrate a fan of rays; same call as ``pygenray.shoot_rays``.  Returns a :class:`RayFan`.
 
     ``n_processes`` is accepted and ignored (the fan is one GPU launch).  Dropped rays (vertical,
     left the sound-speed grid, bounced backwards, step size underflow) are absent from the fan.
+    ``device_trajectories=True`` (an extension): ``ts`` / ``zs`` / ``ps`` of the returned fan stay on the GPU as
+    :class:`DeviceRows` and are copied to the host only when indexed; everything else (angles, bounce counts, ray
+    ids) is on the host as usual.
     """
     if type(launch_angles) is list:
         launch_angles = np.array(launch_angles)
@@ -584,6 +590,12 @@ def shoot_rays(source_depth, source_range, launch_angles, receiver_range, num_ra
         internal = launch_angles
         stored = -launch_angles    # ray.launch_angle = -launch_angles[k] (launch_rays.py:180-182)
 
+    if device_trajectories and not small:
+        dres = shoot_fan_arrays(denv, source_depth, src_i, rcv_i, angles=internal, num_range_save=num_range_save,
+                                rtol=rtol, terminate_backwards=terminate_backwards, stored_convention=True,
+                                ray_id_counts=True, compact=True, to_host=False)
+        res = {k: (v if k in ("traj", "range_save") else v.cpu().numpy()) for k, v in dres.items()}
+        return _fan_from_device(res, stored, source_depth, backwards)
     if launch_angles.shape[0] >= _PIPELINE_MIN_RAYS and num_range_save:
         res = _shoot_fan_pipelined(denv, source_depth, src_i, rcv_i, internal, num_range_save, rtol,
                                    terminate_backwards)

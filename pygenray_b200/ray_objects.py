@@ -10,7 +10,68 @@ The reference's plot methods are out of scope and not prov
 import numpy as np
 from scipy import io
 
-__all__ = ["Ray", "RayFan", "EigenRays"]
+__all__ = ["Ray", "RayFan", "EigenRays", "DeviceRows"]
+
+
+class DeviceRows:
+    """A float64 ``(M, N)`` array that stays in GPU memory; indexing copies just the requested rows / columns /
+    slices to the host as numpy, ``np.asarray(x)`` fetches (and caches) everything.
+
+    ``shoot_rays(..., device_trajectories=True)`` returns a ``RayFan`` whose ``ts`` / ``zs`` / ``ps`` are of this
+    type: the 24 bytes per save point per ray -- 241 MB for a 10k-ray fan with 1001 save points, the whole
+    end-to-end cost at 8 GPUs on one host -- cross PCIe only when, and as far as, somebody looks at them
+    (``find_eigenrays`` reads one column, ``fan[i]`` one row)."""
+
+    def __init__(self, tensor):
+        self._t = tensor
+        self._host = None
+
+    shape = property(lambda self: tuple(self._t.shape))
+    ndim = property(lambda self: self._t.ndim)
+    size = property(lambda self: int(self._t.numel()))
+    dtype = property(lambda self: np.dtype(np.float64))
+    nbytes = property(lambda self: int(self._t.numel()) * 8)
+    device_tensor = property(lambda self: self._t)
+
+    def __len__(self):
+        return int(self._t.shape[0])
+
+    def __array__(self, dtype=None, copy=None):
+        if self._host is None:
+            self._host = self._t.cpu().numpy()
+        return self._host if dtype is None else self._host.astype(dtype, copy=False)
+
+    def _index(self, key):
+        import torch  # noqa: PLC0415
+
+        def conv(k):
+            if isinstance(k, np.ndarray):
+                return torch.from_numpy(np.ascontiguousarray(k)).to(self._t.device)
+            if isinstance(k, (list,)):
+                return torch.as_tensor(k, device=self._t.device)
+            if isinstance(k, (np.integer,)):
+                return int(k)
+            return k
+
+        return tuple(conv(k) for k in key) if isinstance(key, tuple) else conv(key)
+
+    def __getitem__(self, key):
+        if self._host is not None:
+            return self._host[key]
+        try:
+            out = self._t[self._index(key)]
+        except Exception:  # noqa: BLE001  (index forms torch does not take, e.g. negative steps)
+            return np.asarray(self)[key]
+        return out.cpu().numpy() if out.ndim else float(out.item())
+
+    def min(self):
+        return float(self._t.min().item())
+
+    def max(self):
+        return float(self._t.max().item())
+
+    def __repr__(self):
+        return f"DeviceRows(shape={self.shape}, device={self._t.device})"
 
 
 class Ray:

@@ -697,3 +697,27 @@ def test_single_save_point_like_the_reference(pr):
     assert np.array_equal(g["traj"][:, :, 0], g["final"])
     ray = pr.shoot_ray(1000.0, 0.0, -5.0, 80e3, 1, env, flatearth=False, debug=False)
     assert ray.r.shape == (1,) and ray.r[0] == 0.0 and ray.t.shape == (1,) and ray.t[0] > 50.0
+
+
+def test_device_trajectories_are_fetched_lazily(pr):
+    """shoot_rays(device_trajectories=True): ts/zs/ps stay on the GPU (DeviceRows); rows, columns and slices come to the
+    host on demand and equal the ordinary fan; find_eigenrays works on such a fan (it reads one column)."""
+    env = make_env(cases.config2_arrays())
+    user = np.linspace(-17, 17, 300)
+    host = pr.shoot_rays(1000.0, 0.0, user, 300e3, 41, env, debug=False, flatearth=False)
+    dev = pr.shoot_rays(1000.0, 0.0, user, 300e3, 41, env, debug=False, flatearth=False, device_trajectories=True)
+    assert isinstance(dev.zs, pr.DeviceRows) and dev.zs.shape == host.zs.shape and len(dev) == len(host) <= 300
+    assert np.array_equal(dev.thetas, host.thetas) and np.array_equal(dev.n_botts, host.n_botts)
+    assert list(dev.ray_ids) == list(host.ray_ids)
+    assert np.array_equal(dev.zs[:, -1], host.zs[:, -1]) and np.array_equal(dev.ts[7], host.ts[7])
+    assert np.array_equal(dev.ps[3:9, ::4], host.ps[3:9, ::4]) and dev.ts[5, 40] == host.ts[5, 40]
+    assert np.array_equal(dev.zs[np.array([2, 0, 11])], host.zs[[2, 0, 11]])
+    assert np.array_equal(dev.zs[::-1][0], host.zs[-1])  # an index form torch does not take: falls back to a full fetch
+    ray = dev[4]
+    assert np.array_equal(ray.z, host[4].z) and np.array_equal(ray.t, host[4].t)
+    e_h = pr.find_eigenrays(host, [1500.0], 1000.0, 0.0, 300e3, 21, env, ztol=0.5, flatearth=False, debug=False)
+    dev2 = pr.shoot_rays(1000.0, 0.0, user, 300e3, 41, env, debug=False, flatearth=False, device_trajectories=True)
+    e_d = pr.find_eigenrays(dev2, [1500.0], 1000.0, 0.0, 300e3, 21, env, ztol=0.5, flatearth=False, debug=False)
+    assert dev2.zs._host is None  # the eigenray search did not pull the trajectories
+    assert np.array_equal(e_h.launch_angles[0], e_d.launch_angles[0]) and np.array_equal(e_h.ts[0], e_d.ts[0])
+    assert np.array_equal(np.asarray(dev.zs), host.zs)

@@ -247,3 +247,20 @@ def test_eflat_and_eflatinv_against_reference_values():
         assert np.abs(d - dep).max() < 1e-9 and np.abs(c - (1480.0 + 0.017 * dep)).max() < 1e-9
     d, c = eflatinv(np.array([100.0, 2000.0]), np.array([10.0, 50.0]))
     assert d.shape == (2,) and (c == 0).all()
+
+
+def test_device_rows_indexing_semantics():
+    """DeviceRows behaves like the numpy array it stands for (exercised here on a CPU tensor)."""
+    import torch
+
+    from pygenray_b200.ray_objects import DeviceRows
+
+    a = np.arange(60, dtype=np.float64).reshape(6, 10)
+    d = DeviceRows(torch.from_numpy(a.copy()))
+    assert d.shape == (6, 10) and d.ndim == 2 and len(d) == 6 and d.dtype == np.float64 and d.nbytes == 480
+    assert np.array_equal(d[:, -1], a[:, -1]) and np.array_equal(d[2], a[2]) and d[3, 4] == a[3, 4]
+    assert np.array_equal(d[1:5, ::3], a[1:5, ::3]) and np.array_equal(d[np.array([4, 0])], a[[4, 0]])
+    assert np.array_equal(d[np.array([True, False, True, False, False, True])], a[[0, 2, 5]])
+    assert d._host is None and d.min() == 0.0 and d.max() == 59.0
+    assert np.array_equal(d[::-1], a[::-1]) and d._host is not None  # negative step: full fetch, then cached
+    assert np.array_equal(np.asarray(d), a) and np.array_equal(d[:, 0], a[:, 0])
