@@ -657,7 +657,9 @@ PRT_HD void prt_rhs(const prt_envp& E, double x, double z, double p, double& dT,
 // The same as ONE out-of-line function for the seven stages of the exact trial step (the cold path of an attempt and
 // the rebuild of a parked step): 14 inlined copies of the general lookup were a third of the kernels' 132 KB of
 // code, and the kernels stall on instruction fetch when their warps are in different phases (35 % of the stall
-// samples of the eigenray refinement, profiles/r02_ncu_final.md).  Same arithmetic, same bits.
+// samples of the eigenray refinement, profiles/r02_ncu_final.md): 92 KB now, refinement 14 % faster, fan unchanged.
+// (Going further -- segment start-up and root search through the call as well -- gains another 5 % on the refinement
+// and loses 1-9 % on the fans; measured, not shipped.)  Same arithmetic, same bits.
 PRT_HD_NOINLINE void prt_rhs_cold(const prt_env_view* V, const prt_d2* grid, int zm, double x, double z, double p,
                                   double* out4)
 {
@@ -1169,10 +1171,8 @@ struct prt_ray {
     PRT_HD void seg_init(const prt_envp& E, const prt_shot& S)
     {
         if (COUNT) ++c_seg;
-        double o4[4];  // out-of-line lookups: a segment starts once per reflection
-        prt_rhs_cold(&E.v, E.grid, E.zm, t, z, p, o4);
-        f0 = o4[0]; f1 = o4[1]; f2 = o4[2];
-        const double c_here = o4[3];
+        double c_here;
+        prt_rhs(E, t, z, p, f0, f1, f2, c_here);
         g = prt_events(E, t, z, p, c_here);
         double interval = fabs(S.x_end - t);
         double s0 = PRT_FMA(fabs(T), S.rtol, S.atol), s1 = PRT_FMA(fabs(z), S.rtol, S.atol),
@@ -1181,8 +1181,8 @@ struct prt_ray {
         double d1 = prt_rms3(f0 / s0, f1 / s1, f2 / s2);
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : (0.01 * d0) / d1;
         h0 = prt_py_min(h0, interval);
-        prt_rhs_cold(&E.v, E.grid, E.zm, t + h0, PRT_FMA(h0, f1, z), PRT_FMA(h0, f2, p), o4);
-        const double g0 = o4[0], g1 = o4[1], g2 = o4[2];
+        double g0, g1, g2, cc;
+        prt_rhs(E, t + h0, PRT_FMA(h0, f1, z), PRT_FMA(h0, f2, p), g0, g1, g2, cc);
         double d2 = prt_rms3((g0 - f0) / s0, (g1 - f1) / s1, (g2 - f2) / s2) / h0;
         double h1;
         if (d1 <= 1e-15 && d2 <= 1e-15) h1 = prt_py_max(1e-6, h0 * 1e-3);
@@ -1224,9 +1224,9 @@ struct prt_ray {
         prt_try v;
         bool ok = (E.v.spec_off == 0);  // irregular grids: straight to the exact lookup
         if (ok) prt_rk_try<false, SAVE>(E, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, v, ok);
-        if (!ok) {  // (always the DENSE instantiation: one copy of the exact trial step per kernel, the rows are cheap)
+        if (!ok) {
             prt_try cold;
-            prt_rk_try_exact<true>(&E.v, E.grid, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, &cold);
+            prt_rk_try_exact<SAVE>(&E.v, E.grid, S.rtol, S.atol, t, hh, T, z, p, f0, f1, f2, &cold);
             v = cold;
         }
         // controller (rk.py:153-165); one power serves accepting and rejecting lanes.  ms == 0 needs no special
