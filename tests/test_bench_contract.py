@@ -1,0 +1,49 @@
+"""bench.py on a machine without a GPU: the reference arm (`--impl reference`) runs here, and its JSON line must carry
+the keys of the driver contract with the same `config` object the GPU arm prints."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_the_contract_line():
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg2",
+                        "--steps", "1", "--warmup", "1", "--ref-rays", "64", "--no-python-ref"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "ray_km_per_s" and d["unit"] == "ray-km/s" and d["dtype"] == "f64"
+    assert d["value"] > 1e4 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "64 rays" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "ray-km/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_both_arms_share_one_config_object_and_workload_definition():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    for name, n_total, scaling in (("cfg3", 1 << 20, "strong"), ("cfg2", 10000, "weak")):
+        w = bench.workload(name, 0, 1)
+        c = bench.config_block(w, 1)
+        assert c["rays_total"] == n_total and c["scaling"] == scaling and c["workload"].startswith(name)
+        assert len(w["angles"]) == n_total and np.array_equal(w["angles"], w["all_angles"])
+        sub = bench.sample_angles(w, 64)
+        assert len(sub) == 64 and sub[0] == w["all_angles"][0] and sub[-1] == w["all_angles"][-1]
+    # strong scaling: the ranks' shares partition ONE fan; weak scaling: the fan grows with the ranks
+    shares = [bench.workload("cfg3", r, 4)["angles"] for r in range(4)]
+    assert sum(len(s) for s in shares) == 1 << 20 and np.array_equal(np.sort(np.concatenate(shares)), bench.workload("cfg3")["all_angles"])
+    weak = [bench.workload("cfg2", r, 4) for r in range(4)]
+    assert weak[1]["n_total"] == 40000 and sum(len(w["angles"]) for w in weak) == 40000
+    assert all(abs(len(w["angles"]) - 10000) <= 32 for w in weak)  # cyclic blocks of 32 angles
+    flops = bench.algorithmic_flops(np.array([[10], [2], [1], [1], [4], [1]], dtype=np.uint32))
+    assert flops == 38 * 10 + 200 * 2 + 40 * 1 + 168 * 1 + 60 * 4
