@@ -11,8 +11,11 @@
  *   _interpolate_ray(sols, range_save)                   :745-784   > prt_shoot_fan (batched over
  *   Pool.imap(_shoot_single_ray_process, y0s)            :157-164  /   launch angles)
  *   find_eigenrays / _find_single_eigenray               eigenrays.py:62-120, 206-268
- *                                                                  -> prt_find_brackets,
+ *                                                                  -> prt_count_brackets + prt_fill_brackets,
  *                                                                     prt_refine_brackets
+ *   EigenRays.__init__ (received angles, ray ids)         ray_objects.py:505-548 -> prt_eigen_table,
+ *                                                                     prt_received_angles
+ *   eflat / flat_earth_transform / flat_earth_c           environment.py:121-173, 239-401 -> prt_flat_earth
  *
  * Conventions
  *   - plain C types only; every array is a raw pointer + explicit sizes; FP64 everywhere.
