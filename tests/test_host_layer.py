@@ -264,3 +264,17 @@ def test_device_rows_indexing_semantics():
     assert d._host is None and d.min() == 0.0 and d.max() == 59.0
     assert np.array_equal(d[::-1], a[::-1]) and d._host is not None  # negative step: full fetch, then cached
     assert np.array_equal(np.asarray(d), a) and np.array_equal(d[:, 0], a[:, 0])
+
+
+def test_header_is_plain_c_and_library_links_from_c(tmp_path):
+    """include/prt.h compiles as C99 with -Wall -Werror and a C program links against libprt.so (the drop-in boundary
+    is a C ABI: plain pointers and sizes, no C++ or torch types)."""
+    exe = str(tmp_path / "abi_check")
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "host_harness", "abi_check.c"), "-o", exe, "-L", lib_dir, "-l:libprt.so",
+           "-Wl,-rpath," + lib_dir]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0, (p.returncode, p.stdout, p.stderr)
+    assert p.stdout.startswith("abi 2 ok")
