@@ -121,6 +121,8 @@ def all_gather_rows(local_rows, n_total, rank, world, block=BLOCK, group=None):
 
     if local_rows.ndim != 2:
         raise ValueError("all_gather_rows: local_rows must be [n_local, width]")
+    if n_total == 0:  # nothing to exchange (e.g. a fan without any eigenray bracket): the same on every rank, no collective
+        return local_rows[:0]
     if world == 1:
         if local_rows.shape[0] != n_total:
             raise ValueError(f"all_gather_rows: {local_rows.shape[0]} local rows for {n_total} in total at world size 1")

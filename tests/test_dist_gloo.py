@@ -180,3 +180,4 @@ def test_sharded_calls_reject_bad_arguments():
         pdist.all_gather_rows(torch.zeros((3, 6), dtype=torch.float64), 4, 0, 1)
     with pytest.raises(ValueError):
         pdist.all_gather_arrivals(torch.zeros((4, 5), dtype=torch.float64), 4, 0, 1)
+    assert pdist.all_gather_rows(torch.zeros((0, 10), dtype=torch.float64), 0, 1, 4).shape == (0, 10)  # no collective
