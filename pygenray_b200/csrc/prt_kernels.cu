@@ -91,6 +91,21 @@ struct prt_fan_params {
 // Lanes that hit a boundary wait (at most this many step attempts of the other lanes) so that the
 // event root searches of a warp run together; tunable for experiments via PRT_PARK_WAIT.
 static int g_park_wait = -1;
+// The eigenray refinement waits longer (PRT_PARK_WAIT_REFINE, default 128): its trial rays are mostly steep, multiply
+// reflecting ones, and a root-search pass costs a warp about three step attempts whether one lane or twenty take part,
+// so batching more lanes per pass pays -- measured on config 4 (816 408 brackets, 22 rounds): 16 -> 3.70 s, 32 -> 3.10,
+// 64 -> 3.03, 128 -> 2.89, 256 -> 3.05 s; the fans prefer 16 (10k-ray config 2: 4.85 ms against 5.27-5.67 at 64-128;
+// 1M-ray fans within 2 % either way; profiles/r02_variants.md).  Interleaving only: results do not depend on it.
+static int park_wait_refine_setting()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PRT_PARK_WAIT_REFINE");
+        v = e ? atoi(e) : 128;
+        if (v < 0) v = 0;
+    }
+    return v;
+}
 static int park_wait_setting()
 {
     if (g_park_wait < 0) {
@@ -1465,7 +1480,7 @@ int prt_refine_brackets(const prt_env_t* env, int64_t n_br, const double* z1_dev
     P.receiver_range = receiver_range; P.rtol = rtol; P.atol = atol; P.ztol = ztol;
     P.terminate_backwards = terminate_backwards; P.max_iter = max_iter;
     P.max_bounces = max_bounces > 0 ? max_bounces : (1 << 20);
-    P.park_wait = park_wait_setting();
+    P.park_wait = park_wait_refine_setting();
     if (P.rtol < 100.0 * PRT_EPS) P.rtol = 100.0 * PRT_EPS;
     P.out_theta = out_theta_dev; P.out_final = out_final_dev; P.out_nb = out_n_bottom_dev; P.out_ns = out_n_surface_dev;
     P.out_status = out_status_dev; P.out_shots = out_shots_dev; P.out_ray_status = out_ray_status_dev;
