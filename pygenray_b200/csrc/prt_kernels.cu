@@ -82,7 +82,7 @@ struct prt_fan_params {
     uint32_t* out_counters;
     int32_t max_bounces;
     int32_t stored_convention;
-    int32_t park_wait;
+    int32_t park_wait, park_wait_long;
     int32_t lanes;  // rays per warp (32, 16, 8, 4, 2 or 1): small fans use partly filled warps, see pick_lanes()
     int64_t rays_per_env;  // ensembles: ray r belongs to realisation r / rays_per_env and uses angles[r % rays_per_env]
     int32_t reorder;       // 1: second half of the blocks takes its chunks in reverse order (see prt_fan_kernel)
@@ -157,13 +157,16 @@ struct prt_park_slot {
 //     root search, the reflection and the next segment's start-up run once for all parked lanes, when
 //     no lane is left stepping or the oldest parked lane has waited `park_wait` iterations
 //     (neighbouring launch angles reach a boundary within a few steps of each other).
+//   * the wait adapts: after a pass in which at least half of the lanes still in play took part (a warp of steep rays
+//     that reflect together) the next wait is `park_wait_long`, otherwise `park_wait` (mixed warps, where parked lanes
+//     would idle while their neighbours step on)
 template <bool SAVE, bool COUNT>
 __device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SAVE, COUNT>& r, const prt_shot& S,
-                                                   const prt_traj_sink& sink, int park_wait,
+                                                   const prt_traj_sink& sink, int park_wait, int park_wait_long,
                                                    const prt_park_slot& park)
 {
     const unsigned full = 0xffffffffu;
-    int waited = 0;
+    int waited = 0, limit = park_wait;
     for (;;) {
         if (r.phase == PRT_PH_INIT) r.seg_init(E, S);  // INIT -> STEP, always
         const unsigned stepping_now = __ballot_sync(full, r.phase == PRT_PH_STEP);
@@ -184,7 +187,8 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SA
         } else {
             const unsigned stepping = __ballot_sync(full, r.phase == PRT_PH_STEP);
             ++waited;
-            if (!stepping || waited > park_wait) {
+            if (!stepping || waited > limit) {
+                limit = (2 * __popc(parked) >= __popc(parked | stepping)) ? park_wait_long : park_wait;
                 if (r.phase == PRT_PH_ROOT) {
                     prt_step st;
                     park.rebuild(E, S, r, st);
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(SAVE ? PRT_BLOCK : PRT_BLOCK_ARR, SAVE ? PRT_M
     prt_ray<SAVE, COUNT> r;
     r.start(T, z, p, P.source_range, S);
     if (!live) r.phase = PRT_PH_DONE;
-    prt_integrate_warp(E, r, S, sink, P.park_wait, park);
+    prt_integrate_warp(E, r, S, sink, P.park_wait, P.park_wait_long, park);
     if (!live) return;
     prt_ray_result res;
     uint32_t cnt[PRT_CNT_N];
@@ -599,7 +603,7 @@ __global__ void __launch_bounds__(PRT_BLOCK_ARR, PRT_MIN_BLOCKS_ARR) prt_refine_
     prt_ray<false, false> r;
     r.start(T, z, p, P.source_range, shot);
     if (!live) r.phase = PRT_PH_DONE;
-    prt_integrate_warp(E, r, shot, sink, P.park_wait, park);
+    prt_integrate_warp(E, r, shot, sink, P.park_wait, P.park_wait, park);
     if (!live) return;
     prt_ray_result res;
     r.result(shot, sink, res, nullptr);
@@ -1135,6 +1139,16 @@ static int shoot_fan_impl(const prt_env_t* env, int64_t n_rays, int64_t rays_per
     P.out_counters = out_counters_dev; P.max_bounces = max_bounces > 0 ? max_bounces : (1 << 20);
     P.stored_convention = stored_convention;
     P.park_wait = park_wait_setting();
+    {
+        // wait of warps whose lanes reflect together (PRT_PARK_WAIT_LONG, default 128; < 0: same as park_wait).
+        // Measured (profiles/r02_variants.md): a +-40 deg 10k-ray fan 26.9 -> 18.3 ms, everything else within 1 %.
+        static int lw = -2;
+        if (lw == -2) {
+            const char* e = getenv("PRT_PARK_WAIT_LONG");
+            lw = e ? atoi(e) : 128;
+        }
+        P.park_wait_long = lw >= 0 ? lw : P.park_wait;
+    }
     P.rays_per_env = rays_per_env;
     {
         static int reorder = -1;  // PRT_REORDER=0 switches the block order off (experiments)
