@@ -274,9 +274,11 @@ def case_cfg4_sub():
 
 
 def case_flatearth():
-    """eflat / eflatinv of the reference (environment.py:371-466) on a spread of depths and latitudes.
-    (flat_earth_c needs xarray's DataArray.interp, which the import stub does not provide: unpinned.)"""
-    from pygenray.environment import eflat, eflatinv
+    """eflat / eflatinv of the reference (environment.py:371-466) on a spread of depths and latitudes, and the
+    reference's range-dependent flat_earth_c (environment.py:239-303, sequential branch) on a 37 x 301 config-2 grid
+    with one latitude per range column and on an irregular depth grid that does not start at the surface.  xarray's
+    1-D linear DataArray.interp is the stand-in's scipy interp1d (see oracle/stubs/xarray)."""
+    from pygenray.environment import eflat, eflatinv, flat_earth_c
 
     dep = np.concatenate(([1.0], np.linspace(10.0, 6000.0, 41)))
     out = {"dep": dep, "lats": np.array([-60.0, 0.0, 35.0, 80.0])}
@@ -284,6 +286,19 @@ def case_flatearth():
         depf, csf = eflat(dep, lat, 1480.0 + 0.017 * dep)
         d_inv, c_inv = eflatinv(depf, lat, csf)
         out[f"depf_{lat}"] = depf; out[f"csf_{lat}"] = csf; out[f"dinv_{lat}"] = d_inv; out[f"cinv_{lat}"] = c_inv
+    a = cases.config2_arrays(n_r=37, n_z=301)
+    lat = np.linspace(20.0, 47.0, 37)
+    c = xr.DataArray(a["c"].T, dims=["depth", "range"], coords={"depth": a["z"], "range": a["r"], "lat": ("range", lat)})
+    fe = flat_earth_c(c, verbose=False, n_cpus=1)
+    assert fe.dims == ("range", "depth")
+    out["fec_lat"] = lat; out["fec_out"] = fe.values; out["fec_c_sha"] = sha(a["c"])
+    z = np.sort(np.concatenate(([5.0, 5400.0], np.random.default_rng(2).uniform(5.0, 5400.0, 120))))
+    c2 = np.array([munk_ssp(z, 1300.0 + 10 * i, 0.00737) for i in range(9)])
+    lat2 = np.linspace(-70, 70, 9)
+    fe2 = flat_earth_c(xr.DataArray(c2.T, dims=["depth", "range"],
+                                    coords={"depth": z, "range": np.arange(9.0), "lat": ("range", lat2)}),
+                       verbose=False, n_cpus=1)
+    out["fec2_z"] = z; out["fec2_c"] = c2; out["fec2_lat"] = lat2; out["fec2_out"] = fe2.values
     save("ref_flatearth", **out)
 
 

@@ -49,6 +49,21 @@ def golden(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 
 
+def flat_earth_c_numpy(c, depth, lat):
+    """flat_earth_c (ref:environment.py:239-303) restated: per range column eflat with its own latitude, then xarray's
+    linear interp back onto the original depth grid (scipy interp1d, bounds_error=False -> NaN outside).  Pinned
+    against the reference's own output by tests/test_oracle_vs_reference.py::test_flat_earth_c_restatement."""
+    from scipy.interpolate import interp1d
+
+    import pygenray_b200 as pr
+
+    out = np.empty_like(c)
+    for r in range(c.shape[0]):
+        depf, cf = pr.eflat(depth, lat[r], c[r])
+        out[r] = interp1d(depf, cf, kind="linear", bounds_error=False)(depth)
+    return out
+
+
 def make_env(arrays, flat=False, lat=35):
     import pygenray_b200 as pr
 

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from conftest import assert_same_fan, golden, make_env, oracle_env_from, ray_angle_numpy
+from conftest import assert_same_fan, flat_earth_c_numpy, golden, make_env, oracle_env_from, ray_angle_numpy
 import workloads as cases
 from oracle import oracle as orc
 
@@ -548,18 +548,6 @@ def test_find_eigenrays_when_nothing_converges(pr):
 
 
 # ---- earth flattening on the device (environment.py:121-173, 239-401) -----------------------------------------------
-def _flat_earth_c_numpy(c, depth, lat):
-    """flat_earth_c restated: per range column eflat with its own latitude, then xarray's linear interp back onto the
-    original depth grid (scipy interp1d, bounds_error=False -> NaN outside)."""
-    from scipy.interpolate import interp1d
-
-    out = np.empty_like(c)
-    for r in range(c.shape[0]):
-        depf, cf = __import__("pygenray_b200").eflat(depth, lat[r], c[r])
-        out[r] = interp1d(depf, cf, kind="linear", bounds_error=False)(depth)
-    return out
-
-
 def test_flat_earth_c_and_transform_rd(pr):
     import torch
     from pygenray_b200.environment import flat_earth_c, flat_earth_device
@@ -569,15 +557,22 @@ def test_flat_earth_c_and_transform_rd(pr):
     c = pr.DataArray(a["c"].T, dims=["depth", "range"], coords={"depth": a["z"], "range": a["r"], "lat": lat})
     out = flat_earth_c(c, verbose=False, n_cpus=3)
     assert out.dims == ("range", "depth") and np.array_equal(out.coords["lat"].values, lat)
-    exp = _flat_earth_c_numpy(a["c"], a["z"], lat)
+    exp = flat_earth_c_numpy(a["c"], a["z"], lat)
     assert np.array_equal(np.isnan(out.values), np.isnan(exp))
     np.testing.assert_allclose(out.values, exp, rtol=1e-13, atol=0, equal_nan=True)
     assert np.abs(out.values - a["c"]).max() > 0.1  # the transform does something (c_f - c ~ c z / R_e)
+    # the reference's own flat_earth_c on the same input (oracle/make_golden.py: case_flatearth)
+    g = golden("ref_flatearth_jit.npz")
+    assert np.array_equal(g["fec_lat"], lat)
+    np.testing.assert_allclose(out.values, g["fec_out"], rtol=1e-13, atol=0, equal_nan=True)
     # irregular, non-zero-based depth grid: generic interval search, NaN above the first flattened node
     z = np.sort(np.concatenate(([5.0, 5400.0], np.random.default_rng(2).uniform(5.0, 5400.0, 120))))
     c2 = np.array([cases.munk_ssp(z, 1300.0 + 10 * i) for i in range(9)])
     o2 = flat_earth_device(torch.from_numpy(c2).cuda(), z, np.linspace(-70, 70, 9), resample=True).cpu().numpy()
-    e2 = _flat_earth_c_numpy(c2, z, np.linspace(-70, 70, 9))
+    e2 = flat_earth_c_numpy(c2, z, np.linspace(-70, 70, 9))
+    assert np.array_equal(g["fec2_z"], z) and np.array_equal(g["fec2_c"], c2)
+    assert np.array_equal(np.isnan(o2), np.isnan(g["fec2_out"]))
+    np.testing.assert_allclose(o2, g["fec2_out"], rtol=1e-13, atol=0, equal_nan=True)
     assert np.isnan(e2[:, 0]).all() and np.array_equal(np.isnan(o2), np.isnan(e2))
     np.testing.assert_allclose(o2, e2, rtol=1e-13, atol=0, equal_nan=True)
     # environment method: attributes as the reference sets them (bathymetry copied, dcdz on the flattened field)

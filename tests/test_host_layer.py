@@ -4,6 +4,7 @@ Mirrors the reference's unit tests (tests/test_environment.py, tests/test_ray_ob
 drop-in objects behave the same, then checks the boundary: libprt.so exports every symbol that
 include/prt.h declares and the product refuses to run without a CUDA device (no CPU fallback)."""
 import ctypes as C
+import hashlib
 import json
 import os
 import re
@@ -247,6 +248,23 @@ def test_eflat_and_eflatinv_against_reference_values():
         assert np.abs(d - dep).max() < 1e-9 and np.abs(c - (1480.0 + 0.017 * dep)).max() < 1e-9
     d, c = eflatinv(np.array([100.0, 2000.0]), np.array([10.0, 50.0]))
     assert d.shape == (2,) and (c == 0).all()
+
+
+def test_flat_earth_c_restatement_against_reference_output():
+    """The numpy restatement the device kernel is compared with (conftest.flat_earth_c_numpy) reproduces the
+    reference's own flat_earth_c (ref:environment.py:239-303; golden made by oracle/make_golden.py: case_flatearth)
+    on a 37 x 301 grid with per-column latitudes and on an irregular depth grid that starts below the surface."""
+    from conftest import flat_earth_c_numpy
+    import workloads as cases
+
+    g = golden("ref_flatearth_jit.npz")
+    a = cases.config2_arrays(n_r=37, n_z=301)
+    assert hashlib.sha256(np.ascontiguousarray(a["c"]).tobytes()).hexdigest() == str(g["fec_c_sha"])
+    mine = flat_earth_c_numpy(a["c"], a["z"], g["fec_lat"])
+    assert not np.isnan(g["fec_out"]).any() and np.array_equal(mine, g["fec_out"])
+    mine2 = flat_earth_c_numpy(g["fec2_c"], g["fec2_z"], g["fec2_lat"])
+    assert np.isnan(g["fec2_out"][:, 0]).all() and np.isnan(g["fec2_out"]).sum() == 9  # above the first flattened node
+    assert np.array_equal(mine2, g["fec2_out"], equal_nan=True)
 
 
 def test_device_rows_indexing_semantics():
