@@ -1166,7 +1166,19 @@ static int shoot_fan_impl(const prt_env_t* env, int64_t n_rays, int64_t rays_per
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int zm = prt_z_mode(env->view);  // depth-axis variant compiled in: plain / refined guess / exactly uniform grid
     const bool cnt = out_counters_dev != nullptr;
-#define PRT_FAN_LAUNCH(SV, Z, CN) prt_fan_kernel<SV, Z, CN><<<grid, block, 0, s>>>(env->view, P)
+    // experiment hook: PRT_SMEM_CARVEOUT=<percent> passes a shared-memory carve-out preference for the fan kernels
+    // (they use 3 KB per block; the driver's default choice is a 32 KB configuration, profiles/r02_fan_cfg3_1M_final_raw.csv)
+    static int carve = -2;
+    if (carve == -2) {
+        const char* e = getenv("PRT_SMEM_CARVEOUT");
+        carve = e ? atoi(e) : -1;
+    }
+#define PRT_FAN_LAUNCH(SV, Z, CN)                                                                                      \
+    do {                                                                                                               \
+        if (carve >= 0)                                                                                                \
+            cudaFuncSetAttribute(prt_fan_kernel<SV, Z, CN>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);    \
+        prt_fan_kernel<SV, Z, CN><<<grid, block, 0, s>>>(env->view, P);                                               \
+    } while (0)
 #define PRT_FAN_PICK_CN(SV, Z) do { if (cnt) PRT_FAN_LAUNCH(SV, Z, true); else PRT_FAN_LAUNCH(SV, Z, false); } while (0)
 #define PRT_FAN_PICK_Z(SV) do { if (zm == 3) PRT_FAN_PICK_CN(SV, 3); else if (zm == 2) PRT_FAN_PICK_CN(SV, 2); else if (zm == 1) PRT_FAN_PICK_CN(SV, 1); else PRT_FAN_PICK_CN(SV, 0); } while (0)
     if (save) PRT_FAN_PICK_Z(true);
