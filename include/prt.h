@@ -90,7 +90,7 @@ PRT_API const char *prt_last_error(void);
  * fans are spread over warps, never results.  Default 1. */
 PRT_API int prt_set_concurrency(int n_fans);
 
-/* Launch hint: rays per warp (1, 2, 4, 8, 16 or 32) of the launches that follow on this host thread's behalf;
+/* Launch hint: rays per warp (1 .. 32) of the launches that follow on this host thread's behalf;
  * 0 (default) lets the library choose from the fan size.  Fewer rays per warp shorten the critical path of
  * reflecting (steep) rays, whose lanes otherwise wait for one another's root searches; affects only speed. */
 PRT_API int prt_set_lanes(int lanes);

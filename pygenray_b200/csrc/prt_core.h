@@ -159,9 +159,6 @@ struct prt_envp {
     const prt_env_view& v;
     const prt_d2* grid;
     int zm;   // grid mode (prt_z_mode), a compile-time constant in each kernel instantiation
-    int ol;   // 1: every exact field lookup goes through ONE out-of-line copy (prt_field_cold): smaller kernel code
-              //    for the eigenray refinement, whose warps sit in different phases and stall on instruction fetch;
-              //    a compile-time constant like zm (0 when the aggregate initialiser omits it).  Same arithmetic.
 };
 
 // np.nextafter(t, +inf) (scipy rk.py:119) by integer increment of the bit pattern (select-only: it opens
@@ -479,17 +476,8 @@ PRT_HD unsigned prt_guess_z(const prt_envp& E, double z) { return prt_guess_z_fr
 // nodes) is issued from the guessed indices at once; the guesses are verified afterwards (two compares per
 // axis against edges padded with -inf / +inf at the grid ends, false for NaN) and the rare miss
 // (cell-boundary rounding, non-uniform grids) takes the general lookup.
-PRT_HD_NOINLINE void prt_field_cold(const prt_env_view* V, const prt_d2* grid, int zm, double x, double z, double* c2);
-
 PRT_HD void prt_field(const prt_envp& E, double x, double z, double& c, double& cz)
 {
-    if (E.ol) {
-        double c2[2];
-        prt_field_cold(&E.v, E.grid, E.zm, x, z, c2);
-        c = c2[0];
-        cz = c2[1];
-        return;
-    }
     const prt_env_view& V = E.v;
     unsigned i = prt_guess(x, V.r_inv, V.r_off, V.n_r - 2);
     unsigned j = prt_guess_z(E, z);
@@ -523,12 +511,6 @@ PRT_HD void prt_field(const prt_envp& E, double x, double z, double& c, double& 
         wy = (z - ze.x) * prt_ld(V.zrecip + j);
     }
     prt_bilerp(v00, v01, v10, v11, wx, wy, c, cz);
-}
-
-PRT_HD_NOINLINE void prt_field_cold(const prt_env_view* V, const prt_d2* grid, int zm, double x, double z, double* c2)
-{
-    const prt_envp E{*V, grid, zm, 0};
-    prt_field(E, x, z, c2[0], c2[1]);
 }
 
 // Speculative lookup for the Runge-Kutta stages: the same arithmetic from the guessed cell, but NO branch
@@ -681,7 +663,7 @@ PRT_HD void prt_rhs(const prt_envp& E, double x, double z, double p, double& dT,
 PRT_HD_NOINLINE void prt_rhs_cold(const prt_env_view* V, const prt_d2* grid, int zm, double x, double z, double p,
                                   double* out4)
 {
-    const prt_envp E{*V, grid, zm, 0};
+    const prt_envp E{*V, grid, zm};
     prt_rhs(E, x, z, p, out4[0], out4[1], out4[2], out4[3]);
 }
 
@@ -1132,7 +1114,7 @@ PRT_HD_NOINLINE void prt_rk_try_exact(const prt_env_view* V, const prt_d2* grid,
                                       double hh, double T, double z, double p, double f0, double f1, double f2,
                                       prt_try* out)
 {
-    const prt_envp E{*V, grid, prt_z_mode(*V), 0};
+    const prt_envp E{*V, grid, prt_z_mode(*V)};
     bool ok = true;
 #if defined(PRT_COUNT_COLD) && !defined(__CUDACC__)
     extern long long prt_cold_count;

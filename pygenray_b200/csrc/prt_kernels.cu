@@ -123,10 +123,6 @@ static int park_wait_setting()
 // parked record this small leaves the kernel with 2 KB of shared memory per block, i.e. practically the
 // whole 256 KB of an SM as L1 for the sound-speed grid (the 2001 x 1201 internal-wave grid of config 3 runs
 // 3.6x slower when a third of the L1 is taken away; profiles/r01_variants.md).
-// eigenray refinement: exact field lookups through one out-of-line copy (prt_envp::ol); 0 = inlined as in the fans
-#ifndef PRT_REFINE_OUTLINE
-#define PRT_REFINE_OUTLINE 1
-#endif
 #define PRT_PARK_FIELDS 2
 struct prt_park_slot {
     double* base;  // &park[0][threadIdx.x]
@@ -245,7 +241,7 @@ __global__ void __launch_bounds__(SAVE ? PRT_BLOCK : PRT_BLOCK_ARR, SAVE ? PRT_M
         angle_index = ray - env * P.rays_per_env;
         grid = E0.grid + env * E0.grid_stride;
     }
-    const prt_envp E{E0, grid, ZM, 0};
+    const prt_envp E{E0, grid, ZM};
     prt_shot S;
     S.x_end = P.receiver_range; S.rtol = P.rtol; S.atol = P.atol;
     S.terminate_backwards = P.terminate_backwards; S.n_save = P.n_save; S.max_bounces = P.max_bounces;
@@ -330,13 +326,13 @@ static std::atomic<int> g_lanes_override{0};
 static int lanes_forced()
 {
     const int ov = g_lanes_override.load();
-    if (ov == 1 || ov == 2 || ov == 4 || ov == 8 || ov == 16 || ov == 32) return ov;
+    if (ov >= 1 && ov <= 32) return ov;
     static int forced = -1;
     if (forced < 0) {
         const char* e = getenv("PRT_LANES");
         forced = e ? atoi(e) : 0;
     }
-    if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16 || forced == 32) return forced;
+    if (forced >= 1 && forced <= 32) return forced;  // any count works: ray = warp * lanes + lane, lanes >= count idle
     return 0;
 }
 
@@ -572,7 +568,7 @@ __global__ void __launch_bounds__(PRT_BLOCK_ARR, PRT_MIN_BLOCKS_ARR) prt_refine_
                                                                prt_refine_state S, const int32_t* __restrict__ list_in,
                                                                const int32_t* n_in)
 {
-    const prt_envp E{E0, E0.grid, ZM, PRT_REFINE_OUTLINE};
+    const prt_envp E{E0, E0.grid, ZM};
     const int n_active = *n_in;
     // rays per warp: the rule of pick_lanes() on the number of brackets still active, which only the device knows
     // (the host never waits for a round): few survivors are spread over more, partly filled warps

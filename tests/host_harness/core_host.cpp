@@ -60,7 +60,7 @@ __attribute__((visibility("default"))) int hh_shoot_fan(void* env, int64_t n_ray
                                                          int max_bounces)
 {
     const prt_env_view& V = static_cast<hh_env*>(env)->view;
-    const prt_envp E{V, V.grid, prt_z_mode(V), 0};
+    const prt_envp E{V, V.grid, prt_z_mode(V)};
     for (int64_t i = 0; i < n_rays; ++i) {
         double T, z, p;
         if (y0s) {
