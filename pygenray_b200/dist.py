@@ -105,6 +105,8 @@ def _gather_index(n_rays, world, block, device):
             mine = shard_indices(n_rays, r, world, block)
             src[mine] = r * pad + np.arange(mine.shape[0])
         idx = (torch.from_numpy(src).to(device), sizes, pad)
+        if len(_GATHER_INDEX_CACHE) >= 16:  # bracket counts differ from fan to fan: keep the device copies bounded
+            _GATHER_INDEX_CACHE.clear()
         _GATHER_INDEX_CACHE[key] = idx
     return idx
 
