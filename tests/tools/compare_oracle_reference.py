@@ -1,8 +1,8 @@
 """Regenerate the numbers of DESIGN.md section 5 (oracle vs reference vs the reference's own jit / no-jit spread) from the
 committed golden vectors: three-way distances of the arrival depth / time on configs 2 and 3, bounce-count detail of the
-chaotic rays, eigenray comparison on config 4.  Run on the CPU: python tools/compare_oracle_reference.py"""
+chaotic rays, eigenray comparison on config 4.  Run on the CPU: python tests/tools/compare_oracle_reference.py"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from conftest import golden, make_env, oracle_env_from

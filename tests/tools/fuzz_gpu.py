@@ -1,6 +1,6 @@
-"""Dev: extended GPU-vs-oracle fuzz (same generator as tests/fuzz_cases.py, more seeds).  Usage: fuzz_gpu.py LO HI"""
+"""Test infrastructure (lives under tests/ because it calls the oracle): extended GPU-vs-oracle fuzz (same generator as tests/fuzz_cases.py, more seeds).  Usage: fuzz_gpu.py LO HI"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import pygenray_b200 as pr

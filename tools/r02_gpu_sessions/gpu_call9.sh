@@ -2,7 +2,7 @@
 # GPU session 9: final kernel (grid mode 3) -- parity suite, extra fuzz seeds, ncu launch list + full captures
 mkdir -p gpurun_out
 ( time timeout 1500 python -m pytest tests -m gpu -q ) > gpurun_out/r02_pytest_gpu.log 2>&1; tail -3 gpurun_out/r02_pytest_gpu.log
-timeout 900 python tools/fuzz_gpu.py 600 760 > gpurun_out/r02_fuzz_gpu.log 2>&1; tail -2 gpurun_out/r02_fuzz_gpu.log
+timeout 900 python tests/tools/fuzz_gpu.py 600 760 > gpurun_out/r02_fuzz_gpu.log 2>&1; tail -2 gpurun_out/r02_fuzz_gpu.log
 timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/plain_bench.log 2>&1 &&
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/r02_launches_bench_cfg3_final.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_bench.log 2>&1
