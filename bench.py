@@ -245,6 +245,9 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL writes its banner ("NCCL version ...") and any NCCL_DEBUG output to stdout by default; stdout is
+        # reserved for the ONE JSON line of the contract
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.require_gpu()
 
