@@ -225,7 +225,7 @@ def run_reference(args):
                 "oracle/prt_oracle.c on all host threads (a rate: per-step sample stated above), with the unmodified "
                 "Python reference timed beside it on config 1 (cpu_baseline.python_reference)",
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -245,9 +245,6 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL writes its banner ("NCCL version ...") and any NCCL_DEBUG output to stdout by default; stdout is
-        # reserved for the ONE JSON line of the contract
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.require_gpu()
 
@@ -534,9 +531,30 @@ def run_b200(args):
             "wall_s_timed_region": t_wall,
             "eigenrays": eig,
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_OUT = None
+
+
+def _reserve_stdout():
+    """stdout carries exactly ONE JSON line (the bench contract), but libraries write there too -- NCCL prints its
+    "NCCL version ..." banner to the C stdout whenever NCCL_DEBUG is VERSION or WARN (NCCL_DEBUG_FILE is only honoured
+    above that level), worker pools and numba may print.  Keep a private handle on the real stdout for the JSON line and
+    point file descriptor 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -551,6 +569,7 @@ def main():
     ap.add_argument("--no-python-ref", action="store_true", help="skip the Python reference baseline")
     ap.add_argument("--ref-rays", type=int, default=0, help="CPU reference arm: rays per step (default per workload)")
     args = ap.parse_args()
+    _reserve_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
