@@ -15,8 +15,8 @@ def test_reference_arm_prints_the_contract_line():
                         "--steps", "1", "--warmup", "1", "--ref-rays", "64", "--no-python-ref"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
-    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
-    assert len(lines) == 1
+    lines = p.stdout.splitlines()
+    assert len(lines) == 1 and lines[0].startswith("{"), p.stdout[:400]  # stdout is the ONE JSON line, nothing else
     d = json.loads(lines[0])
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
@@ -47,3 +47,14 @@ def test_both_arms_share_one_config_object_and_workload_definition():
     assert all(abs(len(w["angles"]) - 10000) <= 32 for w in weak)  # cyclic blocks of 32 angles
     flops = bench.algorithmic_flops(np.array([[10], [2], [1], [1], [4], [1]], dtype=np.uint32))
     assert flops == 38 * 10 + 200 * 2 + 40 * 1 + 168 * 1 + 60 * 4
+
+
+def test_stdout_is_reserved_for_the_json_line():
+    """Libraries write to the C stdout (NCCL prints its version banner there under torchrun): bench.py keeps a private
+    handle for the JSON line and points file descriptor 1 at stderr for everything else."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench._reserve_stdout(); "
+            "os.write(1, b'NCCL version x.y\\n'); print('stray print'); bench._emit({'a': 1})" % ROOT)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert p.stdout == '{"a": 1}\n'
+    assert "NCCL version x.y" in p.stderr and "stray print" in p.stderr
