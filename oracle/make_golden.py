@@ -140,6 +140,20 @@ def case_cfg2_sub():
          **{"al_" + k: v for k, v in al.items()})
 
 
+def case_cfg5_sub():
+    """BASELINE config 5 sub-sample: two members of the tomography ensemble (config-2 grid + internal-wave perturbation,
+    seeds 1000 + i), 21 of the 4096 launch angles each, 500 km."""
+    out = {}
+    angles = np.linspace(-15, 15, 4096)[::204][:21]
+    for i in (0, 7):
+        a = cases.config5_realisation(i)
+        env = make_env(a)
+        al = array_level(env, False, 1000.0, 0.0, 500e3, -angles, 101)
+        out.update({f"m{i}_al_" + k: v for k, v in al.items()})
+        out[f"m{i}_c_sha"] = sha(a["c"])
+    save("ref_cfg5_sub", user_angles=angles, **out)
+
+
 def case_bounce_fine():
     """Default 1 m grid env, steep rays that bounce (stable-step regime with reflections)."""
     env = OceanEnvironment2D()
@@ -304,9 +318,9 @@ def case_flatearth():
 
 CASES = dict(cfg1=case_cfg1, fixture=case_fixture, cfg2_sub=case_cfg2_sub, bounce_fine=case_bounce_fine,
              physics=case_physics, eigen=case_eigen, cfg3_sub=case_cfg3_sub,
-             cfg4_sub=case_cfg4_sub, flatearth=case_flatearth)
+             cfg4_sub=case_cfg4_sub, flatearth=case_flatearth, cfg5_sub=case_cfg5_sub)
 # cases re-run without the JIT to measure the reference's own self-consistency envelope
-NOJIT_CASES = ("cfg1", "cfg2_sub", "bounce_fine", "cfg3_sub", "cfg4_sub")
+NOJIT_CASES = ("cfg1", "cfg2_sub", "bounce_fine", "cfg3_sub", "cfg4_sub", "cfg5_sub")
 
 if __name__ == "__main__":
     want = sys.argv[1:] or list(CASES)

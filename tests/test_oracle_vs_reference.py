@@ -164,6 +164,31 @@ def test_config2_chaotic_regime_within_reference_envelope():
     assert abs(o["counters"][:, 0].sum() / g["al_nfev"].sum() - 1) < 0.02
 
 
+def test_config5_ensemble_members_within_reference_envelope():
+    """BASELINE config 5: two members of the tomography ensemble (config-2 grid + internal-wave perturbation), 21 of the
+    4096 launch angles each, through the unmodified reference (jit / no-jit) and through the oracle."""
+    g, gn = golden("ref_cfg5_sub_jit.npz"), golden("ref_cfg5_sub_nojit.npz")
+    parts = {"o": [], "g": [], "gn": []}
+    for i in (0, 7):
+        a = cases.config5_realisation(i)
+        assert _sha(a["c"]) == str(g[f"m{i}_c_sha"])
+        oenv = oracle_env_from(make_env(a), False)
+        o = orc.shoot_fan(oenv, 1000.0, 0.0, 500e3, angles_deg=g[f"m{i}_al_internal_angles"],
+                          range_save=g[f"m{i}_al_range_save"])
+        parts["o"].append(o)
+        parts["g"].append({k[len(f"m{i}_"):]: g[k] for k in g.files if k.startswith(f"m{i}_al_")})
+        parts["gn"].append({k[len(f"m{i}_"):]: gn[k] for k in gn.files if k.startswith(f"m{i}_al_")})
+        # work per ray-km is the reference's
+        assert abs(o["counters"][:, 0].sum() / g[f"m{i}_al_nfev"].sum() - 1) < 0.02
+
+    def cat(ds, keys):
+        return {k: np.concatenate([d[k] for d in ds]) for k in keys}
+
+    keys = ("al_ok", "al_n_bottom", "al_n_surface", "al_final")
+    _envelope_check(cat(parts["o"], ("status", "n_bottom", "n_surface", "final")), cat(parts["g"], keys),
+                    cat(parts["gn"], keys), 2.0, "config 5 members 0 and 7")
+
+
 def test_reflections_on_fine_grid_within_reference_envelope():
     import pygenray_b200 as pr
 
