@@ -64,7 +64,7 @@ def array_level(env, flat, z_src, r_src, r_rcv, internal_angles, n_save, rtol=1e
     final = np.full((n, 3), np.nan)
     nb = np.zeros(n, np.int64); ns = np.zeros(n, np.int64)
     ok = np.zeros(n, bool); nfev = np.zeros(n, np.int64); nsteps = np.zeros(n, np.int64)
-    nseg = np.zeros(n, np.int64)
+    nseg = np.zeros(n, np.int64); raised = np.zeros(n, bool)
     for k, a in enumerate(internal_angles):
         y0 = np.array([0, z_src, np.sin(np.radians(a)) / c0])
         try:
@@ -72,6 +72,7 @@ def array_level(env, flat, z_src, r_src, r_rcv, internal_angles, n_save, rtol=1e
                                                 rtol, terminate_backwards, False)
         except Exception:
             sols = None
+            raised[k] = True
         if sols is None:
             continue
         ok[k] = True
@@ -83,7 +84,7 @@ def array_level(env, flat, z_src, r_src, r_rcv, internal_angles, n_save, rtol=1e
         nsteps[k] = sum(len(x.sol.interpolants) for x in sols)
         nseg[k] = len(sols)
     return dict(traj=traj, final=final, n_bottom=nb, n_surface=ns, ok=ok, nfev=nfev, nsteps=nsteps,
-                nseg=nseg, range_save=rs, internal_angles=np.asarray(internal_angles, float))
+                nseg=nseg, raised=raised, range_save=rs, internal_angles=np.asarray(internal_angles, float))
 
 
 def fan_dict(rf, prefix="fan_"):
@@ -152,6 +153,25 @@ def case_cfg5_sub():
         out.update({f"m{i}_al_" + k: v for k, v in al.items()})
         out[f"m{i}_c_sha"] = sha(a["c"])
     save("ref_cfg5_sub", user_angles=angles, **out)
+
+
+def case_fuzz_short():
+    """40 random environments of tests/fuzz_cases.py: short_case (2-30 km): irregular / regular grids, noisy sound speeds,
+    flat-earth on / off, offset sources, rtol 1e-6 .. 1e-11 -- the reference ray by ray."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fuzz_cases import short_case
+
+    out = {}
+    for seed in range(40):
+        k = short_case(seed)
+        a = k["arrays"]
+        ssp = xr.DataArray(a["c"], dims=["range", "depth"], coords={"range": a["r"], "depth": a["z"]})
+        bathy = xr.DataArray(a["bathy"], dims=["range"], coords={"range": a["bathy_r"]})
+        env = OceanEnvironment2D(sound_speed=ssp, bathymetry=bathy, lat=k["lat"], flat_earth_transform=k["flat"])
+        al = array_level(env, k["flat"], k["zs"], k["r0"], k["r1"], k["angles"], k["n_save"], rtol=k["rtol"],
+                         terminate_backwards=k["terminate_backwards"])
+        out.update({f"s{seed}_" + kk: v for kk, v in al.items()})
+    save("ref_fuzz_short", **out)
 
 
 def case_bounce_fine():
@@ -318,9 +338,10 @@ def case_flatearth():
 
 CASES = dict(cfg1=case_cfg1, fixture=case_fixture, cfg2_sub=case_cfg2_sub, bounce_fine=case_bounce_fine,
              physics=case_physics, eigen=case_eigen, cfg3_sub=case_cfg3_sub,
-             cfg4_sub=case_cfg4_sub, flatearth=case_flatearth, cfg5_sub=case_cfg5_sub)
+             cfg4_sub=case_cfg4_sub, flatearth=case_flatearth, cfg5_sub=case_cfg5_sub,
+             fuzz_short=case_fuzz_short)
 # cases re-run without the JIT to measure the reference's own self-consistency envelope
-NOJIT_CASES = ("cfg1", "cfg2_sub", "bounce_fine", "cfg3_sub", "cfg4_sub", "cfg5_sub")
+NOJIT_CASES = ("cfg1", "cfg2_sub", "bounce_fine", "cfg3_sub", "cfg4_sub", "cfg5_sub", "fuzz_short")
 
 if __name__ == "__main__":
     want = sys.argv[1:] or list(CASES)

@@ -42,3 +42,19 @@ def random_case(seed):
     tb = bool(rng.random() < 0.8)
     return dict(arrays=arrays, flat=bool(rng.random() < 0.3), zs=zs, r0=r0, r1=r1, angles=angles, n_save=n_save,
                 rtol=rtol, terminate_backwards=tb, lat=float(rng.uniform(-60, 60)))
+
+
+def short_case(seed):
+    """The same generator scaled to short ranges (2-30 km, a few dozen steps per ray): there the reference reproduces
+    itself to ~1e-9, so the oracle can be compared with it ray by ray on random environments (irregular grids, noisy
+    sound speeds, flat-earth on / off, offset sources); used by oracle/make_golden.py: case_fuzz_short and
+    tests/test_oracle_vs_reference.py."""
+    k = random_case(seed)
+    f = 0.1
+    a = k["arrays"]
+    k["arrays"] = dict(c=a["c"], r=a["r"] * f, z=a["z"], bathy=a["bathy"], bathy_r=a["bathy_r"] * f)
+    k["r0"], k["r1"] = k["r0"] * f, k["r1"] * f
+    ang = k["angles"]
+    k["angles"] = ang[np.abs(ang) <= 30.0][:8] if (np.abs(ang) <= 30.0).any() else np.clip(ang[:4], -30.0, 30.0)
+    k["n_save"] = 17
+    return k

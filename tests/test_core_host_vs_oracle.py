@@ -164,6 +164,19 @@ def test_backwards_mirrored_environment(harness):
     assert_same_fan(o, h, "mirrored environment, negative ranges")
 
 
+def test_reference_pinned_random_environments(harness):
+    """The 40 short random environments of the reference comparison (fuzz_cases.short_case): product core == oracle."""
+    from fuzz_cases import short_case
+
+    for seed in range(40):
+        k = short_case(seed)
+        env = make_env(k["arrays"], flat=k["flat"], lat=k["lat"])
+        oenv = oracle_env_from(env, k["flat"])
+        o, h = _both(harness, oenv, k["zs"], k["r0"], k["r1"], k["angles"], k["n_save"], rtol=k["rtol"],
+                     terminate_backwards=k["terminate_backwards"])
+        assert_same_fan(o, h, f"short fuzz seed {seed}")
+
+
 @pytest.mark.parametrize("seed", range(40))
 def test_fuzz_random_environments(harness, seed):
     """Random grids (uniform and irregular, noisy sound speed), bathymetry shorter or longer than the

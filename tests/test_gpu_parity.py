@@ -324,6 +324,27 @@ def test_fuzz_random_environments_gpu(pr, seed):
     assert_same_fan(o, g, f"fuzz seed {seed}")
 
 
+def test_reference_pinned_random_environments_gpu(pr):
+    """The 40 short random environments on which the oracle is compared with the unmodified reference ray by ray
+    (tests/test_oracle_vs_reference.py::test_random_short_range_environments_against_reference): libprt.so == oracle,
+    bit for bit, on exactly those inputs -- and kept / dropped and bounce counts == the reference's."""
+    from fuzz_cases import short_case
+
+    g = golden("ref_fuzz_short_jit.npz")
+    for seed in range(40):
+        k = short_case(seed)
+        env = make_env(k["arrays"], flat=k["flat"], lat=k["lat"])
+        d = _gpu_fan(pr, env, k["flat"], k["zs"], k["r0"], k["r1"], k["angles"], k["n_save"], rtol=k["rtol"],
+                     terminate_backwards=k["terminate_backwards"])
+        o = _oracle_fan(env, k["flat"], k["zs"], k["r0"], k["r1"], k["angles"], k["n_save"], rtol=k["rtol"],
+                        terminate_backwards=k["terminate_backwards"])
+        assert_same_fan(o, d, f"short fuzz seed {seed}")
+        P = f"s{seed}_"
+        m = g[P + "ok"]
+        assert np.array_equal(d["status"] == 0, m), seed
+        assert np.array_equal(d["n_bottom"][m], g[P + "n_bottom"][m]) and np.array_equal(d["n_surface"][m], g[P + "n_surface"][m])
+
+
 def test_sharded_fan_single_rank_and_records(pr):
     """dist.shoot_fan_sharded at world 1 == plain fan; prt_pack_arrivals lays out [n][6] records."""
     from pygenray_b200 import dist as pdist
