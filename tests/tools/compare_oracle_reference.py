@@ -58,7 +58,53 @@ def config4():
             print(line)
 
 
+def _three_lines(label, O, G, N):
+    for comp, nm in ((1, "depth [m]"), (0, "time [s]")):
+        for a, b, lab in ((O, G, "oracle-jit  "), (O, N, "oracle-nojit"), (G, N, "jit-nojit   ")):
+            d = np.abs(a - b)[:, comp]
+            print(f"   {label:34s} {nm:9s} {lab} median {np.median(d):9.3g}  p90 {np.percentile(d, 90):9.3g}  "
+                  f"p99 {np.percentile(d, 99):9.3g}  max {d.max():9.3g}")
+
+
+def config5():
+    g, gn = golden("ref_cfg5_sub_jit.npz"), golden("ref_cfg5_sub_nojit.npz")
+    O, G, N = [], [], []
+    for i in (0, 7):
+        oenv = oracle_env_from(make_env(cases.config5_realisation(i)), False)
+        P = f"m{i}_al_"
+        o = orc.shoot_fan(oenv, 1000.0, 0.0, 500e3, angles_deg=g[P + "internal_angles"], range_save=g[P + "range_save"])
+        m = g[P + "ok"] & gn[P + "ok"] & (o["status"] == 0)
+        m &= (g[P + "n_bottom"] == gn[P + "n_bottom"]) & (g[P + "n_surface"] == gn[P + "n_surface"])
+        print(f"== config 5 member {i}: {len(m)} rays, kept by all three with the variants agreeing on bounces {m.sum()}, oracle counts equal "
+              f"{np.array_equal(o['n_bottom'][m], g[P + 'n_bottom'][m]) and np.array_equal(o['n_surface'][m], g[P + 'n_surface'][m])}, "
+              f"RHS evaluations oracle / reference {o['counters'][:, 0].sum() / g[P + 'nfev'].sum():.4f}")
+        O.append(o["final"][m]); G.append(g[P + "final"][m]); N.append(gn[P + "final"][m])
+    _three_lines("config 5, members 0 and 7", np.concatenate(O), np.concatenate(G), np.concatenate(N))
+
+
+def fuzz_short():
+    from fuzz_cases import short_case
+
+    g, gn = golden("ref_fuzz_short_jit.npz"), golden("ref_fuzz_short_nojit.npz")
+    O, G, N, n, kept_equal, counts_equal = [], [], [], 0, 0, 0
+    for seed in range(40):
+        k = short_case(seed)
+        oenv = oracle_env_from(make_env(k["arrays"], flat=k["flat"], lat=k["lat"]), k["flat"])
+        P = f"s{seed}_"
+        o = orc.shoot_fan(oenv, k["zs"], k["r0"], k["r1"], angles_deg=k["angles"], range_save=g[P + "range_save"], rtol=k["rtol"],
+                          terminate_backwards=k["terminate_backwards"])
+        m = g[P + "ok"]
+        n += len(m); kept_equal += int(((o["status"] == 0) == m).sum())
+        counts_equal += int(((o["n_bottom"] == g[P + "n_bottom"]) & (o["n_surface"] == g[P + "n_surface"]))[m].sum())
+        O.append(o["final"][m]); G.append(g[P + "final"][m]); N.append(gn[P + "final"][m])
+    O, G, N = np.concatenate(O), np.concatenate(G), np.concatenate(N)
+    print(f"== 40 random short-range environments: {n} rays, kept / dropped equal on {kept_equal}, {len(O)} kept, bounce counts equal on {counts_equal}")
+    _three_lines("random short-range environments", O, G, N)
+
+
 if __name__ == "__main__":
     three_way("ref_cfg2_sub", make_env(cases.config2_arrays()), 1000.0, 500e3)
     three_way("ref_cfg3_sub", make_env(cases.config3_arrays()), 1000.0, 1000e3)
     config4()
+    config5()
+    fuzz_short()
