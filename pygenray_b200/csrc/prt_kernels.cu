@@ -82,7 +82,7 @@ struct prt_fan_params {
     uint32_t* out_counters;
     int32_t max_bounces;
     int32_t stored_convention;
-    int32_t park_wait, park_wait_long;
+    int32_t park_wait, park_wait_long, park_long_num;
     int32_t lanes;  // rays per warp (32, 16, 8, 4, 2 or 1): small fans use partly filled warps, see pick_lanes()
     int64_t rays_per_env;  // ensembles: ray r belongs to realisation r / rays_per_env and uses angles[r % rays_per_env]
     int32_t reorder;       // 1: second half of the blocks takes its chunks in reverse order (see prt_fan_kernel)
@@ -157,13 +157,14 @@ struct prt_park_slot {
 //     root search, the reflection and the next segment's start-up run once for all parked lanes, when
 //     no lane is left stepping or the oldest parked lane has waited `park_wait` iterations
 //     (neighbouring launch angles reach a boundary within a few steps of each other).
-//   * the wait adapts: after a pass in which at least half of the lanes still in play took part (a warp of steep rays
-//     that reflect together) the next wait is `park_wait_long`, otherwise `park_wait` (mixed warps, where parked lanes
-//     would idle while their neighbours step on)
+//   * the wait adapts: after a pass in which at least three quarters of the lanes still in play took part (a warp of
+//     steep rays that reflect together) the next wait is `park_wait_long`, otherwise `park_wait` (mixed warps, where
+//     parked lanes would idle while their neighbours step on).  Measured (profiles/r02_variants.md): half -> +2.2 % on
+//     the config-5 ensemble, three quarters -> +1.3 %, all lanes -> 0 % but the steep fans lose most of their -32 %.
 template <bool SAVE, bool COUNT>
 __device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SAVE, COUNT>& r, const prt_shot& S,
                                                    const prt_traj_sink& sink, int park_wait, int park_wait_long,
-                                                   const prt_park_slot& park)
+                                                   const prt_park_slot& park, int park_long_num = 3)
 {
     const unsigned full = 0xffffffffu;
     int waited = 0, limit = park_wait;
@@ -188,7 +189,7 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SA
             const unsigned stepping = __ballot_sync(full, r.phase == PRT_PH_STEP);
             ++waited;
             if (!stepping || waited > limit) {
-                limit = (2 * __popc(parked) >= __popc(parked | stepping)) ? park_wait_long : park_wait;
+                limit = (4 * __popc(parked) >= park_long_num * __popc(parked | stepping)) ? park_wait_long : park_wait;
                 if (r.phase == PRT_PH_ROOT) {
                     prt_step st;
                     park.rebuild(E, S, r, st);
@@ -201,10 +202,10 @@ __device__ __forceinline__ void prt_integrate_warp(const prt_envp& E, prt_ray<SA
     }
 }
 
-// Resident blocks of 128 threads per SM.  Trajectory-saving kernels: 4 (128 registers per thread; measured on B200,
-// 1M-ray fan: 3 blocks / 142 regs 160 ms, 4 blocks 100 ms).  Arrival-table kernels keep no stage values across the
-// trial step (prt_rk_try) and fit 5 blocks (102 registers): the ray ODE is one long dependent FP64 chain, so the
-// FP64 pipe is fed by resident warps, not by ILP (profiles/r02_variants.md).
+// Resident blocks of 128 threads per SM: 4 for every kernel (128 registers per thread; measured on B200, 1M-ray fan:
+// 3 blocks / 142 regs 160 ms, 4 blocks 100 ms).  The arrival-table kernels keep no stage values across the trial step
+// (prt_rk_try) and would fit a fifth block at 96 registers, but that build spills and puts 25 % more scattered loads on
+// the L1 data pipe: 12-16 % SLOWER, measured twice (profiles/r02_variants.md sections 1 and 5c).
 #ifndef PRT_MIN_BLOCKS
 #define PRT_MIN_BLOCKS 4
 #endif
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(SAVE ? PRT_BLOCK : PRT_BLOCK_ARR, SAVE ? PRT_M
     prt_ray<SAVE, COUNT> r;
     r.start(T, z, p, P.source_range, S);
     if (!live) r.phase = PRT_PH_DONE;
-    prt_integrate_warp(E, r, S, sink, P.park_wait, P.park_wait_long, park);
+    prt_integrate_warp(E, r, S, sink, P.park_wait, P.park_wait_long, park, P.park_long_num);
     if (!live) return;
     prt_ray_result res;
     uint32_t cnt[PRT_CNT_N];
@@ -1141,13 +1142,21 @@ static int shoot_fan_impl(const prt_env_t* env, int64_t n_rays, int64_t rays_per
     P.park_wait = park_wait_setting();
     {
         // wait of warps whose lanes reflect together (PRT_PARK_WAIT_LONG, default 128; < 0: same as park_wait).
-        // Measured (profiles/r02_variants.md): a +-40 deg 10k-ray fan 26.9 -> 18.3 ms, everything else within 1 %.
+        // Measured (profiles/r02_variants.md): a +-40 deg 10k-ray fan 26.9 -> 18.3 ms, the config-5 ensemble +1.3 %,
+        // everything else within 0.5 %.
         static int lw = -2;
         if (lw == -2) {
             const char* e = getenv("PRT_PARK_WAIT_LONG");
             lw = e ? atoi(e) : 128;
         }
         P.park_wait_long = lw >= 0 ? lw : P.park_wait;
+        static int num = -1;  // quarters of the lanes in play that must have taken part (PRT_PARK_LONG_NUM, 1..4)
+        if (num < 0) {
+            const char* e = getenv("PRT_PARK_LONG_NUM");
+            num = e ? atoi(e) : 3;
+            if (num < 1 || num > 4) num = 3;
+        }
+        P.park_long_num = num;
     }
     P.rays_per_env = rays_per_env;
     {
