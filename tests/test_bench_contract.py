@@ -58,3 +58,21 @@ def test_stdout_is_reserved_for_the_json_line():
     assert p.returncode == 0, p.stderr[-2000:]
     assert p.stdout == '{"a": 1}\n'
     assert "NCCL version x.y" in p.stderr and "stray print" in p.stderr
+
+
+def test_reference_arm_under_torchrun_only_rank_zero_works():
+    """N > 1: the driver launches the reference arm under torchrun as well; rank 0 alone runs and prints, the other ranks
+    exit 0 at once with nothing on stdout."""
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29999")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert p.returncode == 0 and p.stdout == "", (p.stdout[:200], p.stderr[-500:])
+    env["RANK"] = env["LOCAL_RANK"] = "0"
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload",
+                        "cfg2", "--steps", "1", "--warmup", "1", "--ref-rays", "64", "--no-python-ref"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = p.stdout.splitlines()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["config"]["n_gpus"] == 2
