@@ -174,6 +174,25 @@ def case_fuzz_short():
     save("ref_fuzz_short", **out)
 
 
+def case_fuzz_smooth():
+    """24 random smooth environments on 1-2 m depth grids (tests/fuzz_cases.py: smooth_case): the regime in which the
+    reference reproduces itself, with reflections off sloping / undulating bottoms."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fuzz_cases import smooth_case
+
+    out = {}
+    for seed in range(24):
+        k = smooth_case(seed)
+        a = k["arrays"]
+        ssp = xr.DataArray(a["c"], dims=["range", "depth"], coords={"range": a["r"], "depth": a["z"]})
+        bathy = xr.DataArray(a["bathy"], dims=["range"], coords={"range": a["bathy_r"]})
+        env = OceanEnvironment2D(sound_speed=ssp, bathymetry=bathy, lat=k["lat"], flat_earth_transform=k["flat"])
+        al = array_level(env, k["flat"], k["zs"], k["r0"], k["r1"], k["angles"], k["n_save"], rtol=k["rtol"],
+                         terminate_backwards=k["terminate_backwards"])
+        out.update({f"s{seed}_" + kk: v for kk, v in al.items()})
+    save("ref_fuzz_smooth", **out)
+
+
 def case_bounce_fine():
     """Default 1 m grid env, steep rays that bounce (stable-step regime with reflections)."""
     env = OceanEnvironment2D()
@@ -339,9 +358,9 @@ def case_flatearth():
 CASES = dict(cfg1=case_cfg1, fixture=case_fixture, cfg2_sub=case_cfg2_sub, bounce_fine=case_bounce_fine,
              physics=case_physics, eigen=case_eigen, cfg3_sub=case_cfg3_sub,
              cfg4_sub=case_cfg4_sub, flatearth=case_flatearth, cfg5_sub=case_cfg5_sub,
-             fuzz_short=case_fuzz_short)
+             fuzz_short=case_fuzz_short, fuzz_smooth=case_fuzz_smooth)
 # cases re-run without the JIT to measure the reference's own self-consistency envelope
-NOJIT_CASES = ("cfg1", "cfg2_sub", "bounce_fine", "cfg3_sub", "cfg4_sub", "cfg5_sub", "fuzz_short")
+NOJIT_CASES = ("cfg1", "cfg2_sub", "bounce_fine", "cfg3_sub", "cfg4_sub", "cfg5_sub", "fuzz_short", "fuzz_smooth")
 
 if __name__ == "__main__":
     want = sys.argv[1:] or list(CASES)

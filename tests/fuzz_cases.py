@@ -58,3 +58,32 @@ def short_case(seed):
     k["angles"] = ang[np.abs(ang) <= 30.0][:8] if (np.abs(ang) <= 30.0).any() else np.clip(ang[:4], -30.0, 30.0)
     k["n_save"] = 17
     return k
+
+
+def smooth_case(seed):
+    """Random SMOOTH environments on 1-2 m depth grids (the regime in which the reference reproduces itself to ~1e-9, so
+    the north-star tolerances can be checked directly): range-dependent Munk axis, a smooth range-dependent perturbation,
+    sloping / undulating bathymetry (exercises the bottom-angle spline and the reflection law), flat-earth on / off,
+    10-40 km, launch angles up to +-25 deg.  Used by oracle/make_golden.py: case_fuzz_smooth and the tests."""
+    rng = np.random.default_rng(5000 + seed)
+    n_r = int(rng.integers(5, 40))
+    R = float(rng.uniform(1e4, 4e4))
+    zmax = float(rng.uniform(3000, 6000))
+    dz = float(rng.choice([1.0, 2.0]))
+    z = np.arange(0.0, zmax, dz)
+    r = np.linspace(0.0, R, n_r)
+    axis, drift = rng.uniform(700, 1500), rng.uniform(-150, 150)
+    amp, L, zs_scale = rng.uniform(0.0, 1.5), rng.uniform(0.5, 3.0) * R, rng.uniform(400, 1200)
+    c = np.array([cases.munk_ssp(z, axis + drift * ri / R) + amp * np.sin(2 * np.pi * ri / L) * np.exp(-z / zs_scale)
+                  for ri in r])
+    n_b = int(rng.integers(5, 30))
+    bathy_r = np.linspace(0.0, R, n_b)
+    d0 = rng.uniform(0.45, 0.9) * z[-1]
+    bathy = d0 + rng.uniform(-0.08, 0.08) * z[-1] * bathy_r / R \
+        + rng.uniform(0, 0.04) * z[-1] * np.sin(np.linspace(0, rng.uniform(1, 7), n_b))
+    bathy = np.minimum(bathy, z[-1] - 10.0)
+    arrays = dict(c=c, r=r, z=z, bathy=bathy, bathy_r=bathy_r)
+    zs = float(rng.uniform(50, 0.8 * bathy.min()))
+    angles = np.sort(rng.uniform(-25.0, 25.0, 8))
+    return dict(arrays=arrays, flat=bool(rng.random() < 0.4), zs=zs, r0=0.0, r1=R, angles=angles, n_save=17,
+                rtol=float(rng.choice([1e-9, 1e-10])), terminate_backwards=True, lat=float(rng.uniform(-60, 60)))

@@ -165,16 +165,17 @@ def test_backwards_mirrored_environment(harness):
 
 
 def test_reference_pinned_random_environments(harness):
-    """The 40 short random environments of the reference comparison (fuzz_cases.short_case): product core == oracle."""
-    from fuzz_cases import short_case
+    """The 40 short and 24 smooth random environments of the reference comparison (fuzz_cases.short_case /
+    smooth_case): product core == oracle."""
+    from fuzz_cases import short_case, smooth_case
 
-    for seed in range(40):
-        k = short_case(seed)
+    todo = [("short", s, short_case(s)) for s in range(40)] + [("smooth", s, smooth_case(s)) for s in range(24)]
+    for tag, seed, k in todo:
         env = make_env(k["arrays"], flat=k["flat"], lat=k["lat"])
         oenv = oracle_env_from(env, k["flat"])
         o, h = _both(harness, oenv, k["zs"], k["r0"], k["r1"], k["angles"], k["n_save"], rtol=k["rtol"],
                      terminate_backwards=k["terminate_backwards"])
-        assert_same_fan(o, h, f"short fuzz seed {seed}")
+        assert_same_fan(o, h, f"{tag} fuzz seed {seed}")
 
 
 @pytest.mark.parametrize("seed", range(40))

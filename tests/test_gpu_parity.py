@@ -325,20 +325,24 @@ def test_fuzz_random_environments_gpu(pr, seed):
 
 
 def test_reference_pinned_random_environments_gpu(pr):
-    """The 40 short random environments on which the oracle is compared with the unmodified reference ray by ray
-    (tests/test_oracle_vs_reference.py::test_random_short_range_environments_against_reference): libprt.so == oracle,
-    bit for bit, on exactly those inputs -- and kept / dropped and bounce counts == the reference's."""
-    from fuzz_cases import short_case
+    """The 40 short and 24 smooth random environments on which the oracle is compared with the unmodified reference ray
+    by ray (tests/test_oracle_vs_reference.py::test_random_*): libprt.so == oracle, bit for bit, on exactly those
+    inputs -- and kept / dropped and bounce counts == the reference's."""
+    from fuzz_cases import short_case, smooth_case
 
-    g = golden("ref_fuzz_short_jit.npz")
-    for seed in range(40):
-        k = short_case(seed)
+    for tag, gen, n in (("short", short_case, 40), ("smooth", smooth_case, 24)):
+        _reference_pinned_cases(pr, golden(f"ref_fuzz_{tag}_jit.npz"), gen, n)
+
+
+def _reference_pinned_cases(pr, g, gen, n_seeds):
+    for seed in range(n_seeds):
+        k = gen(seed)
         env = make_env(k["arrays"], flat=k["flat"], lat=k["lat"])
         d = _gpu_fan(pr, env, k["flat"], k["zs"], k["r0"], k["r1"], k["angles"], k["n_save"], rtol=k["rtol"],
                      terminate_backwards=k["terminate_backwards"])
         o = _oracle_fan(env, k["flat"], k["zs"], k["r0"], k["r1"], k["angles"], k["n_save"], rtol=k["rtol"],
                         terminate_backwards=k["terminate_backwards"])
-        assert_same_fan(o, d, f"short fuzz seed {seed}")
+        assert_same_fan(o, d, f"reference-pinned fuzz seed {seed}")
         P = f"s{seed}_"
         m = g[P + "ok"]
         assert np.array_equal(d["status"] == 0, m), seed

@@ -233,6 +233,50 @@ def test_random_short_range_environments_against_reference():
             assert max(stat(d_oj[:, comp]), stat(d_on[:, comp])) <= lim, (name, stat(d_oj[:, comp]), stat(d_on[:, comp]), lim)
 
 
+def test_random_smooth_environments_meet_north_star_tolerances():
+    """24 random SMOOTH environments on 1-2 m depth grids (tests/fuzz_cases.py: smooth_case -- range-dependent Munk axis,
+    smooth perturbation, sloping / undulating bottom, flat-earth on / off, 10-40 km, +-25 deg), 192 rays with 0-9
+    reflections.  This is the regime in which the reference reproduces itself, so the north-star tolerances are checked
+    DIRECTLY: every ray kept, both bounce counts identical on every ray, arrival time / depth / angle of every ray with
+    at most one reflection within 1e-6 s / 1e-3 m / 1e-6 rad of BOTH reference variants (whole trajectory for the
+    bounce-free ones); rays with two or more reflections within 2x of the variants' own spread."""
+    from fuzz_cases import smooth_case
+
+    g, gn = golden("ref_fuzz_smooth_jit.npz"), golden("ref_fuzz_smooth_nojit.npz")
+    few, many = [], []
+    for seed in range(24):
+        k = smooth_case(seed)
+        oenv = oracle_env_from(make_env(k["arrays"], flat=k["flat"], lat=k["lat"]), k["flat"])
+        P = f"s{seed}_"
+        assert np.array_equal(g[P + "internal_angles"], k["angles"])
+        o = orc.shoot_fan(oenv, k["zs"], k["r0"], k["r1"], angles_deg=k["angles"], range_save=g[P + "range_save"],
+                          rtol=k["rtol"], terminate_backwards=True)
+        assert g[P + "ok"].all() and gn[P + "ok"].all() and (o["status"] == 0).all(), seed
+        for key in ("n_bottom", "n_surface"):
+            assert np.array_equal(g[P + key], gn[P + key]) and np.array_equal(o[key], g[P + key]), (seed, key)
+        nb = g[P + "n_bottom"] + g[P + "n_surface"]
+        free = nb == 0
+        assert np.array_equal(o["counters"][free, 0], g[P + "nfev"][free]), seed  # identical solver work, ray by ray
+        c_end = 1500.0  # p c = sin(theta): |d theta| <= |d p| c / cos(theta), cos >= 0.9 here
+        for ref in (g, gn):
+            d = np.abs(o["traj"] - ref[P + "traj"])[free]
+            if free.any():
+                assert d[:, 0].max() < 1e-7 < TOL_T and d[:, 1].max() < 1e-4 < TOL_Z, seed       # measured 2.4e-8 s, 5.6e-5 m
+                assert (d[:, 2] * c_end / 0.9).max() < 1e-7 < TOL_ANGLE, seed
+        a = np.maximum(np.abs(o["final"] - g[P + "final"]), np.abs(o["final"] - gn[P + "final"]))
+        b = np.abs(g[P + "final"] - gn[P + "final"])
+        few.append(a[nb <= 1])
+        many.append((np.abs(o["final"] - g[P + "final"])[nb >= 2], np.abs(o["final"] - gn[P + "final"])[nb >= 2], b[nb >= 2]))
+    few = np.concatenate(few)
+    assert len(few) == 108
+    assert few[:, 0].max() < TOL_T and few[:, 1].max() < TOL_Z and (few[:, 2] * 1500.0 / 0.9).max() < TOL_ANGLE  # 5.2e-8 s, 2.0e-4 m
+    d_oj, d_on, d_jn = (np.concatenate([m[i] for m in many]) for i in range(3))
+    assert len(d_jn) == 84
+    for comp in (0, 1):  # the three-way criterion of _envelope_check
+        for stat in (np.median, lambda v: np.percentile(v, 90), np.max):
+            assert max(stat(d_oj[:, comp]), stat(d_on[:, comp])) <= 2.0 * stat(d_jn[:, comp]), (comp, stat(d_oj[:, comp]), stat(d_on[:, comp]), stat(d_jn[:, comp]))
+
+
 def test_reflections_on_fine_grid_within_reference_envelope():
     import pygenray_b200 as pr
 

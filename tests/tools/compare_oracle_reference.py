@@ -102,9 +102,35 @@ def fuzz_short():
     _three_lines("random short-range environments", O, G, N)
 
 
+def fuzz_smooth():
+    from fuzz_cases import smooth_case
+
+    g, gn = golden("ref_fuzz_smooth_jit.npz"), golden("ref_fuzz_smooth_nojit.npz")
+    rows = {}
+    n = counts_equal = nfev_equal = 0
+    for seed in range(24):
+        k = smooth_case(seed)
+        oenv = oracle_env_from(make_env(k["arrays"], flat=k["flat"], lat=k["lat"]), k["flat"])
+        P = f"s{seed}_"
+        o = orc.shoot_fan(oenv, k["zs"], k["r0"], k["r1"], angles_deg=k["angles"], range_save=g[P + "range_save"], rtol=k["rtol"],
+                          terminate_backwards=True)
+        nb = g[P + "n_bottom"] + g[P + "n_surface"]
+        n += len(nb)
+        counts_equal += int(((o["n_bottom"] == g[P + "n_bottom"]) & (o["n_surface"] == g[P + "n_surface"])).sum())
+        nfev_equal += int((o["counters"][:, 0] == g[P + "nfev"])[nb == 0].sum())
+        for i, b in enumerate(nb):
+            rows.setdefault(min(int(b), 6), []).append((o["final"][i], g[P + "final"][i], gn[P + "final"][i]))
+    print(f"== 24 random smooth environments: {n} rays, all kept, bounce counts equal on {counts_equal}, RHS evaluations equal on "
+          f"{nfev_equal} of {len(rows[0])} bounce-free rays")
+    for b in sorted(rows):
+        O, G, N = (np.array([r[i] for r in rows[b]]) for i in range(3))
+        _three_lines(f"{b}{'+' if b == 6 else ''} reflections ({len(O)} rays)", O, G, N)
+
+
 if __name__ == "__main__":
     three_way("ref_cfg2_sub", make_env(cases.config2_arrays()), 1000.0, 500e3)
     three_way("ref_cfg3_sub", make_env(cases.config3_arrays()), 1000.0, 1000e3)
     config4()
     config5()
     fuzz_short()
+    fuzz_smooth()
