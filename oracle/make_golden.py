@@ -277,6 +277,39 @@ def case_eigen():
     save("ref_eigen", **out)
 
 
+def case_eigen_smooth():
+    """The reference's public shoot_rays + find_eigenrays on 6 random smooth environments (tests/fuzz_cases.py:
+    smooth_case): 81-ray fan +-20 deg, two receiver depths, ztol 1e-3 -- eigenrays with 0-5 reflections off sloping bottoms,
+    flat-earth on / off."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fuzz_cases import smooth_case
+
+    out = {}
+    for seed in range(6):
+        k = smooth_case(seed)
+        a = k["arrays"]
+        ssp = xr.DataArray(a["c"], dims=["range", "depth"], coords={"range": a["r"], "depth": a["z"]})
+        bathy = xr.DataArray(a["bathy"], dims=["range"], coords={"range": a["bathy_r"]})
+        env = OceanEnvironment2D(sound_speed=ssp, bathymetry=bathy, lat=k["lat"], flat_earth_transform=k["flat"])
+        angles = np.linspace(-20, 20, 81)
+        rf = pr.shoot_rays(k["zs"], 0.0, angles, k["r1"], 33, env, rtol=k["rtol"], n_processes=8, debug=False,
+                           flatearth=k["flat"])
+        d0 = float(a["bathy"].min())
+        rds = [round(0.3 * d0, 1), round(0.6 * d0, 1)]
+        er = pr.find_eigenrays(rf, rds, k["zs"], 0.0, k["r1"], 33, env, ztol=1e-3, max_iter=20, num_workers=8, debug=False,
+                               rtol=k["rtol"], flatearth=k["flat"])
+        P = f"s{seed}_"
+        out.update({P + kk: v for kk, v in fan_dict(rf).items()})
+        out[P + "receiver_depths"] = np.array(rds)
+        for i in range(len(rds)):
+            out[P + f"e{i}_ts"] = er.ts[i]; out[P + f"e{i}_zs"] = er.zs[i]; out[P + f"e{i}_rs"] = er.rs[i]
+            out[P + f"e{i}_launch"] = er.launch_angles[i]; out[P + f"e{i}_recv"] = er.received_angles[i]
+            out[P + f"e{i}_ray_id_int"] = er.ray_id_int[i]
+            out[P + f"e{i}_nb"] = er.n_botts[i]; out[P + f"e{i}_ns"] = er.n_surfs[i]
+            out[P + f"e{i}_num"] = np.array(er.num_eigenrays[rds[i]]); out[P + f"e{i}_found"] = np.array(er.num_eigenrays_found[i])
+    save("ref_eigen_smooth", **out)
+
+
 def case_cfg3_sub():
     """BASELINE config 3 sub-sample: Munk + internal waves on the 2001 x 1201 grid, 1000 km; 64 rays of the
     1 048 576-ray fan linspace(-15, 15, 1 << 20) (evenly spread ray indices, both ends included)."""
@@ -358,7 +391,8 @@ def case_flatearth():
 CASES = dict(cfg1=case_cfg1, fixture=case_fixture, cfg2_sub=case_cfg2_sub, bounce_fine=case_bounce_fine,
              physics=case_physics, eigen=case_eigen, cfg3_sub=case_cfg3_sub,
              cfg4_sub=case_cfg4_sub, flatearth=case_flatearth, cfg5_sub=case_cfg5_sub,
-             fuzz_short=case_fuzz_short, fuzz_smooth=case_fuzz_smooth)
+             fuzz_short=case_fuzz_short, fuzz_smooth=case_fuzz_smooth,
+             eigen_smooth=case_eigen_smooth)
 # cases re-run without the JIT to measure the reference's own self-consistency envelope
 NOJIT_CASES = ("cfg1", "cfg2_sub", "bounce_fine", "cfg3_sub", "cfg4_sub", "cfg5_sub", "fuzz_short", "fuzz_smooth")
 

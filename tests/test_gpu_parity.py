@@ -214,6 +214,40 @@ def test_find_eigenrays_against_reference(pr):
         assert np.array_equal(er.rs[i], g[f"e{i}_rs"])
 
 
+def test_find_eigenrays_on_random_smooth_environments_against_reference(pr):
+    """The public shoot_rays + find_eigenrays of the product against the reference's on 6 random smooth environments
+    (oracle/make_golden.py: case_eigen_smooth; sloping bottoms, flat-earth on / off, eigenrays with 0-4 reflections):
+    same fan, same brackets, same converged set, launch / received angles within 1e-6 rad, arrival times within 1e-6 s,
+    ray ids and bounce counts identical."""
+    from fuzz_cases import smooth_case
+
+    g = golden("ref_eigen_smooth_jit.npz")
+    n_found = 0
+    for seed in range(6):
+        k = smooth_case(seed)
+        env = make_env(k["arrays"], flat=k["flat"], lat=k["lat"])
+        P = f"s{seed}_"
+        fan = pr.shoot_rays(k["zs"], 0.0, np.linspace(-20, 20, 81), k["r1"], 33, env, rtol=k["rtol"], debug=False,
+                            flatearth=k["flat"])
+        assert np.array_equal(fan.thetas, g[P + "fan_thetas"]) and np.array_equal(fan.n_botts, g[P + "fan_n_botts"])
+        assert np.array_equal(fan.n_surfs, g[P + "fan_n_surfs"]) and np.array_equal(fan.ray_ids, g[P + "fan_ray_ids"])
+        rds = [float(v) for v in g[P + "receiver_depths"]]
+        er = pr.find_eigenrays(fan, rds, k["zs"], 0.0, k["r1"], 33, env, ztol=1e-3, max_iter=20, debug=False,
+                               rtol=k["rtol"], flatearth=k["flat"])
+        for i, rd in enumerate(rds):
+            e = P + f"e{i}_"
+            assert er.num_eigenrays[rd] == int(g[e + "num"]) and er.num_eigenrays_found[i] == int(g[e + "found"]), (seed, rd)
+            n_found += er.num_eigenrays_found[i]
+            assert np.abs(np.radians(er.launch_angles[i] - g[e + "launch"])).max() < 1e-6
+            assert np.abs(np.radians(er.received_angles[i] - g[e + "recv"])).max() < 1e-6
+            assert np.abs(er.ts[i][:, -1] - g[e + "ts"][:, -1]).max() < 1e-6
+            assert np.abs(er.zs[i][:, -1] + rd).max() < 1e-3
+            assert np.array_equal(er.ray_id_int[i], g[e + "ray_id_int"])
+            assert np.array_equal(er.n_botts[i], g[e + "nb"]) and np.array_equal(er.n_surfs[i], g[e + "ns"])
+            assert np.array_equal(er.rs[i], g[e + "rs"])
+    assert n_found == 54
+
+
 def test_eigenray_refinement_bit_identical_to_oracle(pr):
     """Brackets over 16 receiver depths on the range-dependent grid; device regula falsi == oracle."""
     env = make_env(cases.config2_arrays())

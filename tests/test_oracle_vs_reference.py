@@ -409,6 +409,41 @@ def test_eigenrays_against_reference_find_eigenrays():
         assert np.abs(-o["traj"][:, 1] - g[f"e{i}_zs"]).max() < 2e-3  # both sides converged to ztol = 1e-3
 
 
+def test_eigenrays_on_random_smooth_environments_against_reference():
+    """The reference's public shoot_rays + find_eigenrays on 6 random smooth environments (case_eigen_smooth: sloping
+    bottoms, flat-earth on / off, 81-ray fans, two receiver depths, ztol 1e-3): the oracle finds the same brackets,
+    converges on the same ones, and its eigenrays (0-4 reflections) agree to 1e-9 rad / 1e-7 s -- three orders inside
+    the north-star tolerances -- with identical bounce counts."""
+    from fuzz_cases import smooth_case
+
+    g = golden("ref_eigen_smooth_jit.npz")
+    n_found = 0
+    for seed in range(6):
+        k = smooth_case(seed)
+        oenv = oracle_env_from(make_env(k["arrays"], flat=k["flat"], lat=k["lat"]), k["flat"])
+        P = f"s{seed}_"
+        zs_end, thetas = g[P + "fan_zs"][:, -1], g[P + "fan_thetas"]
+        # the fan itself (public API of the reference, pool branch: stored theta = user angle)
+        o = orc.shoot_fan(oenv, k["zs"], 0.0, k["r1"], angles_deg=-np.linspace(-20, 20, 81), rtol=k["rtol"])
+        kept = o["status"] == 0
+        assert np.array_equal(np.linspace(-20, 20, 81)[kept], thetas)
+        assert np.array_equal(o["n_bottom"][kept], g[P + "fan_n_botts"]) and np.array_equal(o["n_surface"][kept], g[P + "fan_n_surfs"])
+        for i, rd in enumerate(g[P + "receiver_depths"]):
+            e = P + f"e{i}_"
+            kk = np.where(np.diff(np.sign(zs_end + rd)))[0]
+            assert len(kk) == int(g[e + "num"])
+            ref = orc.refine_brackets(oenv, zs_end[kk], zs_end[kk + 1], thetas[kk], thetas[kk + 1], np.full(len(kk), rd),
+                                      k["zs"], 0.0, k["r1"], ztol=1e-3, max_iter=20, rtol=k["rtol"])
+            conv = ref["status"] == 0
+            assert conv.sum() == int(g[e + "found"]), (seed, rd)
+            n_found += int(conv.sum())
+            assert np.abs(np.radians(ref["theta"][conv] - g[e + "launch"])).max() < 1e-9 < TOL_ANGLE   # measured 5.2e-10
+            assert np.abs(ref["final"][conv, 0] - g[e + "ts"][:, -1]).max() < 1e-7 < TOL_T             # measured 1.8e-8
+            assert np.abs(-ref["final"][conv, 1] + rd).max() < 1e-3
+            assert np.array_equal(ref["n_bottom"][conv], g[e + "nb"]) and np.array_equal(ref["n_surface"][conv], g[e + "ns"])
+    assert n_found == 54
+
+
 # ---- BASELINE configs 3 and 4: 1000 km through the internal-wave field (2001 x 1201 grid) ---------------------
 def _three_way(o, a, b, rows, comp):
     """Distances oracle-jit, oracle-nojit and jit-nojit of one arrival component over `rows`."""
