@@ -310,6 +310,34 @@ def case_eigen_smooth():
     save("ref_eigen_smooth", **out)
 
 
+def case_backwards_smooth():
+    """The reference's public shoot_ray (single-ray branch: sign flip, backwards mirroring, stored conventions) on 6
+    random smooth environments (tests/fuzz_cases.py: smooth_case, seeds 6-11): 5 launch angles each, BACKWARDS from the far
+    end of the track to 10 % of it, with flat-earth on / off; the first and last environment also with
+    terminate_backwards=False."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fuzz_cases import smooth_case
+
+    out = {}
+    for seed in range(6, 12):
+        k = smooth_case(seed)
+        a = k["arrays"]
+        ssp = xr.DataArray(a["c"], dims=["range", "depth"], coords={"range": a["r"], "depth": a["z"]})
+        bathy = xr.DataArray(a["bathy"], dims=["range"], coords={"range": a["bathy_r"]})
+        env = OceanEnvironment2D(sound_speed=ssp, bathymetry=bathy, lat=k["lat"], flat_earth_transform=k["flat"])
+        tb = seed not in (6, 11)
+        for j, ang in enumerate((-15.0, -7.0, 0.0, 7.0, 15.0)):
+            ray = pr.shoot_ray(k["zs"], k["r1"], ang, 0.1 * k["r1"], 25, env, rtol=k["rtol"], terminate_backwards=tb,
+                               flatearth=k["flat"], debug=False)
+            tag = f"s{seed}_a{j}"
+            out[tag + "_none"] = np.array(ray is None)
+            if ray is not None:
+                out[tag + "_r"] = ray.r; out[tag + "_t"] = ray.t; out[tag + "_z"] = ray.z; out[tag + "_p"] = ray.p
+                out[tag + "_nb"] = np.array(ray.n_bottom); out[tag + "_ns"] = np.array(ray.n_surface)
+                out[tag + "_la"] = np.array(ray.launch_angle)
+    save("ref_backwards_smooth", **out)
+
+
 def case_cfg3_sub():
     """BASELINE config 3 sub-sample: Munk + internal waves on the 2001 x 1201 grid, 1000 km; 64 rays of the
     1 048 576-ray fan linspace(-15, 15, 1 << 20) (evenly spread ray indices, both ends included)."""
@@ -392,9 +420,9 @@ CASES = dict(cfg1=case_cfg1, fixture=case_fixture, cfg2_sub=case_cfg2_sub, bounc
              physics=case_physics, eigen=case_eigen, cfg3_sub=case_cfg3_sub,
              cfg4_sub=case_cfg4_sub, flatearth=case_flatearth, cfg5_sub=case_cfg5_sub,
              fuzz_short=case_fuzz_short, fuzz_smooth=case_fuzz_smooth,
-             eigen_smooth=case_eigen_smooth)
+             eigen_smooth=case_eigen_smooth, backwards_smooth=case_backwards_smooth)
 # cases re-run without the JIT to measure the reference's own self-consistency envelope
-NOJIT_CASES = ("cfg1", "cfg2_sub", "bounce_fine", "cfg3_sub", "cfg4_sub", "cfg5_sub", "fuzz_short", "fuzz_smooth")
+NOJIT_CASES = ("cfg1", "cfg2_sub", "bounce_fine", "cfg3_sub", "cfg4_sub", "cfg5_sub", "fuzz_short", "fuzz_smooth", "backwards_smooth")
 
 if __name__ == "__main__":
     want = sys.argv[1:] or list(CASES)
