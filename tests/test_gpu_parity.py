@@ -197,6 +197,32 @@ def test_shoot_ray_conventions_and_drops(pr):
         pr.shoot_ray(200.0, 0.0, -10.0, 1e4, 10, bad, flatearth=False)
 
 
+def test_backwards_shoot_ray_on_random_smooth_environments_against_reference(pr):
+    """The public shoot_ray of the product, BACKWARDS, against the reference's on 6 random smooth environments
+    (oracle/make_golden.py: case_backwards_smooth; flat-earth on / off, terminate_backwards on / off): stored launch
+    angle, range grid and bounce counts exact, arrival within the north-star tolerances."""
+    from fuzz_cases import smooth_case
+
+    g = golden("ref_backwards_smooth_jit.npz")
+    n = 0
+    for seed in range(6, 12):
+        k = smooth_case(seed)
+        env = make_env(k["arrays"], flat=k["flat"], lat=k["lat"])
+        for j, ang in enumerate((-15.0, -7.0, 0.0, 7.0, 15.0)):
+            ray = pr.shoot_ray(k["zs"], k["r1"], ang, 0.1 * k["r1"], 25, env, rtol=k["rtol"], flatearth=k["flat"],
+                               terminate_backwards=seed not in (6, 11), debug=False)
+            tag = f"s{seed}_a{j}"
+            assert (ray is None) == bool(g[tag + "_none"]), tag
+            if ray is None:
+                continue
+            n += 1
+            assert ray.launch_angle == float(g[tag + "_la"]) and np.array_equal(ray.r, g[tag + "_r"]), tag
+            assert ray.n_bottom == int(g[tag + "_nb"]) and ray.n_surface == int(g[tag + "_ns"]), tag
+            assert abs(ray.t[-1] - g[tag + "_t"][-1]) < 1e-6 and abs(ray.z[-1] - g[tag + "_z"][-1]) < 1e-3, tag
+            assert abs(ray.p[-1] - g[tag + "_p"][-1]) * 1500.0 < 1e-6, tag
+    assert n == 30
+
+
 def test_find_eigenrays_against_reference(pr):
     g = golden("ref_eigen_jit.npz")
     env = pr.OceanEnvironment2D()
